@@ -1,0 +1,50 @@
+"""Pin oracle/mopg_oracle.py (float64 numpy restatement) against outputs of the
+unmodified reference stored in tests/golden/mopg_*.npz (made by make_golden_mopg.py)."""
+import numpy as np
+import pytest
+
+from oracle import mopg_oracle as orc
+from pgmorl_b200 import synthetic
+from tests.helpers import load_mopg_case, rel_err, task_traj
+
+CASES = ["mopg_walker_small.npz", "mopg_hopper3_small.npz", "mopg_humanoid_small.npz"]
+
+
+def run_case(name, tasks=None, tol=1e-9):
+    z, meta = load_mopg_case(name)
+    d = meta["dims"]
+    dims = (d.obs, d.act, d.obj)
+    for task in (tasks if tasks is not None else range(meta["n_tasks"])):
+        flat = z[f"t{task}_init"].copy()
+        # product-side init reproduces the reference's Policy init (LAPACK QR may differ by an
+        # ulp with thread count / CPU, hence a tolerance instead of array_equal)
+        assert rel_err(synthetic.init_policy_flat(d, seed=1000 + task).numpy(), flat) < 1e-14
+        m = np.zeros_like(flat); v = np.zeros_like(flat); step = 0
+        for k, j in enumerate(meta["iters"]):
+            traj = task_traj(meta, j, task)
+            eps, perm = synthetic.host_rng_streams(j, meta["T"], meta["N"], d.act, meta["E"])
+            lr = synthetic.linear_lr(3e-4, j, 1.0, meta["total_num_updates"])
+            out = orc.mopg_iteration(flat, m, v, step, lr, dims, traj, eps.numpy(), perm.numpy(),
+                                     z[f"t{task}_weights"], z[f"t{task}_obj_var"],
+                                     gamma=meta["gamma"], lam=meta["lam"], num_mini_batch=meta["B"])
+            step = out["step"]
+            pre = f"t{task}_i{k}_"
+            assert abs(lr - float(z[pre + "lr"])) < 1e-18
+            assert step == int(z[pre + "adam_step"])
+            for key in ("value", "action", "logp", "returns", "adv"):
+                if pre + key in z:
+                    assert rel_err(out[key], z[pre + key]) < 1e-12, key
+            assert rel_err(out["losses"], z[pre + "losses"]) < tol
+            assert rel_err(flat, z[pre + "params"]) < tol
+            assert rel_err(m, z[pre + "adam_m"]) < tol
+            assert rel_err(v, z[pre + "adam_v"]) < tol
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_small(name):
+    run_case(name)
+
+
+def test_oracle_matches_reference_full_c2():
+    # full HalfCheetah-shape iteration (320 Adam steps on 8192 samples), one task
+    run_case("mopg_halfcheetah_full.npz", tasks=[1], tol=1e-8)
