@@ -1,0 +1,125 @@
+"""Torch-tensor level launchers over the C ABI. PyTorch only owns memory and streams here;
+all arithmetic runs in the hand-written sm_100a kernels of libpgmorl_b200.so."""
+import ctypes as C
+
+import torch
+
+from ._lib import PpoHyper, check, lib, ptr
+from .layout import NetDims
+
+ACT_SAMPLE, ACT_DETERMINISTIC, ACT_EVALUATE = 0, 1, 2
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous float32 CUDA tensor, got {t.dtype} {t.device} "
+                         f"contiguous={t.is_contiguous()}")
+    return t
+
+
+def policy_forward(params, obs, dims: NetDims, eps=None, action=None, mode=ACT_SAMPLE, rows_a=None,
+                   out=None):
+    """K1. params [P,n_par]; obs [P,rows_v,O]; eps [P or 1,rows_a,A] (SAMPLE);
+    action [P,rows_a,A] given for EVALUATE. Returns (value [P,rows_v,M], action, logp [P,rows_a])."""
+    _f32c(params, "params"); _f32c(obs, "obs"); _f32c(eps, "eps")
+    P, rows_v, O = obs.shape
+    assert O == dims.obs and params.shape == (P, dims.n_par)
+    if rows_a is None:
+        rows_a = rows_v
+    dev = obs.device
+    if out is not None:
+        value, act_out, logp = out
+    else:
+        value = torch.empty(P, rows_v, dims.obj, device=dev, dtype=torch.float32)
+        act_out = torch.empty(P, rows_a, dims.act, device=dev, dtype=torch.float32) if mode != ACT_EVALUATE else None
+        logp = torch.empty(P, rows_a, device=dev, dtype=torch.float32)
+    if mode == ACT_EVALUATE:
+        act_out = _f32c(action, "action")
+        assert act_out.shape == (P, rows_a, dims.act)
+    eps_shared = 0
+    if mode == ACT_SAMPLE and rows_a > 0:
+        assert eps is not None and eps.shape[1:] == (rows_a, dims.act) and eps.shape[0] in (1, P)
+        eps_shared = int(eps.shape[0] == 1 and P > 1)
+    check(lib().pgm_policy_forward_f32(ptr(params), ptr(obs), ptr(eps), eps_shared, ptr(act_out), ptr(value),
+                                       ptr(logp), mode, P, rows_v, rows_a, dims.obs, dims.act, dims.obj,
+                                       _stream()))
+    return value, act_out, logp
+
+
+def gae_adv(rewards, value, masks, bad_masks, gamma, lam, weights=None, obj_var=None, out=None):
+    """K2. rewards [P,T,N,M]; value [P,T+1,N,M]; masks/bad_masks [P,T+1,N]; weights/obj_var [P,M].
+    Returns (returns [P,T,N,M], adv [P,T,N] or None)."""
+    for n, t in (("rewards", rewards), ("value", value), ("masks", masks), ("bad_masks", bad_masks),
+                 ("weights", weights), ("obj_var", obj_var)):
+        _f32c(t, n)
+    P, T, N, M = rewards.shape
+    assert value.shape == (P, T + 1, N, M) and masks.shape == (P, T + 1, N) and bad_masks.shape == (P, T + 1, N)
+    if out is not None:
+        returns, adv = out
+    else:
+        returns = torch.empty_like(rewards)
+        adv = torch.empty(P, T, N, device=rewards.device, dtype=torch.float32) if weights is not None else None
+    check(lib().pgm_gae_adv_f32(ptr(rewards), ptr(value), ptr(masks), ptr(bad_masks), ptr(weights), ptr(obj_var),
+                                float(gamma), float(lam), ptr(returns), ptr(adv), P, T, N, M, _stream()))
+    return returns, adv
+
+
+def ppo_workspace(P, S, dims: NetDims, device, cluster=0):
+    n = lib().pgm_ppo_workspace_bytes(P, S, dims.obs, dims.act, dims.obj, cluster)
+    return torch.empty(n + 256, dtype=torch.uint8, device=device)
+
+
+def _aligned(ws):
+    off = (-ws.data_ptr()) % 256
+    return C.c_void_p(ws.data_ptr() + off), ws.numel() - off
+
+
+def ppo_update(params, adam_m, adam_v, adam_step, lr, obs, action, logp_old, value_old, returns, adv, perm,
+               num_mini_batch, dims: NetDims, hyper: PpoHyper = None, workspace=None, cluster=0, losses=None):
+    """K3. In place on params/adam_m/adam_v [P,n_par] and adam_step [P] int32.
+    obs [P,>=S,O] / value_old [P,>=S,M] may carry the extra T+1 slot (only the first S rows are read);
+    action [P,S,A]; logp_old, adv [P,S]; returns [P,S,M]; perm int32 [P or 1,E,S]; lr float64 [P].
+    Returns losses [P,3] = (value_loss, action_loss, entropy) averaged over the E*B updates."""
+    P, S, A = action.shape
+    for n, t in (("params", params), ("adam_m", adam_m), ("adam_v", adam_v), ("obs", obs), ("action", action),
+                 ("logp_old", logp_old), ("value_old", value_old), ("returns", returns), ("adv", adv)):
+        _f32c(t, n)
+    assert adam_step.dtype == torch.int32 and lr.dtype == torch.float64 and perm.dtype == torch.int32
+    assert perm.is_cuda and perm.is_contiguous() and perm.shape[-1] == S and perm.shape[0] in (1, P)
+    assert obs.shape[0] == P and obs.shape[1] >= S and obs.shape[2] == dims.obs
+    assert value_old.shape[0] == P and value_old.shape[1] >= S and value_old.shape[2] == dims.obj
+    hyper = hyper or PpoHyper()
+    if workspace is None:
+        workspace = ppo_workspace(P, S, dims, params.device, cluster)
+    wp, wn = _aligned(workspace)
+    if losses is None:
+        losses = torch.empty(P, 3, device=params.device, dtype=torch.float32)
+    E = perm.shape[1]
+    check(lib().pgm_ppo_update_f32(
+        ptr(params), ptr(adam_m), ptr(adam_v), ptr(adam_step), ptr(lr), ptr(obs), obs.stride(0), ptr(action),
+        ptr(logp_old), ptr(value_old), value_old.stride(0), ptr(returns), ptr(adv), ptr(perm),
+        int(perm.shape[0] == 1 and P > 1), E, num_mini_batch, C.byref(hyper), ptr(losses), wp, wn, cluster,
+        P, S, dims.obs, dims.act, dims.obj, _stream()))
+    return losses
+
+
+def ppo_grad(params, obs, action, logp_old, value_old, returns, adv, idx, dims: NetDims, hyper=None,
+             cluster=0):
+    """Verification aid: un-clipped gradient [P,n_par] and losses [P,3] of one minibatch `idx` (int32 [mb])."""
+    P, S, A = action.shape
+    hyper = hyper or PpoHyper()
+    ws = ppo_workspace(P, S, dims, params.device, cluster)
+    wp, wn = _aligned(ws)
+    grad = torch.zeros(P, dims.n_par, device=params.device, dtype=torch.float32)
+    losses = torch.empty(P, 3, device=params.device, dtype=torch.float32)
+    check(lib().pgm_ppo_grad_f32(ptr(params), ptr(obs), obs.stride(0), ptr(action), ptr(logp_old), ptr(value_old),
+                                 value_old.stride(0), ptr(returns), ptr(adv), ptr(idx), idx.numel(),
+                                 C.byref(hyper), ptr(grad), ptr(losses), wp, wn, cluster, P, S, dims.obs, dims.act,
+                                 dims.obj, _stream()))
+    return grad, losses

@@ -1,0 +1,54 @@
+"""CPU-side checks of the C-ABI library: it builds, loads, and exports every symbol the
+header declares (no compute calls -- those need a GPU)."""
+import os
+import re
+import shutil
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    from pgmorl_b200 import _lib, build
+    if shutil.which("nvcc") or os.path.exists(build.NVCC):
+        build.build()
+    return _lib.lib()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pgmorl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported_and_bound(library):
+    from pgmorl_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 7
+    for s in syms:
+        assert hasattr(library, s), f"{s} declared in include/pgmorl_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in pgmorl_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_n_par_matches_python_layout(library):
+    from pgmorl_b200.layout import ENV_SHAPES
+    for d in ENV_SHAPES.values():
+        assert library.pgm_n_par(d.obs, d.act, d.obj) == d.n_par
+    assert library.pgm_n_par(17, 6, 2) == 11150 and library.pgm_n_par(376, 17, 2) == 57828
+
+
+def test_argument_errors_are_reported_without_a_gpu(library):
+    # argument validation happens before any CUDA call
+    rc = library.pgm_gae_adv_f32(None, None, None, None, None, None, 0.99, 0.95, None, None, 1, 1, 1, 1, None)
+    assert rc == 1 and b"null" in library.pgm_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from pgmorl_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PgmError):
+        _lib.lib()

@@ -1,0 +1,190 @@
+"""GPU parity tests of K1 / K2 / K3 against the float64 oracle, through the C ABI.
+
+Tolerance (north_star): FP32 kernels vs the float64 oracle, norm-wise per tensor,
+max|a-b| <= tol * max|b| with tol = 1e-4 for parameters / returns (much tighter where
+the arithmetic is short). Written beside each assert.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mopg_oracle as orc
+from pgmorl_b200 import synthetic
+from pgmorl_b200.layout import NetDims
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+DIMS = {"walker": NetDims(17, 6, 2), "hopper3": NetDims(11, 3, 3), "humanoid": NetDims(376, 17, 2)}
+
+
+def dev(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device="cuda", dtype=dtype).contiguous()
+
+
+def make_case(d, P, T, N, seed):
+    """Random policies + synthetic trajectories + oracle rollout/GAE/adv in float64."""
+    rng = np.random.RandomState(seed)
+    params = np.stack([synthetic.init_policy_flat(d, seed=seed * 100 + p).numpy() for p in range(P)])
+    params[:, -d.act:] = rng.uniform(-0.5, 0.3, (P, d.act))          # non-trivial logstd
+    traj = synthetic.make_trajectories(P, T, N, d, seed=seed, p_done=0.05)
+    traj = {k: v.numpy() for k, v in traj.items()}
+    eps, perm = synthetic.host_rng_streams(seed, T, N, d.act, 2)
+    eps = eps.numpy()
+    weights = rng.dirichlet(np.ones(d.obj), P)
+    obj_var = rng.uniform(0.5, 2.0, (P, d.obj))
+    out = []
+    for p in range(P):
+        net = orc.Net(params[p].copy(), d.obs, d.act, d.obj)
+        value, action, logp = orc.rollout(net, traj["obs"][p].astype(np.float64), eps)
+        ret = orc.gae_returns(traj["rewards"][p].astype(np.float64), value, traj["masks"][p].astype(np.float64),
+                              traj["bad_masks"][p].astype(np.float64), 0.995, 0.95)
+        adv = orc.advantages(ret, value, weights[p], obj_var[p])
+        out.append(dict(value=value, action=action, logp=logp, returns=ret, adv=adv))
+    return params, traj, eps, perm.numpy(), weights, obj_var, out
+
+
+@pytest.mark.parametrize("name,P,T,N", [("walker", 3, 50, 4), ("hopper3", 2, 33, 2), ("walker", 1, 1, 4)])
+@pytest.mark.parametrize("shared_eps", [True, False])
+def test_k1_rollout_matches_oracle(name, P, T, N, shared_eps):
+    from pgmorl_b200 import kernels as K
+    d = DIMS[name]
+    params, traj, eps, _, _, _, ref = make_case(d, P, T, N, seed=3)
+    obs = dev(traj["obs"]).reshape(P, (T + 1) * N, d.obs)
+    e = dev(eps).reshape(1, T * N, d.act)
+    if not shared_eps:
+        e = e.expand(P, -1, -1).contiguous()
+    value, action, logp = K.policy_forward(dev(params), obs, d, eps=e, rows_a=T * N)
+    torch.cuda.synchronize()
+    for p in range(P):
+        # FP32 forward of a 3-layer MLP: 2e-5 norm-wise
+        assert rel_err(value[p].cpu().numpy().reshape(T + 1, N, -1), ref[p]["value"]) < 2e-5
+        assert rel_err(action[p].cpu().numpy().reshape(T, N, -1), ref[p]["action"]) < 2e-5
+        assert rel_err(logp[p].cpu().numpy().reshape(T, N), ref[p]["logp"]) < 2e-5
+
+
+def test_k1_modes():
+    from pgmorl_b200 import kernels as K
+    d = DIMS["walker"]
+    P, T, N = 2, 40, 4
+    params, traj, eps, _, _, _, ref = make_case(d, P, T, N, seed=5)
+    obs = dev(traj["obs"]).reshape(P, (T + 1) * N, d.obs)
+    gp = dev(params)
+    # deterministic: action == mean, logp = log N(mean | mean, std)
+    value, action, logp = K.policy_forward(gp, obs, d, mode=K.ACT_DETERMINISTIC)
+    for p in range(P):
+        net = orc.Net(params[p].copy(), d.obs, d.act, d.obj)
+        v, mean, _ = orc.forward(net, traj["obs"][p].reshape(-1, d.obs).astype(np.float64))
+        assert rel_err(action[p].cpu().numpy(), mean) < 2e-5
+        assert rel_err(logp[p].cpu().numpy(), orc.log_prob(net, mean, mean)) < 2e-5
+        assert rel_err(value[p].cpu().numpy(), v) < 2e-5
+    # evaluate: log-prob of given actions (a2c/model.py:75-82)
+    given = dev(np.stack([r["action"].reshape(T * N, d.act) for r in ref]))
+    value2, a2, logp2 = K.policy_forward(gp, obs, d, action=given, mode=K.ACT_EVALUATE, rows_a=T * N)
+    assert a2.data_ptr() == given.data_ptr()
+    for p in range(P):
+        assert rel_err(logp2[p].cpu().numpy().reshape(T, N), ref[p]["logp"]) < 2e-5
+    # get_value only
+    v3, _, _ = K.policy_forward(gp, obs, d, rows_a=0, mode=K.ACT_DETERMINISTIC)
+    assert torch.equal(v3, value)
+
+
+@pytest.mark.parametrize("name,P,T,N", [("walker", 3, 64, 4), ("hopper3", 2, 45, 2), ("walker", 2, 2048, 4),
+                                         ("walker", 1, 7, 1), ("humanoid", 2, 100, 8)])
+def test_k2_gae_adv_matches_oracle(name, P, T, N):
+    from pgmorl_b200 import kernels as K
+    d = DIMS[name]
+    rng = np.random.RandomState(T)
+    traj = {k: v.numpy() for k, v in synthetic.make_trajectories(P, T, N, d, seed=T, p_done=0.03).items()}
+    value = rng.randn(P, T + 1, N, d.obj) * 3
+    weights = rng.dirichlet(np.ones(d.obj), P)
+    obj_var = rng.uniform(0.5, 2.0, (P, d.obj))
+    ret, adv = K.gae_adv(dev(traj["rewards"]), dev(value), dev(traj["masks"]), dev(traj["bad_masks"]), 0.995, 0.95,
+                         weights=dev(weights), obj_var=dev(obj_var))
+    ret_only, none = K.gae_adv(dev(traj["rewards"]), dev(value), dev(traj["masks"]), dev(traj["bad_masks"]),
+                               0.995, 0.95)
+    torch.cuda.synchronize()
+    assert none is None and torch.equal(ret_only, ret)
+    v32 = dev(value).cpu().numpy().astype(np.float64)     # the kernel saw the float32-rounded values
+    for p in range(P):
+        r = orc.gae_returns(traj["rewards"][p].astype(np.float64), v32[p], traj["masks"][p].astype(np.float64),
+                            traj["bad_masks"][p].astype(np.float64), 0.995, 0.95)
+        a = orc.advantages(r, v32[p], weights[p], obj_var[p])
+        assert rel_err(ret[p].cpu().numpy(), r) < 1e-5        # returns: 1e-5 (gate 1e-4)
+        assert rel_err(adv[p].cpu().numpy(), a) < 1e-4        # normalised advantage: 1e-4
+
+
+def _ppo_inputs(d, P, T, N, seed):
+    params, traj, eps, perm, weights, obj_var, ref = make_case(d, P, T, N, seed)
+    rng = np.random.RandomState(seed + 1)
+    # evaluate at perturbed parameters so ratios leave 1 and the value clip is exercised
+    cur = params + rng.randn(*params.shape) * 0.02
+    S = T * N
+    obs = traj["obs"].reshape(P, (T + 1) * N, d.obs)
+    pack = dict(
+        obs=obs, action=np.stack([r["action"].reshape(S, d.act) for r in ref]),
+        logp=np.stack([r["logp"].reshape(S) for r in ref]),
+        value=np.stack([r["value"].reshape((T + 1) * N, d.obj) for r in ref]),
+        returns=np.stack([r["returns"].reshape(S, d.obj) for r in ref]),
+        adv=np.stack([r["adv"].reshape(S) for r in ref]))
+    return cur, pack, perm
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("name,P,T,N,mb", [("walker", 2, 64, 4, 256), ("walker", 1, 30, 4, 100),
+                                            ("hopper3", 2, 48, 2, 64), ("humanoid", 1, 32, 8, 96)])
+def test_k3_gradient_matches_oracle(name, P, T, N, mb, cluster):
+    from pgmorl_b200 import kernels as K
+    d = DIMS[name]
+    if name == "humanoid" and cluster == 1:
+        pytest.skip("wide networks need cluster >= 2 (both halves do not fit one CTA's shared memory)")
+    cur, pk, perm = _ppo_inputs(d, P, T, N, seed=11)
+    S = T * N
+    idx = np.random.RandomState(0).permutation(S)[:mb]
+    hyper = K.PpoHyper(entropy_coef=0.01)
+    g, losses = K.ppo_grad(dev(cur), dev(pk["obs"]), dev(pk["action"]), dev(pk["logp"]), dev(pk["value"]),
+                           dev(pk["returns"]), dev(pk["adv"]), dev(idx, torch.int32), d, hyper=hyper,
+                           cluster=cluster)
+    torch.cuda.synchronize()
+    for p in range(P):
+        net = orc.Net(cur[p].copy(), d.obs, d.act, d.obj)
+        gref, lref = orc.ppo_grad(net, pk["obs"][p][:S][idx].astype(np.float64), pk["action"][p][idx],
+                                  pk["logp"][p][idx], pk["value"][p][:S][idx], pk["returns"][p][idx],
+                                  pk["adv"][p][idx], ecoef=0.01)
+        # FP32 gradient of a mean over <=256 rows: 5e-5 norm-wise per tensor group (whole vector)
+        assert rel_err(g[p].cpu().numpy(), gref) < 5e-5
+        assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 2e-5
+
+
+@pytest.mark.parametrize("cluster", [0, 1, 2, 4, 8])
+@pytest.mark.parametrize("name,P,T,N,B", [("walker", 3, 64, 4, 4), ("hopper3", 2, 48, 2, 3)])
+def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
+    from pgmorl_b200 import kernels as K
+    d = DIMS[name]
+    cur, pk, perm = _ppo_inputs(d, P, T, N, seed=13)
+    S = T * N
+    rng = np.random.RandomState(2)
+    m0 = rng.randn(P, d.n_par) * 1e-3
+    v0 = rng.rand(P, d.n_par) * 1e-5
+    step0 = np.array([0, 7, 640][:P], dtype=np.int32)
+    lr = np.array([3e-4, 2.5e-4, 1e-4][:P])
+    gp, gm, gv = dev(cur), dev(m0), dev(v0)
+    gstep = dev(step0, torch.int32)
+    losses = K.ppo_update(gp, gm, gv, gstep, dev(lr, torch.float64), dev(pk["obs"]), dev(pk["action"]),
+                          dev(pk["logp"]), dev(pk["value"]), dev(pk["returns"]), dev(pk["adv"]),
+                          dev(perm[None], torch.int32), B, d, cluster=cluster)
+    torch.cuda.synchronize()
+    for p in range(P):
+        flat = dev(cur[p]).cpu().numpy().astype(np.float64)
+        m = dev(m0[p]).cpu().numpy().astype(np.float64)
+        v = dev(v0[p]).cpu().numpy().astype(np.float64)
+        obs3 = pk["obs"][p].reshape(T + 1, N, d.obs).astype(np.float64)
+        step, lref = orc.ppo_update(flat, m, v, int(step0[p]), lr[p], (d.obs, d.act, d.obj), obs3,
+                                    pk["action"][p].reshape(T, N, -1), pk["logp"][p].reshape(T, N),
+                                    pk["value"][p].reshape(T + 1, N, -1), pk["returns"][p].reshape(T, N, -1),
+                                    pk["adv"][p].reshape(T, N), perm, B)
+        assert int(gstep[p]) == step
+        assert rel_err(gp[p].cpu().numpy(), flat) < 1e-5       # parameters (gate 1e-4)
+        assert rel_err(gm[p].cpu().numpy(), m) < 1e-4          # Adam first moment
+        assert rel_err(gv[p].cpu().numpy(), v) < 1e-4          # Adam second moment
+        assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 1e-4
