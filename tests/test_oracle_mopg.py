@@ -48,3 +48,25 @@ def test_oracle_matches_reference_small(name):
 def test_oracle_matches_reference_full_c2():
     # full HalfCheetah-shape iteration (320 Adam steps on 8192 samples), one task
     run_case("mopg_halfcheetah_full.npz", tasks=[1], tol=1e-8)
+
+
+def test_torch_port_matches_reference():
+    """oracle/mopg_torch_port.py (the CPU-baseline leg of bench.py) reproduces the reference too."""
+    import torch
+    from oracle.mopg_torch_port import PortPolicy, mopg_iteration_port
+    z, meta = load_mopg_case("mopg_walker_small.npz")
+    d = meta["dims"]
+    task = 1
+    pol = PortPolicy(z[f"t{task}_init"], d.obs, d.act, d.obj)
+    opt = torch.optim.Adam(pol.ordered(), lr=3e-4, eps=1e-5)
+    for k, j in enumerate(meta["iters"]):
+        traj = task_traj(meta, j, task)
+        lr = synthetic.linear_lr(3e-4, j, 1.0, meta["total_num_updates"])
+        out = mopg_iteration_port(pol, opt, traj, j, lr, z[f"t{task}_weights"], z[f"t{task}_obj_var"],
+                                  gamma=meta["gamma"], lam=meta["lam"], ppo_epoch=meta["E"],
+                                  num_mini_batch=meta["B"])
+        pre = f"t{task}_i{k}_"
+        assert rel_err(out["returns"], z[pre + "returns"]) < 1e-12
+        assert rel_err(out["adv"], z[pre + "adv"]) < 1e-12
+        assert rel_err(out["losses"], z[pre + "losses"]) < 1e-9
+        assert rel_err(pol.flat(), z[pre + "params"]) < 1e-9
