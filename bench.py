@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--cluster", type=int, default=int(os.environ.get("PGM_PPO_CLUSTER", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-sample", action="store_true",
+                    help="reference arm: time the full-size iteration instead of the T/4 bounded sample")
     args = ap.parse_args()
 
     from pgmorl_b200.layout import ENV_SHAPES
@@ -159,7 +161,7 @@ def main():
         if rank != 0:
             return 0
         # bounded sample: same per-row work (minibatch of 256 rows, 10 epochs) on T/4 steps
-        Ts, Bs = max(T // 4, 1), max(B // 4, 1)
+        Ts, Bs = (T, B) if args.full_sample else (max(T // 4, 1), max(B // 4, 1))
         v, ms, cores = cpu_reference_leg(d, P, Ts, N, E, Bs, gamma, args.steps, min(args.warmup, 1))
         sample = (f"each step = one MOPG iteration of {P} tasks on T={Ts} steps x {N} envs with {Bs} minibatches "
                   f"of {Ts * N // Bs} rows x {E} epochs (same minibatch size as the full workload), "
@@ -304,11 +306,17 @@ def main():
             "ppo_cluster": args.cluster, "finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cms, cores = cpu_reference_leg(d, P, T, N, E, B, gamma, 1, 0)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "ms_per_step": cms,
-                                    "sample": f"1 full MOPG iteration of all {P} tasks ({P * S} env-steps), oracle torch "
-                                              f"port with the reference's op sequence, process per task, 1 thread each"}
+            # fresh CPU-only process: fork-based worker pools cannot follow CUDA/autograd use in this one
+            env_cpu = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                    "--warmup", "0", "--config", args.config, "--full-sample"],
+                                   capture_output=True, text=True, env=env_cpu, timeout=900)
+                ref = json.loads(r.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+                line["cpu_baseline"]["ms_per_step"] = ref["ms_per_step"]
+            except Exception as ex:   # keep the GPU numbers even if the CPU leg fails
+                line["cpu_baseline"] = {"error": repr(ex)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

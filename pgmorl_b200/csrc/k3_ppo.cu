@@ -86,15 +86,37 @@ __device__ __forceinline__ unsigned group_rank() {
     return r;
 }
 
+// half-local flat parameter index -> its location in the padded shared-memory image
+__device__ __forceinline__ float *half_param_ptr(const HalfNet &n, const NetLayout &L, int e) {
+    const int O = L.O;
+    if (e < H * O) { const int j = e / O; return n.W1 + j * L.ldw1 + (e - j * O); }
+    e -= H * O;
+    if (e < H) return n.b1 + e;
+    e -= H;
+    if (e < H * H) return n.W2 + (e >> 6) * LDH + (e & 63);
+    e -= H * H;
+    if (e < H) return n.b2 + e;
+    e -= H;
+    if (e < n.KH * H) return n.Wh + (e >> 6) * LDH + (e & 63);
+    e -= n.KH * H;
+    if (e < n.KH) return n.bh + e;
+    return n.ls + (e - n.KH);
+}
+
 // C: CTAs per task; TM: rows per thread per chunk (chunk = 16*TM rows);
 // KG1: 4-column groups of dW1 per thread (OP <= 64*KG1); NA: head rows per thread (A,M <= 16*NA);
 // DB: double-buffered record gather.
-template <int C, int TM, int KG1, int NA, bool DB>
+// RED: "redundant Adam" -- every CTA of a half keeps the half's parameters AND Adam moments in
+//      shared memory, reduces all G partial gradients itself and applies the identical update,
+//      so a step needs two cluster barriers and no parameter reload (small networks, C >= 2).
+//      Otherwise each CTA updates a 1/G slice in global memory and all reload (three barriers).
+template <int C, int TM, int KG1, int NA, bool DB, bool RED>
 __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
     constexpr int RC = 16 * TM;
     constexpr int NHALF = (C == 1) ? 2 : 1;
     constexpr int G = (C == 1) ? 1 : C / 2;
     static_assert(!(DB && NHALF == 2), "double-buffered gather needs one half per CTA");
+    static_assert(!(RED && NHALF == 2), "redundant Adam needs one half per CTA");
     extern __shared__ __align__(16) float smem[];
     __shared__ float red[34];
     __shared__ double sh_d[4];
@@ -120,12 +142,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
     float *dz = p; p += RC * LDH;
     float *ho = p; p += round_up(RC * ldo, 4);
     float *els = p; p += round_up(RC * ldo, 4);
-    float *recb = p;   // [DB ? 2 : 1][RC][RSS]
+    float *recb = p; p += (DB ? 2 : 1) * RC * RSS;   // [DB ? 2 : 1][RC][RSS]
+    float *mS = p, *vS = p + a.NHP, *gS = p + 2 * a.NHP;   // RED only: Adam moments + reduced gradient
 
     float *gparams = a.params + (size_t)task * L.n_par;
 #pragma unroll
     for (int hh = 0; hh < NHALF; ++hh) halfnet_load<false>(net[hh], gparams, L, half0 + hh);
 
+    if (RED && !a.grad_only) {
+        const int nH = L.half_size(half0);
+        for (int e = tid; e < nH; e += NTHREADS) {
+            const size_t gi = (size_t)task * L.n_par + L.to_global(half0, e);
+            mS[e] = a.adam_m[gi];
+            vS[e] = a.adam_v[gi];
+        }
+    }
     const float clip = (float)a.hy.clip_param;
     const float inv_mb = 1.f / (float)a.mb;
     const float vscale = (float)(a.hy.value_loss_coef * 0.5 / ((double)a.mb * M));
@@ -407,6 +438,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 
         sync_group<C>();   // (1) all partial gradients of this task are in L2
 
+        if (RED) {
+            // ---- every CTA reduces ALL partials of its half (same order everywhere -> bitwise equal) ----
+            const int half = half0;
+            const HalfNet &n = net[0];
+            const int nH = L.half_size(half);
+            const int nH4 = (nH + 3) >> 2;
+            const float *slot0 = a.gpart + (size_t)(task * 2 + half) * G * a.NHP;
+            const int lls = L.n_base + n.KH * H + n.KH;
+            float sq = 0.f;
+            constexpr int U = 4;
+            for (int base = 0; base < nH4; base += U * NTHREADS) {
+                float4 acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i4 = base + u * NTHREADS + tid;
+                    acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i4 < nH4) {
+#pragma unroll
+                        for (int gg = 0; gg < G; ++gg) {
+                            const float4 t = __ldcg(reinterpret_cast<const float4 *>(slot0 + (size_t)gg * a.NHP) + i4);
+                            acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i4 = base + u * NTHREADS + tid;
+                    if (i4 < nH4) {
+                        float v4[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int e = 4 * i4 + c;
+                            if (e >= nH) v4[c] = 0.f;                          // slot padding is never written
+                            else if (half == 0 && e >= lls) v4[c] -= ecoef;     // d(-ecoef * entropy)/d logstd
+                            sq = fmaf(v4[c], v4[c], sq);
+                        }
+                        sts4(gS + 4 * i4, make_float4(v4[0], v4[1], v4[2], v4[3]));
+                    }
+                }
+            }
+            sq = block_sum(sq, red);
+            if (tid == 0) a.ssq[task * 16 + rank] = sq;
+            if (a.grad_only) {
+                if (g == 0)
+                    for (int e = tid; e < nH; e += NTHREADS) a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gS[e];
+                break;
+            }
+            if (tid == 0) {   // Adam scalars of step k = step0 + s + 1, in double
+                b1pow *= a.hy.beta1; b2pow *= a.hy.beta2;
+                sh_d[0] = lr / (1.0 - b1pow);            // step_size
+                sh_d[1] = 1.0 / sqrt(1.0 - b2pow);       // 1 / bias_correction2_sqrt
+            }
+            sync_group<C>();   // (2) both halves' squared norms visible
+            const float tot = __ldcg(a.ssq + task * 16 + 0) + __ldcg(a.ssq + task * 16 + G);
+            const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
+            const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
+            for (int e = tid; e < nH; e += NTHREADS) {
+                const float gr = gS[e] * coef;
+                float m = mS[e], v = vS[e];
+                float *pp = half_param_ptr(n, L, e);
+                m = fmaf(gr - m, omb1, m);                 // exp_avg.lerp_(grad, 1 - beta1)
+                v = fmaf(omb2 * gr, gr, v * b2f);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+                const float denom = sqrtf(v) * ibc2 + aeps;
+                *pp -= step_size * (m / denom);
+                mS[e] = m; vS[e] = v;
+            }
+            __syncthreads();
+            continue;
+        }
+
         // ---- reduce my slice over the G partials, squared-norm partial ----
         float sq = 0.f;
 #pragma unroll
@@ -467,6 +568,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
         __syncthreads();
     }
 
+    if (RED && !a.grad_only && g == 0) {   // one CTA per half writes the final state back (reference order)
+        const int nH = L.half_size(half0);
+        for (int e = tid; e < nH; e += NTHREADS) {
+            const size_t gi = (size_t)task * L.n_par + L.to_global(half0, e);
+            a.params[gi] = *half_param_ptr(net[0], L, e);
+            a.adam_m[gi] = mS[e];
+            a.adam_v[gi] = vS[e];
+        }
+    }
+
     // ---- losses: per-CTA partial sums -> rank 0 combines in fixed order ----
     {
         const float la = block_sum(loss_act, red), lv = block_sum(loss_val, red), le = block_sum(loss_ent, red);
@@ -497,12 +608,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 // ------------------------------------------------------------------------------------------
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
-    bool DB;
+    bool DB, RED;
     size_t smem;
     size_t off_rec, off_gpart, off_ssq, off_lpart, total;
 };
 
-static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS) {
+static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS, bool RED, int NHP) {
     const int RC = 16 * TM;
     const int ldo = ((L.A > L.M ? L.A : L.M) | 1);
     size_t f = 0;
@@ -510,6 +621,7 @@ static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS)
     else f += halfnet_smem_floats(L, 0) > halfnet_smem_floats(L, 1) ? halfnet_smem_floats(L, 0) : halfnet_smem_floats(L, 1);
     f += 3 * (size_t)RC * LDH + 2 * (size_t)round_up(RC * ldo, 4);
     f += (size_t)(DB ? 2 : 1) * RC * RSS;
+    if (RED) f += 3 * (size_t)NHP;
     return f * sizeof(float);
 }
 
@@ -521,11 +633,10 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
                 "ppo: cluster must be 0,1,2,4,8 or 16 (got %d)", cluster);
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
-        C = 1;
+        C = 2;   // one CTA per network half is the throughput configuration (large populations)
         while (C < 8 && (long long)P * C * 2 <= sms && mb / C >= 32) C *= 2;
     }
     const bool big = (L.OP > 64) || (A > 16) || (M > 16);
-    if (big && C == 1 && cluster == 0) C = 2;   // both halves of a wide network do not fit one CTA's shared memory
     pl.C = C; pl.G = C == 1 ? 1 : C / 2;
     pl.KG1 = big ? 6 : 1; pl.NA = big ? 2 : 1;
     const int rows = (mb + pl.G - 1) / pl.G;          // rows per CTA per step
@@ -536,7 +647,8 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     pl.RSS = stride4odd(pl.RSG);
     pl.NHP = round_up(L.half_size(0) > L.half_size(1) ? L.half_size(0) : L.half_size(1), 64);
     pl.DB = (C > 1) && !big;
-    pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS);
+    pl.RED = (C > 1) && !big;
+    pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS, pl.RED, pl.NHP);
     PGM_REQUIRE(pl.smem <= 227 * 1024, "ppo: configuration needs %zu B of shared memory (O=%d, cluster=%d)", pl.smem, O, C);
     size_t off = 0;
     auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -548,9 +660,9 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     return PGM_OK;
 }
 
-template <int C, int TM, int KG1, int NA, bool DB>
+template <int C, int TM, int KG1, int NA, bool DB, bool RED>
 static int k3_launch_t(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
-    auto kern = k3_ppo_kernel<C, TM, KG1, NA, DB>;
+    auto kern = k3_ppo_kernel<C, TM, KG1, NA, DB, RED>;
     PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     if (C > 8) PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -565,11 +677,12 @@ static int k3_launch_t(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
 
 template <int C>
 static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
-    if (pl.KG1 == 6) return k3_launch_t<C, 2, 6, 2, false>(a, pl, P, st);
-    if constexpr (C > 1) {
-        if (pl.DB) return pl.TM == 2 ? k3_launch_t<C, 2, 1, 1, true>(a, pl, P, st) : k3_launch_t<C, 4, 1, 1, true>(a, pl, P, st);
+    if (pl.KG1 == 6) return k3_launch_t<C, 2, 6, 2, false, false>(a, pl, P, st);
+    if constexpr (C > 1) {   // small networks on a cluster: double-buffered gather + redundant Adam
+        return pl.TM == 2 ? k3_launch_t<C, 2, 1, 1, true, true>(a, pl, P, st) : k3_launch_t<C, 4, 1, 1, true, true>(a, pl, P, st);
+    } else {
+        return pl.TM == 2 ? k3_launch_t<C, 2, 1, 1, false, false>(a, pl, P, st) : k3_launch_t<C, 4, 1, 1, false, false>(a, pl, P, st);
     }
-    return pl.TM == 2 ? k3_launch_t<C, 2, 1, 1, false>(a, pl, P, st) : k3_launch_t<C, 4, 1, 1, false>(a, pl, P, st);
 }
 
 static int k3_launch(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
