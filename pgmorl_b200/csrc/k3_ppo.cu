@@ -86,22 +86,24 @@ __device__ __forceinline__ unsigned group_rank() {
     return r;
 }
 
-// half-local flat parameter index -> its location in the padded shared-memory image
-__device__ __forceinline__ float *half_param_ptr(const HalfNet &n, const NetLayout &L, int e) {
+// half-local flat parameter index -> offset inside the padded shared-memory image of the half
+__device__ __forceinline__ int half_img_off(const HalfNet &n, const NetLayout &L, int e) {
     const int O = L.O;
-    if (e < H * O) { const int j = e / O; return n.W1 + j * L.ldw1 + (e - j * O); }
+    if (e < H * O) { const int j = e / O; return j * L.ldw1 + (e - j * O); }
     e -= H * O;
-    if (e < H) return n.b1 + e;
+    if (e < H) return (int)(n.b1 - n.W1) + e;
     e -= H;
-    if (e < H * H) return n.W2 + (e >> 6) * LDH + (e & 63);
+    if (e < H * H) return (int)(n.W2 - n.W1) + (e >> 6) * LDH + (e & 63);
     e -= H * H;
-    if (e < H) return n.b2 + e;
+    if (e < H) return (int)(n.b2 - n.W1) + e;
     e -= H;
-    if (e < n.KH * H) return n.Wh + (e >> 6) * LDH + (e & 63);
+    if (e < n.KH * H) return (int)(n.Wh - n.W1) + (e >> 6) * LDH + (e & 63);
     e -= n.KH * H;
-    if (e < n.KH) return n.bh + e;
-    return n.ls + (e - n.KH);
+    if (e < n.KH) return (int)(n.bh - n.W1) + e;
+    return (int)(n.ls - n.W1) + (e - n.KH);
 }
+
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // C: CTAs per task; TM: rows per thread per chunk (chunk = 16*TM rows);
 // KG1: 4-column groups of dW1 per thread (OP <= 64*KG1); NA: head rows per thread (A,M <= 16*NA);
@@ -149,12 +151,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 #pragma unroll
     for (int hh = 0; hh < NHALF; ++hh) halfnet_load<false>(net[hh], gparams, L, half0 + hh);
 
+    const int NIMG = RED ? halfnet_smem_floats(L, half0) : 0;   // floats in the image of my half
     if (RED && !a.grad_only) {
+        for (int i = tid; i < NIMG; i += NTHREADS) { mS[i] = 0.f; vS[i] = 0.f; }
+        __syncthreads();
         const int nH = L.half_size(half0);
         for (int e = tid; e < nH; e += NTHREADS) {
             const size_t gi = (size_t)task * L.n_par + L.to_global(half0, e);
-            mS[e] = a.adam_m[gi];
-            vS[e] = a.adam_v[gi];
+            const int io = half_img_off(net[0], L, e);
+            mS[io] = a.adam_m[gi];
+            vS[io] = a.adam_v[gi];
         }
     }
     const float clip = (float)a.hy.clip_param;
@@ -398,22 +404,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
             }
 
             // ---- write this CTA's partial gradient of `half` to its scratch slot ----
+            // RED: slot has the layout of the padded smem image (padding stays zero from the memset at
+            // launch); otherwise the half-local reference order.
             {
                 float *gp = a.gpart + ((size_t)(task * 2 + half) * G + g) * a.NHP;
                 const int tj = tid & 15, tk = tid >> 4;
-                const int lb1 = H * O, lW2 = lb1 + H, lb2 = lW2 + H * H, lWh = lb2 + H, lbh = lWh + KH * H, lls = lbh + KH;
+                const int ldg1 = RED ? L.ldw1 : O, ldg2 = RED ? LDH : H;
+                const int lb1 = RED ? (int)(n.b1 - n.W1) : H * O, lW2 = RED ? (int)(n.W2 - n.W1) : lb1 + H;
+                const int lb2 = RED ? (int)(n.b2 - n.W1) : lW2 + H * H, lWh = RED ? (int)(n.Wh - n.W1) : lb2 + H;
+                const int lbh = RED ? (int)(n.bh - n.W1) : lWh + KH * H, lls = RED ? (int)(n.ls - n.W1) : lbh + KH;
 #pragma unroll
-                for (int q = 0; q < KG1; ++q)
+                for (int q = 0; q < KG1; ++q) {
+                    const int k0 = 4 * (tk + 16 * q);
+                    if (RED) {
+                        if (k0 < OP)
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
+                            for (int jj = 0; jj < 4; ++jj)
+                                sts4(gp + (4 * tj + jj) * ldg1 + k0, make_float4(gW1[q][jj][0], gW1[q][jj][1], gW1[q][jj][2], gW1[q][jj][3]));
+                    } else {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int k = 4 * (tk + 16 * q) + kk;
-                            if (k < O) gp[(4 * tj + jj) * O + k] = gW1[q][jj][kk];
-                        }
+                        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                if (k0 + kk < O) gp[(4 * tj + jj) * ldg1 + k0 + kk] = gW1[q][jj][kk];
+                    }
+                }
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
-                    sts4(gp + lW2 + (4 * tj + jj) * H + 4 * tk, make_float4(gW2[jj][0], gW2[jj][1], gW2[jj][2], gW2[jj][3]));
+                    sts4(gp + lW2 + (4 * tj + jj) * ldg2 + 4 * tk, make_float4(gW2[jj][0], gW2[jj][1], gW2[jj][2], gW2[jj][3]));
                 if (tk == 0) {
                     sts4(gp + lb1 + 4 * tj, make_float4(gb1[0], gb1[1], gb1[2], gb1[3]));
                     sts4(gp + lb2 + 4 * tj, make_float4(gb2[0], gb2[1], gb2[2], gb2[3]));
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 for (int ia = 0; ia < NA; ++ia) {
                     const int aa = a0 + 16 * ia;
                     if (aa < KH) {
-                        sts4(gp + lWh + aa * H + 4 * kg, make_float4(gWh[ia][0], gWh[ia][1], gWh[ia][2], gWh[ia][3]));
+                        sts4(gp + lWh + aa * ldg2 + 4 * kg, make_float4(gWh[ia][0], gWh[ia][1], gWh[ia][2], gWh[ia][3]));
                         if (kg == 0) gp[lbh + aa] = gbh[ia];
                         if (half == 0 && kg == 1) gp[lls + aa] = gls[ia];
                     }
@@ -440,21 +458,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 
         if (RED) {
             // ---- every CTA reduces ALL partials of its half (same order everywhere -> bitwise equal) ----
+            // gradients, moments and parameters all share the padded image layout: pure float4 streams
             const int half = half0;
             const HalfNet &n = net[0];
-            const int nH = L.half_size(half);
-            const int nH4 = (nH + 3) >> 2;
+            const int n4 = NIMG >> 2;
             const float *slot0 = a.gpart + (size_t)(task * 2 + half) * G * a.NHP;
-            const int lls = L.n_base + n.KH * H + n.KH;
+            const int ls4 = (int)(n.ls - n.W1) >> 2;          // first float4 of logstd (actor)
             float sq = 0.f;
             constexpr int U = 4;
-            for (int base = 0; base < nH4; base += U * NTHREADS) {
+            for (int base = 0; base < n4; base += U * NTHREADS) {
                 float4 acc[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i4 = base + u * NTHREADS + tid;
                     acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i4 < nH4) {
+                    if (i4 < n4) {
 #pragma unroll
                         for (int gg = 0; gg < G; ++gg) {
                             const float4 t = __ldcg(reinterpret_cast<const float4 *>(slot0 + (size_t)gg * a.NHP) + i4);
@@ -465,24 +483,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i4 = base + u * NTHREADS + tid;
-                    if (i4 < nH4) {
-                        float v4[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int e = 4 * i4 + c;
-                            if (e >= nH) v4[c] = 0.f;                          // slot padding is never written
-                            else if (half == 0 && e >= lls) v4[c] -= ecoef;     // d(-ecoef * entropy)/d logstd
-                            sq = fmaf(v4[c], v4[c], sq);
+                    if (i4 < n4) {
+                        if (ecoef != 0.f && half == 0 && i4 >= ls4) {   // d(-ecoef * entropy)/d logstd
+                            const int e0 = 4 * (i4 - ls4);
+                            if (e0 + 0 < A) acc[u].x -= ecoef;
+                            if (e0 + 1 < A) acc[u].y -= ecoef;
+                            if (e0 + 2 < A) acc[u].z -= ecoef;
+                            if (e0 + 3 < A) acc[u].w -= ecoef;
                         }
-                        sts4(gS + 4 * i4, make_float4(v4[0], v4[1], v4[2], v4[3]));
+                        sq = fmaf(acc[u].x, acc[u].x, sq); sq = fmaf(acc[u].y, acc[u].y, sq);
+                        sq = fmaf(acc[u].z, acc[u].z, sq); sq = fmaf(acc[u].w, acc[u].w, sq);
+                        sts4(gS + 4 * i4, acc[u]);
                     }
                 }
             }
             sq = block_sum(sq, red);
             if (tid == 0) a.ssq[task * 16 + rank] = sq;
             if (a.grad_only) {
-                if (g == 0)
-                    for (int e = tid; e < nH; e += NTHREADS) a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gS[e];
+                if (g == 0) {
+                    const int nH = L.half_size(half);
+                    for (int e = tid; e < nH; e += NTHREADS)
+                        a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gS[half_img_off(n, L, e)];
+                }
                 break;
             }
             if (tid == 0) {   // Adam scalars of step k = step0 + s + 1, in double
@@ -494,15 +516,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
             const float tot = __ldcg(a.ssq + task * 16 + 0) + __ldcg(a.ssq + task * 16 + G);
             const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
             const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
-            for (int e = tid; e < nH; e += NTHREADS) {
-                const float gr = gS[e] * coef;
-                float m = mS[e], v = vS[e];
-                float *pp = half_param_ptr(n, L, e);
-                m = fmaf(gr - m, omb1, m);                 // exp_avg.lerp_(grad, 1 - beta1)
-                v = fmaf(omb2 * gr, gr, v * b2f);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-                const float denom = sqrtf(v) * ibc2 + aeps;
-                *pp -= step_size * (m / denom);
-                mS[e] = m; vS[e] = v;
+            float *pimg = n.W1;
+            for (int i4 = tid; i4 < n4; i4 += NTHREADS) {
+                const float4 g4 = lds4(gS + 4 * i4);
+                float4 m4 = lds4(mS + 4 * i4), v4 = lds4(vS + 4 * i4), p4 = lds4(pimg + 4 * i4);
+#define PGM_ADAM1(c)                                                                                  \
+                {                                                                                     \
+                    const float gr = g4.c * coef;                                                     \
+                    m4.c = fmaf(gr - m4.c, omb1, m4.c);          /* exp_avg.lerp_(grad, 1 - beta1) */  \
+                    v4.c = fmaf(omb2 * gr, gr, v4.c * b2f);      /* exp_avg_sq.mul_(b2).addcmul_() */  \
+                    const float denom = fmaf(fast_sqrt(v4.c), ibc2, aeps);                            \
+                    p4.c -= step_size * __fdividef(m4.c, denom);                                      \
+                }
+                PGM_ADAM1(x) PGM_ADAM1(y) PGM_ADAM1(z) PGM_ADAM1(w)
+#undef PGM_ADAM1
+                sts4(mS + 4 * i4, m4); sts4(vS + 4 * i4, v4); sts4(pimg + 4 * i4, p4);
             }
             __syncthreads();
             continue;
@@ -572,9 +600,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
         const int nH = L.half_size(half0);
         for (int e = tid; e < nH; e += NTHREADS) {
             const size_t gi = (size_t)task * L.n_par + L.to_global(half0, e);
-            a.params[gi] = *half_param_ptr(net[0], L, e);
-            a.adam_m[gi] = mS[e];
-            a.adam_v[gi] = vS[e];
+            const int io = half_img_off(net[0], L, e);
+            a.params[gi] = net[0].W1[io];
+            a.adam_m[gi] = mS[io];
+            a.adam_v[gi] = vS[io];
         }
     }
 
@@ -645,7 +674,10 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     pl.Rg = round_up(rows, pl.RC);
     pl.RSG = rec_stride(L);
     pl.RSS = stride4odd(pl.RSG);
-    pl.NHP = round_up(L.half_size(0) > L.half_size(1) ? L.half_size(0) : L.half_size(1), 64);
+    {
+        const int i0 = halfnet_smem_floats(L, 0), i1 = halfnet_smem_floats(L, 1);
+        pl.NHP = round_up(i0 > i1 ? i0 : i1, 64);   // covers both the reference-order half and its padded image
+    }
     pl.DB = (C > 1) && !big;
     pl.RED = (C > 1) && !big;
     pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS, pl.RED, pl.NHP);
@@ -712,7 +744,8 @@ extern "C" size_t pgm_ppo_workspace_bytes(int P, int S, int O, int A, int M, int
     // upper bound over every plan the launcher may choose for these dims (cluster 0 = auto)
     NetLayout L(O, A, M);
     const int G = cluster == 0 ? 8 : (cluster == 1 ? 1 : cluster / 2);
-    const int NHP = round_up(L.half_size(0) > L.half_size(1) ? L.half_size(0) : L.half_size(1), 64);
+    const int i0 = halfnet_smem_floats(L, 0), i1 = halfnet_smem_floats(L, 1);
+    const int NHP = round_up(i0 > i1 ? i0 : i1, 64);
     size_t t = 0;
     auto seg = [&](size_t b) { t += (b + 255) / 256 * 256; };
     seg((size_t)P * S * rec_stride(L) * sizeof(float));
@@ -756,6 +789,8 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
                                                (float *)(ws + pl.off_rec), P, S, a.L, pl.RSG);
         PGM_CUDA(cudaGetLastError());
     }
+    // padding entries of the gradient slots are never written by the kernel: keep them zero
+    PGM_CUDA(cudaMemsetAsync(ws + pl.off_gpart, 0, (size_t)P * 2 * pl.G * pl.NHP * sizeof(float), st));
     return k3_launch(a, pl, P, st);
 }
 
