@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpgmorl_b200.so")
+LIB_PATH = os.environ.get("PGM_LIB_PATH", os.path.join(HERE, "libpgmorl_b200.so"))
 
 _lib = None
 

@@ -36,6 +36,16 @@ def _stale(target, srcs):
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
+def build_trace():
+    """Instrumented variant (per-phase clock marks in K3) -> libpgmorl_b200_trace.so; profiling aid only."""
+    out = os.path.join(HERE, "libpgmorl_b200_trace.so")
+    r = subprocess.run([NVCC] + FLAGS + ["-DPGM_K3_TRACE", "-shared", "-o", out] + sources() + ["-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout + r.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdr = deps()
@@ -71,4 +81,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        print(build_trace())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -35,9 +35,11 @@ struct K3Args {
     float *ssq;             // scratch: squared-norm partials       [P][16]
     float *lpart;           // scratch: loss partial sums           [P][16][4]
     float *grad_out;        // grad mode only: [P][n_par]
+    long long *trace;       // PGM_K3_TRACE builds only: [CTA][4 steps][16 marks] clock64 / globaltimer
     int perm_shared, E, B, mb, S, nsteps, grad_only;
     int Rg;                 // rows per CTA per step (multiple of the chunk size)
     int RSG, RSS, NHP;      // record stride in global / shared memory; padded half size
+    int stage_floats;       // fast path: staging floats for row-split partials
     pgm_ppo_hyper hy;
     NetLayout L;
 };
@@ -67,6 +69,17 @@ __global__ void k3_pack_kernel(const float *__restrict__ obs, size_t obs_ts, con
         rec[i] = v;
     }
 }
+
+#ifdef PGM_K3_TRACE
+#define PGM_TR(ph)                                                                                   \
+    if (a.trace && tid == 0 && s >= 8 && s < 12) {                                                   \
+        long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                       \
+        a.trace[(((size_t)blockIdx.x * 4 + (s - 8)) * 16 + (ph)) * 2] = clock64();                   \
+        a.trace[(((size_t)blockIdx.x * 4 + (s - 8)) * 16 + (ph)) * 2 + 1] = gt_;                     \
+    }
+#else
+#define PGM_TR(ph)
+#endif
 
 template <int C>
 __device__ __forceinline__ void sync_group() {
@@ -108,17 +121,15 @@ __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.
 // C: CTAs per task; TM: rows per thread per chunk (chunk = 16*TM rows);
 // KG1: 4-column groups of dW1 per thread (OP <= 64*KG1); NA: head rows per thread (A,M <= 16*NA);
 // DB: double-buffered record gather.
-// RED: "redundant Adam" -- every CTA of a half keeps the half's parameters AND Adam moments in
-//      shared memory, reduces all G partial gradients itself and applies the identical update,
-//      so a step needs two cluster barriers and no parameter reload (small networks, C >= 2).
-//      Otherwise each CTA updates a 1/G slice in global memory and all reload (three barriers).
-template <int C, int TM, int KG1, int NA, bool DB, bool RED>
+// Generic path (any supported dims, incl. wide observations and C == 1): each CTA updates a 1/G
+// slice of its half in global memory and all CTAs reload the parameters (three barriers per step).
+// Small networks on C >= 2 take the fast path in k3_fast.cuh instead.
+template <int C, int TM, int KG1, int NA, bool DB>
 __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
     constexpr int RC = 16 * TM;
     constexpr int NHALF = (C == 1) ? 2 : 1;
     constexpr int G = (C == 1) ? 1 : C / 2;
     static_assert(!(DB && NHALF == 2), "double-buffered gather needs one half per CTA");
-    static_assert(!(RED && NHALF == 2), "redundant Adam needs one half per CTA");
     extern __shared__ __align__(16) float smem[];
     __shared__ float red[34];
     __shared__ double sh_d[4];
@@ -144,25 +155,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
     float *dz = p; p += RC * LDH;
     float *ho = p; p += round_up(RC * ldo, 4);
     float *els = p; p += round_up(RC * ldo, 4);
-    float *recb = p; p += (DB ? 2 : 1) * RC * RSS;   // [DB ? 2 : 1][RC][RSS]
-    float *mS = p, *vS = p + a.NHP, *gS = p + 2 * a.NHP;   // RED only: Adam moments + reduced gradient
+    float *recb = p;   // [DB ? 2 : 1][RC][RSS]
 
     float *gparams = a.params + (size_t)task * L.n_par;
 #pragma unroll
     for (int hh = 0; hh < NHALF; ++hh) halfnet_load<false>(net[hh], gparams, L, half0 + hh);
 
-    const int NIMG = RED ? halfnet_smem_floats(L, half0) : 0;   // floats in the image of my half
-    if (RED && !a.grad_only) {
-        for (int i = tid; i < NIMG; i += NTHREADS) { mS[i] = 0.f; vS[i] = 0.f; }
-        __syncthreads();
-        const int nH = L.half_size(half0);
-        for (int e = tid; e < nH; e += NTHREADS) {
-            const size_t gi = (size_t)task * L.n_par + L.to_global(half0, e);
-            const int io = half_img_off(net[0], L, e);
-            mS[io] = a.adam_m[gi];
-            vS[io] = a.adam_v[gi];
-        }
-    }
     const float clip = (float)a.hy.clip_param;
     const float inv_mb = 1.f / (float)a.mb;
     const float vscale = (float)(a.hy.value_loss_coef * 0.5 / ((double)a.mb * M));
@@ -205,6 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
     __syncthreads();
 
     for (int s = 0; s < a.nsteps; ++s) {
+        PGM_TR(0)
 #pragma unroll
         for (int hh = 0; hh < NHALF; ++hh) {
             const int half = half0 + hh;
@@ -242,9 +241,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 }
                 const int row0 = g * a.Rg + c * RC;
 
+                PGM_TR(1)
                 // ---------------- forward ----------------
                 half_forward<TM>(x, RSS, n, L, h1, h2, ho, ldo, tr, tc);
 
+                PGM_TR(2)
                 // ---------------- loss + d(loss)/d(head output), thread per row ----------------
                 if (tid < RC) {
                     const int r = tid;
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 }
                 __syncthreads();
 
+                PGM_TR(3)
                 // ---------------- phase A: head weight grads, dz2 ----------------
                 {
                     const int kg = tid & 15, a0 = tid >> 4;
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 }
                 __syncthreads();
 
+                PGM_TR(4)
                 // ---------------- phase B: dW2, db2, dz1 (into the h2 buffer) ----------------
                 {
                     const int tj = tid & 15, tk = tid >> 4;
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 }
                 __syncthreads();
 
+                PGM_TR(5)
                 // ---------------- phase C: dW1, db1 ----------------
                 {
                     const int tj = tid & 15, tk = tid >> 4;
@@ -403,35 +407,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 // the reuse of h2 / x behind every thread's phase C
             }
 
+            PGM_TR(6)
             // ---- write this CTA's partial gradient of `half` to its scratch slot ----
-            // RED: slot has the layout of the padded smem image (padding stays zero from the memset at
-            // launch); otherwise the half-local reference order.
             {
                 float *gp = a.gpart + ((size_t)(task * 2 + half) * G + g) * a.NHP;
                 const int tj = tid & 15, tk = tid >> 4;
-                const int ldg1 = RED ? L.ldw1 : O, ldg2 = RED ? LDH : H;
-                const int lb1 = RED ? (int)(n.b1 - n.W1) : H * O, lW2 = RED ? (int)(n.W2 - n.W1) : lb1 + H;
-                const int lb2 = RED ? (int)(n.b2 - n.W1) : lW2 + H * H, lWh = RED ? (int)(n.Wh - n.W1) : lb2 + H;
-                const int lbh = RED ? (int)(n.bh - n.W1) : lWh + KH * H, lls = RED ? (int)(n.ls - n.W1) : lbh + KH;
+                const int lb1 = H * O, lW2 = lb1 + H, lb2 = lW2 + H * H, lWh = lb2 + H, lbh = lWh + KH * H, lls = lbh + KH;
 #pragma unroll
-                for (int q = 0; q < KG1; ++q) {
-                    const int k0 = 4 * (tk + 16 * q);
-                    if (RED) {
-                        if (k0 < OP)
+                for (int q = 0; q < KG1; ++q)
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                sts4(gp + (4 * tj + jj) * ldg1 + k0, make_float4(gW1[q][jj][0], gW1[q][jj][1], gW1[q][jj][2], gW1[q][jj][3]));
-                    } else {
+                    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                if (k0 + kk < O) gp[(4 * tj + jj) * ldg1 + k0 + kk] = gW1[q][jj][kk];
-                    }
-                }
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int k = 4 * (tk + 16 * q) + kk;
+                            if (k < O) gp[(4 * tj + jj) * O + k] = gW1[q][jj][kk];
+                        }
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
-                    sts4(gp + lW2 + (4 * tj + jj) * ldg2 + 4 * tk, make_float4(gW2[jj][0], gW2[jj][1], gW2[jj][2], gW2[jj][3]));
+                    sts4(gp + lW2 + (4 * tj + jj) * H + 4 * tk, make_float4(gW2[jj][0], gW2[jj][1], gW2[jj][2], gW2[jj][3]));
                 if (tk == 0) {
                     sts4(gp + lb1 + 4 * tj, make_float4(gb1[0], gb1[1], gb1[2], gb1[3]));
                     sts4(gp + lb2 + 4 * tj, make_float4(gb2[0], gb2[1], gb2[2], gb2[3]));
@@ -441,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
                 for (int ia = 0; ia < NA; ++ia) {
                     const int aa = a0 + 16 * ia;
                     if (aa < KH) {
-                        sts4(gp + lWh + aa * ldg2 + 4 * kg, make_float4(gWh[ia][0], gWh[ia][1], gWh[ia][2], gWh[ia][3]));
+                        sts4(gp + lWh + aa * H + 4 * kg, make_float4(gWh[ia][0], gWh[ia][1], gWh[ia][2], gWh[ia][3]));
                         if (kg == 0) gp[lbh + aa] = gbh[ia];
                         if (half == 0 && kg == 1) gp[lls + aa] = gls[ia];
                     }
@@ -454,87 +447,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
             }
         }   // halves
 
+        PGM_TR(7)
         sync_group<C>();   // (1) all partial gradients of this task are in L2
-
-        if (RED) {
-            // ---- every CTA reduces ALL partials of its half (same order everywhere -> bitwise equal) ----
-            // gradients, moments and parameters all share the padded image layout: pure float4 streams
-            const int half = half0;
-            const HalfNet &n = net[0];
-            const int n4 = NIMG >> 2;
-            const float *slot0 = a.gpart + (size_t)(task * 2 + half) * G * a.NHP;
-            const int ls4 = (int)(n.ls - n.W1) >> 2;          // first float4 of logstd (actor)
-            float sq = 0.f;
-            constexpr int U = 4;
-            for (int base = 0; base < n4; base += U * NTHREADS) {
-                float4 acc[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i4 = base + u * NTHREADS + tid;
-                    acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i4 < n4) {
-#pragma unroll
-                        for (int gg = 0; gg < G; ++gg) {
-                            const float4 t = __ldcg(reinterpret_cast<const float4 *>(slot0 + (size_t)gg * a.NHP) + i4);
-                            acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i4 = base + u * NTHREADS + tid;
-                    if (i4 < n4) {
-                        if (ecoef != 0.f && half == 0 && i4 >= ls4) {   // d(-ecoef * entropy)/d logstd
-                            const int e0 = 4 * (i4 - ls4);
-                            if (e0 + 0 < A) acc[u].x -= ecoef;
-                            if (e0 + 1 < A) acc[u].y -= ecoef;
-                            if (e0 + 2 < A) acc[u].z -= ecoef;
-                            if (e0 + 3 < A) acc[u].w -= ecoef;
-                        }
-                        sq = fmaf(acc[u].x, acc[u].x, sq); sq = fmaf(acc[u].y, acc[u].y, sq);
-                        sq = fmaf(acc[u].z, acc[u].z, sq); sq = fmaf(acc[u].w, acc[u].w, sq);
-                        sts4(gS + 4 * i4, acc[u]);
-                    }
-                }
-            }
-            sq = block_sum(sq, red);
-            if (tid == 0) a.ssq[task * 16 + rank] = sq;
-            if (a.grad_only) {
-                if (g == 0) {
-                    const int nH = L.half_size(half);
-                    for (int e = tid; e < nH; e += NTHREADS)
-                        a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gS[half_img_off(n, L, e)];
-                }
-                break;
-            }
-            if (tid == 0) {   // Adam scalars of step k = step0 + s + 1, in double
-                b1pow *= a.hy.beta1; b2pow *= a.hy.beta2;
-                sh_d[0] = lr / (1.0 - b1pow);            // step_size
-                sh_d[1] = 1.0 / sqrt(1.0 - b2pow);       // 1 / bias_correction2_sqrt
-            }
-            sync_group<C>();   // (2) both halves' squared norms visible
-            const float tot = __ldcg(a.ssq + task * 16 + 0) + __ldcg(a.ssq + task * 16 + G);
-            const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
-            const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
-            float *pimg = n.W1;
-            for (int i4 = tid; i4 < n4; i4 += NTHREADS) {
-                const float4 g4 = lds4(gS + 4 * i4);
-                float4 m4 = lds4(mS + 4 * i4), v4 = lds4(vS + 4 * i4), p4 = lds4(pimg + 4 * i4);
-#define PGM_ADAM1(c)                                                                                  \
-                {                                                                                     \
-                    const float gr = g4.c * coef;                                                     \
-                    m4.c = fmaf(gr - m4.c, omb1, m4.c);          /* exp_avg.lerp_(grad, 1 - beta1) */  \
-                    v4.c = fmaf(omb2 * gr, gr, v4.c * b2f);      /* exp_avg_sq.mul_(b2).addcmul_() */  \
-                    const float denom = fmaf(fast_sqrt(v4.c), ibc2, aeps);                            \
-                    p4.c -= step_size * __fdividef(m4.c, denom);                                      \
-                }
-                PGM_ADAM1(x) PGM_ADAM1(y) PGM_ADAM1(z) PGM_ADAM1(w)
-#undef PGM_ADAM1
-                sts4(mS + 4 * i4, m4); sts4(vS + 4 * i4, v4); sts4(pimg + 4 * i4, p4);
-            }
-            __syncthreads();
-            continue;
-        }
+        PGM_TR(8)
 
         // ---- reduce my slice over the G partials, squared-norm partial ----
         float sq = 0.f;
@@ -596,17 +511,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
         __syncthreads();
     }
 
-    if (RED && !a.grad_only && g == 0) {   // one CTA per half writes the final state back (reference order)
-        const int nH = L.half_size(half0);
-        for (int e = tid; e < nH; e += NTHREADS) {
-            const size_t gi = (size_t)task * L.n_par + L.to_global(half0, e);
-            const int io = half_img_off(net[0], L, e);
-            a.params[gi] = net[0].W1[io];
-            a.adam_m[gi] = mS[io];
-            a.adam_v[gi] = vS[io];
-        }
-    }
-
     // ---- losses: per-CTA partial sums -> rank 0 combines in fixed order ----
     {
         const float la = block_sum(loss_act, red), lv = block_sum(loss_val, red), le = block_sum(loss_ent, red);
@@ -632,17 +536,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
     }
 }
 
+}  // namespace pgm
+#include "k3_fast.cuh"
+namespace pgm {
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
-    bool DB, RED;
+    bool DB, fast;
+    int stage_floats;
     size_t smem;
-    size_t off_rec, off_gpart, off_ssq, off_lpart, total;
+    size_t off_rec, off_gpart, off_ssq, off_lpart, off_trace, total;
 };
 
-static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS, bool RED, int NHP) {
+static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS) {
     const int RC = 16 * TM;
     const int ldo = ((L.A > L.M ? L.A : L.M) | 1);
     size_t f = 0;
@@ -650,7 +559,6 @@ static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS,
     else f += halfnet_smem_floats(L, 0) > halfnet_smem_floats(L, 1) ? halfnet_smem_floats(L, 0) : halfnet_smem_floats(L, 1);
     f += 3 * (size_t)RC * LDH + 2 * (size_t)round_up(RC * ldo, 4);
     f += (size_t)(DB ? 2 : 1) * RC * RSS;
-    if (RED) f += 3 * (size_t)NHP;
     return f * sizeof(float);
 }
 
@@ -662,8 +570,10 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
                 "ppo: cluster must be 0,1,2,4,8 or 16 (got %d)", cluster);
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
-        C = 2;   // one CTA per network half is the throughput configuration (large populations)
-        while (C < 8 && (long long)P * C * 2 <= sms && mb / C >= 32) C *= 2;
+        C = 2;      // one CTA per network half is the throughput configuration (large populations)
+        // 16-CTA clusters are non-portable: at most one fits a GPC, so only use them for <= 8 tasks
+        const int cmax = (P <= 8) ? 16 : 8;
+        while (C < cmax && (long long)P * C * 2 <= sms && mb / C >= 32) C *= 2;
     }
     const bool big = (L.OP > 64) || (A > 16) || (M > 16);
     pl.C = C; pl.G = C == 1 ? 1 : C / 2;
@@ -679,8 +589,15 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
         pl.NHP = round_up(i0 > i1 ? i0 : i1, 64);   // covers both the reference-order half and its padded image
     }
     pl.DB = (C > 1) && !big;
-    pl.RED = (C > 1) && !big;
-    pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS, pl.RED, pl.NHP);
+    pl.fast = (C > 1) && !big && L.OP <= 48 && pl.RC * (pl.RSG / 4) <= 4 * NTHREADS;
+    pl.stage_floats = 0;
+    if (pl.fast) {
+        const int s0 = k3_fast_stage_floats(L.OP, A), s1 = k3_fast_stage_floats(L.OP, M);
+        pl.stage_floats = s0 > s1 ? s0 : s1;
+        pl.smem = k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G);
+    } else {
+        pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS);
+    }
     PGM_REQUIRE(pl.smem <= 227 * 1024, "ppo: configuration needs %zu B of shared memory (O=%d, cluster=%d)", pl.smem, O, C);
     size_t off = 0;
     auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -688,13 +605,17 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     pl.off_gpart = seg((size_t)P * 2 * pl.G * pl.NHP * sizeof(float));
     pl.off_ssq = seg((size_t)P * 16 * sizeof(float));
     pl.off_lpart = seg((size_t)P * 16 * 4 * sizeof(float));
+#ifdef PGM_K3_TRACE
+    pl.off_trace = seg((size_t)P * 16 * 4 * 16 * 2 * sizeof(long long));
+#else
+    pl.off_trace = 0;
+#endif
     pl.total = off;
     return PGM_OK;
 }
 
-template <int C, int TM, int KG1, int NA, bool DB, bool RED>
-static int k3_launch_t(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
-    auto kern = k3_ppo_kernel<C, TM, KG1, NA, DB, RED>;
+template <typename Kern>
+static int k3_launch_k(Kern kern, int C, const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
     PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     if (C > 8) PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -709,11 +630,17 @@ static int k3_launch_t(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
 
 template <int C>
 static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
-    if (pl.KG1 == 6) return k3_launch_t<C, 2, 6, 2, false, false>(a, pl, P, st);
-    if constexpr (C > 1) {   // small networks on a cluster: double-buffered gather + redundant Adam
-        return pl.TM == 2 ? k3_launch_t<C, 2, 1, 1, true, true>(a, pl, P, st) : k3_launch_t<C, 4, 1, 1, true, true>(a, pl, P, st);
+    if constexpr (C > 1) {
+        if (pl.fast)
+            return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2>, C, a, pl, P, st)
+                              : k3_launch_k(k3_ppo_fast_kernel<C, 4>, C, a, pl, P, st);
+        if (pl.KG1 == 6) return k3_launch_k(k3_ppo_kernel<C, 2, 6, 2, false>, C, a, pl, P, st);
+        return pl.TM == 2 ? k3_launch_k(k3_ppo_kernel<C, 2, 1, 1, true>, C, a, pl, P, st)
+                          : k3_launch_k(k3_ppo_kernel<C, 4, 1, 1, true>, C, a, pl, P, st);
     } else {
-        return pl.TM == 2 ? k3_launch_t<C, 2, 1, 1, false, false>(a, pl, P, st) : k3_launch_t<C, 4, 1, 1, false, false>(a, pl, P, st);
+        if (pl.KG1 == 6) return k3_launch_k(k3_ppo_kernel<1, 2, 6, 2, false>, 1, a, pl, P, st);
+        return pl.TM == 2 ? k3_launch_k(k3_ppo_kernel<1, 2, 1, 1, false>, 1, a, pl, P, st)
+                          : k3_launch_k(k3_ppo_kernel<1, 4, 1, 1, false>, 1, a, pl, P, st);
     }
 }
 
@@ -752,6 +679,9 @@ extern "C" size_t pgm_ppo_workspace_bytes(int P, int S, int O, int A, int M, int
     seg((size_t)P * 2 * G * NHP * sizeof(float));
     seg((size_t)P * 16 * sizeof(float));
     seg((size_t)P * 64 * sizeof(float));
+#ifdef PGM_K3_TRACE
+    seg((size_t)P * 16 * 4 * 16 * 2 * sizeof(long long));
+#endif
     return t;
 }
 
@@ -778,9 +708,14 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_step = adam_step; a.lr = lr;
     a.rec = (const float *)(ws + pl.off_rec); a.perm = perm; a.losses = losses;
     a.gpart = (float *)(ws + pl.off_gpart); a.ssq = (float *)(ws + pl.off_ssq); a.lpart = (float *)(ws + pl.off_lpart);
+#ifdef PGM_K3_TRACE
+    a.trace = (long long *)(ws + pl.off_trace);
+#else
+    a.trace = nullptr;
+#endif
     a.grad_out = grad_out; a.perm_shared = perm_shared; a.E = E; a.B = B; a.mb = mb; a.S = S;
     a.grad_only = grad_out != nullptr; a.nsteps = a.grad_only ? 1 : E * B;
-    a.Rg = pl.Rg; a.RSG = pl.RSG; a.RSS = pl.RSS; a.NHP = pl.NHP; a.hy = *hy; a.L = NetLayout(O, A, M);
+    a.Rg = pl.Rg; a.RSG = pl.RSG; a.RSS = pl.RSS; a.NHP = pl.NHP; a.stage_floats = pl.stage_floats; a.hy = *hy; a.L = NetLayout(O, A, M);
     {
         const size_t total = (size_t)P * S * pl.RSG;
         int blocks = (int)((total + 255) / 256);
