@@ -98,3 +98,81 @@ def host_rng_streams(j, T, N, A, epochs, eps_dtype=torch.float64):
 def linear_lr(lr0, j, lr_decay_ratio, total_num_updates):
     """a2c_ppo_acktr/utils.py:46-50 called as mopg.py:97-101."""
     return lr0 - (lr0 * ((j * lr_decay_ratio) / float(total_num_updates)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Synthetic optimisation histories for the selection path (SURVEY.md section 8(d), C1 / C3)
+# ---------------------------------------------------------------------------------------------
+class ObjSample:
+    """Objective-only stand-in for a Sample: selection reads nothing but .objs / .optgraph_id."""
+
+    def __init__(self, objs, optgraph_id=None):
+        self.env_params = None
+        self.actor_critic = None
+        self.agent = None
+        self.objs = objs
+        self.optgraph_id = optgraph_id
+
+
+class SelectionArgs:
+    """The argparse fields selection reads, with the reference's launch-script values
+    (scripts/walker2d-v2.py:38-49 for 2 objectives, scripts/hopper-v3.py:36-48 for 3)."""
+
+    def __init__(self, obj_num, **kw):
+        self.obj_num = obj_num
+        self.min_weight, self.max_weight = 0.0, 1.0
+        self.num_processes = 4
+        self.pbuffer_size = 2
+        self.num_weight_candidates = 7
+        if obj_num == 2:
+            self.num_tasks, self.delta_weight, self.pbuffer_num, self.sparsity = 6, 0.2, 100, 1.0
+        else:
+            self.num_tasks, self.delta_weight, self.pbuffer_num, self.sparsity = 15, 0.25, 20, 1e6
+        self.__dict__.update(kw)
+
+
+def _response(rng, objs, w):
+    """Toy training response: gain grows with the weight on that objective and saturates."""
+    gain = 3.0 * (0.1 + 1.5 * w) * np.exp(-np.linalg.norm(objs) / 150.0)   # always positive: objectives only grow
+    return gain + rng.normal(0.0, 0.1, size=objs.shape)
+
+
+def run_selection_history(classes, args, generations, seed, update_iter=3, warmup_gens=3, on_generation=None):
+    """Drive EP / Population / OptGraph classes (the product's or the reference's) through a
+    synthetic run shaped like morl/morl.py:55-177; `on_generation(g, state)` sees every call's
+    inputs and outputs. classes: dict(EP, Population, OptGraph, Scalarization)."""
+    import torch
+    rng = np.random.RandomState(seed)
+    M = args.obj_num
+    ep, population, graph = classes["EP"](), classes["Population"](args), classes["OptGraph"]()
+    template = classes["Scalarization"](num_objs=M, weights=np.ones(M) / M)
+    elite_batch, scal_batch = [], []
+    for w in simplex_weights(M, args.delta_weight):
+        s = ObjSample(rng.uniform(5.0, 10.0, M))
+        sc = classes["Scalarization"](num_objs=M, weights=w)
+        s.optgraph_id = graph.insert(sc.weights.clone(), s.objs.copy(), -1)   # roots carry torch weights
+        elite_batch.append(s); scal_batch.append(sc)
+    for g in range(generations):
+        iters = update_iter * (warmup_gens if g == 0 else 1)
+        all_samples, offspring = [], []
+        for elite, sc in zip(elite_batch, scal_batch):
+            w = sc.weights.detach().numpy().astype(np.float64)
+            prev, objs = elite.optgraph_id, np.array(elite.objs, dtype=np.float64)
+            for it in range(iters):
+                objs = objs + _response(rng, objs, w)
+                s = ObjSample(objs.copy())
+                all_samples.append(s)
+                if (it + 1) % update_iter == 0:
+                    prev = graph.insert(w.copy(), objs.copy(), prev)
+                    s.optgraph_id = prev
+                    offspring.append(s)
+        ep.update(all_samples)
+        population.update(offspring)
+        np.random.seed(1000 + g)          # the 3-objective candidate order consumes numpy's global RNG
+        elite_batch, scal_batch, predicted = population.prediction_guided_selection(args, g, ep, graph, template)
+        if on_generation is not None:
+            on_generation(g, dict(ep=ep, population=population, graph=graph, elites=elite_batch,
+                                  scalarizations=scal_batch, predicted=predicted))
+        if len(elite_batch) == 0:
+            break
+    return ep, population, graph

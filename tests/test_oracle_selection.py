@@ -1,0 +1,75 @@
+"""Pin oracle/selection_oracle.py against outputs of the unmodified reference
+(tests/golden/selection_*.npz, made by tests/golden/make_golden_selection.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import selection_oracle as so
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def kats():
+    return np.load(os.path.join(GOLDEN, "selection_kats.npz"))
+
+
+def test_helper_known_answers_bit_exact(kats):
+    for i in range(int(kats["n_kat"])):
+        pts = kats[f"kat{i}_pts"]
+        idx = so.get_ep_indices(pts)
+        assert idx == kats[f"kat{i}_ep_idx"].tolist()
+        if pts.shape[1] == 2:
+            assert so.hv2d(pts) == float(kats[f"kat{i}_hv"])
+            assert so.sparsity2d(pts) == float(kats[f"kat{i}_sp"])
+        elif f"kat{i}_hv" in kats:
+            ep = pts[idx]
+            assert so.hv3d(ep) == float(kats[f"kat{i}_hv"])
+            assert so.hv3d(pts[(pts >= 0).all(1)]) == float(kats[f"kat{i}_hv_all"])   # dominated points included
+            assert so.sparsity_md(ep) == float(kats[f"kat{i}_sp"])
+            upd = np.array(so.update_ep(list(ep), kats[f"kat{i}_new"]))
+            assert np.array_equal(upd, kats[f"kat{i}_upd"])
+
+
+def test_survey_known_answers():
+    # values the survey obtained from the reference
+    pts3 = [[1, 2, 3], [3, 2, 1], [2, 2, 2], [.5, .5, 4]]
+    assert so.hv3d(pts3) == 12.25 and so.sparsity_md(pts3) == 2.5
+    pts2 = [[1, 5], [3, 4], [2, 4.5], [2, 2], [4, 1], [-1, 9], [3, 4]]
+    assert so.get_ep_indices(pts2) in ([0, 2, 1, 6, 4], [0, 2, 6, 1, 4])
+    assert so.hv2d(pts2) == 14.5 and so.sparsity2d(pts2) == 3.125
+    r = np.random.RandomState(0).uniform(0, 10, (200, 3))
+    ep = r[so.get_ep_indices(r)]
+    assert len(ep) == 15 and so.hv3d(ep) == 955.8675 and so.sparsity_md(ep) == 3.5985615333939576
+
+
+@pytest.mark.parametrize("name,M", [("selection_2d.npz", 2), ("selection_3d.npz", 3)])
+def test_greedy_rounds_bit_exact(name, M):
+    """Given the reference's own candidate predictions, the restated scoring + greedy pick reproduces
+    every hv / sparsity value and every chosen index bit for bit."""
+    z = np.load(os.path.join(GOLDEN, name))
+    gens = int(z["meta"][1])
+    alpha = float(z["args_f"][0]); num_tasks = int(z["args"][0])
+    for g in (range(gens) if M == 2 else [0]):      # 3-D scoring is O(C*E^2) in pure Python: one generation,
+        n_rounds = int(z[f"g{g}_n_rounds"])          # three rounds on the CPU; the GPU test covers all of them
+        rounds = n_rounds if M == 2 else 3
+        pred = z[f"g{g}_cand_pred"]
+        sel = so.greedy_select_2d if M == 2 else so.greedy_select_3d
+        best, hvs, sps = sel(z[f"g{g}_round0_vep"], pred, alpha, min(num_tasks, rounds))
+        for r in range(rounds):
+            assert np.array_equal(hvs[r], z[f"g{g}_round{r}_hv"]), (g, r)
+            assert np.array_equal(sps[r], z[f"g{g}_round{r}_sparsity"]), (g, r)
+            # the chosen candidate's prediction is what the reference reports as predicted offspring
+            assert np.array_equal(pred[best[r]], z[f"g{g}_predicted"][r])
+
+
+def test_fit_matches_reference_call():
+    """`fit_scipy` restates the reference's least_squares call: same theta on the stored fit inputs."""
+    z = np.load(os.path.join(GOLDEN, "selection_2d.npz"))
+    for g in (0, 3):
+        for i in range(0, int(z[f"g{g}_n_fits"]), 7):
+            pre = f"g{g}_fit{i}_"
+            res = so.fit_scipy(z[pre + "x"], z[pre + "y"], z[pre + "w"], z[pre + "ub"])
+            assert np.array_equal(res.x, z[pre + "theta"]) and res.status == int(z[pre + "status"])
+            assert np.array_equal(so.upper_bounds(z[pre + "y"]), z[pre + "ub"])
