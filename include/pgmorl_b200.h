@@ -132,6 +132,40 @@ int pgm_ppo_grad_f32(const float *params, const float *obs, size_t obs_task_stri
                      float *losses, void *workspace, size_t workspace_bytes, int cluster, int P,
                      int S, int O, int A, int M, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * K5  Pareto filtering, exact hypervolume / sparsity, greedy candidate pick (all FLOAT64, and
+ * bit-exact with the reference: same summation order, separate multiply / add, no FMA contraction).
+ */
+
+/* Replaces utils.get_ep_indices / check_dominated (morl/utils.py:24-39), the core of EP.update
+ * (morl/ep.py:23-31). objs [n,M]; keep_idx [2n] int32: the first n_keep entries return the indices
+ * of the non-dominated points with all objectives >= 0, ordered by ascending objective 0 (ties by
+ * index); the upper n entries are scratch. n_keep [1] out (device). */
+int pgm_ep_filter_f64(const double *objs, int n, int M, int32_t *keep_idx, int32_t *n_keep, void *stream);
+
+/* Metrics of one point set, out[0] = hypervolume, out[1] = sparsity (device).
+ *   M == 2: Population.compute_hypervolume / compute_sparsity (morl/population_2d.py:185-202):
+ *           Pareto-filter, then closed forms on the front sorted by objective 0.
+ *   M == 3: utils.compute_hypervolume (InnerHyperVolume, morl/hypervolume.py:41-153, round(hv,4))
+ *           and utils.compute_sparsity (morl/utils.py:87-100) of the given front (all coords >= 0).
+ * workspace >= pgm_select_workspace_bytes(n, 1, M, 1). */
+int pgm_front_metrics_f64(const double *pts, int n, int M, double *out, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/* Replaces evaluate_hv / evaluate_sparsity and the greedy loop of prediction_guided_selection
+ * (morl/population_2d.py:207-224,264-302; morl/population_3d.py:206-214,294-331, update_ep
+ * morl/utils.py:42-65). ep [E,M] = current archive front (ordered by objective 0); cand [C,M] =
+ * predicted objectives of every candidate (sample, weight) pair.
+ * Per round r < num_tasks: hv[r,c], sparsity[r,c] of EP_r + {cand c} for unmasked c (0 for masked),
+ * best_ids[r] = first argmax of hv - alpha*sparsity (or -1 when no candidate is left, then stops);
+ * EP_{r+1} = EP_r with the winner's prediction folded in. n_front [1] out: size of the final
+ * virtual front, written to front_out [E+num_tasks, M] (both optional / may be NULL). */
+size_t pgm_select_workspace_bytes(int E, int C, int M, int num_tasks);
+int pgm_select_greedy_f64(const double *ep, int E, const double *cand, int C, int M, double alpha,
+                          int num_tasks, int32_t *best_ids, double *hv, double *sparsity,
+                          double *front_out, int32_t *n_front, void *workspace, size_t workspace_bytes,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

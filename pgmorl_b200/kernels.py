@@ -123,3 +123,74 @@ def ppo_grad(params, obs, action, logp_old, value_old, returns, adv, idx, dims: 
                                  C.byref(hyper), ptr(grad), ptr(losses), wp, wn, cluster, P, S, dims.obs, dims.act,
                                  dims.obj, _stream()))
     return grad, losses
+
+
+# ---------------------------------------------------------------------------------------------
+# K5: Pareto filter, hypervolume / sparsity, greedy pick (float64, bit-exact with the reference)
+# ---------------------------------------------------------------------------------------------
+def _dev_f64(x, device=None):
+    import numpy as np
+    if isinstance(x, torch.Tensor):
+        t = x.to(dtype=torch.float64)
+        return t.cuda() if not t.is_cuda else t.contiguous()
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    return torch.from_numpy(a).to(device or "cuda")
+
+
+def _ws(nbytes, device):
+    t = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    return t, _aligned(t)
+
+
+def ep_filter(objs):
+    """utils.get_ep_indices on the GPU. objs [n,M] (host or device) -> numpy int64 indices of the
+    non-dominated, non-negative points in ascending objective-0 order."""
+    import numpy as np
+    if len(objs) == 0:
+        return np.zeros(0, dtype=np.int64)
+    d = _dev_f64(objs)
+    n, M = d.shape
+    idx = torch.empty(2 * n, dtype=torch.int32, device=d.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=d.device)
+    check(lib().pgm_ep_filter_f64(ptr(d), n, M, ptr(idx), ptr(cnt), _stream()))
+    k = int(cnt.item())
+    return idx[:k].cpu().numpy().astype(np.int64)
+
+
+def front_metrics(pts):
+    """(hypervolume, sparsity) of a point set: Population2d semantics for M=2, utils.* for M=3."""
+    if len(pts) == 0:
+        return 0.0, 0.0
+    d = _dev_f64(pts)
+    n, M = d.shape
+    out = torch.empty(2, dtype=torch.float64, device=d.device)
+    nb = lib().pgm_select_workspace_bytes(n, 1, M, 1)
+    ws, (wp, wn) = _ws(nb, d.device)
+    check(lib().pgm_front_metrics_f64(ptr(d), n, M, ptr(out), wp, wn, _stream()))
+    h, s = out.cpu().tolist()
+    return h, s
+
+
+def select_greedy(ep, cand, alpha, num_tasks):
+    """Greedy prediction-guided pick. ep [E,M] archive front, cand [C,M] predicted objectives.
+    Returns (best_ids [num_tasks] (-1 = no candidate left), hv [num_tasks,C], sparsity [num_tasks,C],
+    final virtual front [n,M]) as numpy arrays."""
+    import numpy as np
+    cand_d = _dev_f64(cand)
+    C, M = cand_d.shape
+    ep = np.asarray(ep, dtype=np.float64).reshape(-1, M)
+    E = ep.shape[0]
+    ep_d = _dev_f64(ep) if E else torch.zeros(1, M, dtype=torch.float64, device=cand_d.device)
+    dev = cand_d.device
+    best = torch.empty(num_tasks, dtype=torch.int32, device=dev)
+    hv = torch.empty(num_tasks, max(C, 1), dtype=torch.float64, device=dev)
+    sp = torch.empty(num_tasks, max(C, 1), dtype=torch.float64, device=dev)
+    front = torch.empty(E + num_tasks + 1, M, dtype=torch.float64, device=dev)
+    nfront = torch.zeros(1, dtype=torch.int32, device=dev)
+    nb = lib().pgm_select_workspace_bytes(E, C, M, num_tasks)
+    ws, (wp, wn) = _ws(nb, dev)
+    check(lib().pgm_select_greedy_f64(ptr(ep_d), E, ptr(cand_d), C, M, float(alpha), num_tasks, ptr(best), ptr(hv),
+                                      ptr(sp), ptr(front), ptr(nfront), wp, wn, _stream()))
+    nf = int(nfront.item())
+    return (best.cpu().numpy().astype(np.int64), hv[:, :C].cpu().numpy(), sp[:, :C].cpu().numpy(),
+            front[:nf].cpu().numpy())

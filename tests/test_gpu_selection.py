@@ -1,0 +1,92 @@
+"""GPU parity tests of K5 (and K4) against the oracle and the reference goldens, through the C ABI.
+Bar: bit-exact for hypervolume, sparsity, Pareto membership and selected indices (float64, same
+summation order as the reference)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import selection_oracle as so
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_ep_filter_and_metrics_known_answers():
+    from pgmorl_b200 import kernels as K
+    z = np.load(os.path.join(GOLDEN, "selection_kats.npz"))
+    for i in range(int(z["n_kat"])):
+        pts = z[f"kat{i}_pts"]
+        idx = K.ep_filter(pts)
+        ref = z[f"kat{i}_ep_idx"]
+        # same set; same order wherever objective 0 is not tied (numpy's unstable argsort breaks ties arbitrarily)
+        assert sorted(idx.tolist()) == sorted(ref.tolist())
+        assert np.array_equal(pts[idx][:, 0], pts[ref][:, 0])
+        if pts.shape[1] == 2:
+            hv, sp = K.front_metrics(pts)
+            assert hv == float(z[f"kat{i}_hv"]) and sp == float(z[f"kat{i}_sp"])
+        elif f"kat{i}_hv" in z:
+            ep = pts[ref]
+            hv, sp = K.front_metrics(ep)
+            assert hv == float(z[f"kat{i}_hv"]) and sp == float(z[f"kat{i}_sp"])
+            hv_all, _ = K.front_metrics(pts[(pts >= 0).all(1)])      # dominated points inside the set
+            assert hv_all == float(z[f"kat{i}_hv_all"])
+
+
+def test_metrics_random_sets_match_oracle():
+    from pgmorl_b200 import kernels as K
+    rng = np.random.RandomState(7)
+    for n in (1, 2, 3, 17, 64, 300):
+        p2 = rng.uniform(0, 50, (n, 2)); p3 = rng.uniform(0, 50, (n, 3))
+        if n > 3:
+            p2[1] = p2[0]; p3[2, 0] = p3[1, 0]; p3[3, 1:] = p3[1, 1:]
+        assert K.front_metrics(p2) == (so.hv2d(p2), so.sparsity2d(p2))
+        assert K.front_metrics(p3) == (so.hv3d(p3), so.sparsity_md(p3))
+    assert K.front_metrics(np.zeros((0, 2))) == (0.0, 0.0)
+
+
+@pytest.mark.parametrize("name,M", [("selection_2d.npz", 2), ("selection_3d.npz", 3)])
+def test_greedy_selection_bit_exact_vs_reference(name, M):
+    """Every round's hv / sparsity array and every chosen candidate equal the reference's, for every
+    generation of the recorded history (candidate predictions taken from the reference, so K5 is
+    tested independently of the K4 fit)."""
+    from pgmorl_b200 import kernels as K
+    z = np.load(os.path.join(GOLDEN, name))
+    gens = int(z["meta"][1])
+    alpha = float(z["args_f"][0]); num_tasks = int(z["args"][0])
+    for g in range(gens):
+        pred = z[f"g{g}_cand_pred"]
+        best, hv, sp, front = K.select_greedy(z[f"g{g}_round0_vep"], pred, alpha, num_tasks)
+        n_rounds = int(z[f"g{g}_n_rounds"])
+        assert n_rounds == num_tasks
+        for r in range(n_rounds):
+            assert np.array_equal(hv[r], z[f"g{g}_round{r}_hv"]), (g, r)
+            assert np.array_equal(sp[r], z[f"g{g}_round{r}_sparsity"]), (g, r)
+            assert np.array_equal(pred[best[r]], z[f"g{g}_predicted"][r]), (g, r)
+            if r + 1 < n_rounds:
+                mask = z[f"g{g}_round{r + 1}_mask"]
+                assert not mask[best[r]] and mask.sum() == len(pred) - (r + 1)
+
+
+def test_greedy_edge_cases():
+    from pgmorl_b200 import kernels as K
+    # fewer candidates than tasks: stops with -1 ("Too few candidates", population_2d.py:287-289)
+    ep = np.array([[1.0, 5.0], [3.0, 2.0]])
+    cand = np.array([[2.0, 4.0], [-1.0, 9.0]])
+    best, hv, sp, front = K.select_greedy(ep, cand, 1.0, 4)
+    ob, ohv, osp = so.greedy_select_2d(ep, cand, 1.0, 4)
+    assert best.tolist() == ob + [-1] * (4 - len(ob))
+    for r in range(len(ob)):
+        assert np.array_equal(hv[r], ohv[r]) and np.array_equal(sp[r], osp[r])
+    # empty archive
+    best, hv, sp, front = K.select_greedy(np.zeros((0, 2)), cand, 1.0, 1)
+    ob, ohv, osp = so.greedy_select_2d([], cand, 1.0, 1)
+    assert best.tolist() == ob and np.array_equal(hv[0], ohv[0]) and np.array_equal(sp[0], osp[0])
+    # 3 objectives, duplicates and a candidate equal to an archive point
+    ep3 = np.array([[1.0, 2.0, 3.0], [2.0, 2.0, 2.0], [3.0, 2.0, 1.0]])
+    c3 = np.array([[2.0, 2.0, 2.0], [2.5, 2.5, 0.5], [5.0, -1.0, 5.0], [0.5, 0.5, 4.0]])
+    best, hv, sp, front = K.select_greedy(ep3, c3, 1e6, 3)
+    ob, ohv, osp = so.greedy_select_3d(ep3, c3, 1e6, 3)
+    assert best.tolist() == ob
+    for r in range(3):
+        assert np.array_equal(hv[r], ohv[r]) and np.array_equal(sp[r], osp[r])
