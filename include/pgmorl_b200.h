@@ -133,6 +133,19 @@ int pgm_ppo_grad_f32(const float *params, const float *obs, size_t obs_task_stri
                      int S, int O, int A, int M, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * K4  batched fit of the hyperbolic prediction model (FLOAT64, one warp per fit).
+ * Replaces the scipy.optimize.least_squares call of predict_hyperbolic
+ * (morl/population_2d.py:56-108, morl/population_3d.py:51-103): bounded Trust Region Reflective,
+ * loss='soft_l1', f_scale=20, start ones(4), bounds ([0,.1,-5,-500], ub), max_nfev 400.
+ *   x, y, w [F,Kmax]: per fit the training weights / objective gains / Gaussian point weights,
+ *   k_len [F] valid points per fit, ub [F,4] upper bounds (A_ub, 20, 5, 500)
+ *   theta [F,4], status [F] (scipy codes 0..4), nfev [F], cost [F] out.
+ */
+int pgm_fit_hyperbolic_f64(const double *x, const double *y, const double *w, const int32_t *k_len,
+                           const double *ub, double *theta, int32_t *status, int32_t *nfev, double *cost,
+                           int F, int Kmax, void *stream);
+
+/* ---------------------------------------------------------------------------
  * K5  Pareto filtering, exact hypervolume / sparsity, greedy candidate pick (all FLOAT64, and
  * bit-exact with the reference: same summation order, separate multiply / add, no FMA contraction).
  */

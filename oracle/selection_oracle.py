@@ -238,3 +238,293 @@ def fit_scipy(x, y, w, ub=None):
     ub = upper_bounds(y) if ub is None else ub
     return least_squares(lambda p, xx, yy: residual(p, xx, yy, w), np.ones(4), loss="soft_l1", f_scale=20.0,
                          args=(x, y), jac=lambda p, xx, yy: jacobian(p, xx, yy, w), bounds=(LB, ub))
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy restatement of scipy's bounded Trust Region Reflective path for this 4-parameter fit
+# (scipy/optimize/_lsq/least_squares.py:900-1030, trf.py:129-412, common.py). With numpy's own
+# LAPACK SVD it reproduces scipy bit for bit (tests/test_oracle_selection.py); the CUDA port
+# (csrc/k4_fit.cu) follows it line by line with a one-sided Jacobi SVD.
+# ------------------------------------------------------------------------------------------------
+EPS = np.finfo(float).eps
+F_SCALE = 20.0
+
+
+def _soft_l1(f, cost_only=False):
+    z = (f / F_SCALE) ** 2
+    t = 1 + z
+    rho0 = 2 * (t ** 0.5 - 1)
+    if cost_only:
+        return 0.5 * F_SCALE ** 2 * np.sum(rho0)
+    return rho0 * F_SCALE ** 2, t ** -0.5, (-0.5 * t ** -1.5) / F_SCALE ** 2
+
+
+def _scale_robust(J, f, rho1, rho2):
+    js = rho1 + 2 * rho2 * f ** 2
+    js[js < EPS] = EPS
+    js = js ** 0.5
+    return J * js[:, None], f * (rho1 / js)
+
+
+def _cl_scaling(x, g, lb, ub):
+    v = np.ones_like(x); dv = np.zeros_like(x)
+    m = g < 0
+    v[m] = ub[m] - x[m]; dv[m] = -1
+    m = g > 0
+    v[m] = x[m] - lb[m]; dv[m] = 1
+    return v, dv
+
+
+def _strictly_feasible(x, lb, ub, rstep):
+    xn = x.copy()
+    lower_dist, upper_dist = x - lb, ub - x
+    if rstep == 0:
+        lower, upper = x <= lb, x >= ub
+        xn[lower] = np.nextafter(lb[lower], ub[lower]); xn[upper] = np.nextafter(ub[upper], lb[upper])
+    else:
+        lt, ut = rstep * np.maximum(1, np.abs(lb)), rstep * np.maximum(1, np.abs(ub))
+        lower = lower_dist <= np.minimum(upper_dist, lt)
+        upper = upper_dist <= np.minimum(lower_dist, ut)
+        xn[lower] = lb[lower] + rstep * np.maximum(1, np.abs(lb[lower]))
+        xn[upper] = ub[upper] - rstep * np.maximum(1, np.abs(ub[upper]))
+    tight = (xn < lb) | (xn > ub)
+    xn[tight] = 0.5 * (lb[tight] + ub[tight])
+    return xn
+
+
+def _step_to_bound(x, s, lb, ub):
+    steps = np.full_like(x, np.inf)
+    nz = s != 0
+    with np.errstate(over="ignore"):
+        steps[nz] = np.maximum((lb - x)[nz] / s[nz], (ub - x)[nz] / s[nz])
+    mn = np.min(steps)
+    return mn, np.equal(steps, mn) * np.sign(s).astype(int)
+
+
+def _quad1d(Jh, g, s, diag, s0=None):
+    v = Jh.dot(s)
+    a = (np.dot(v, v) + np.dot(s * diag, s)) * 0.5
+    b = np.dot(g, s)
+    if s0 is None:
+        return a, b
+    u = Jh.dot(s0)
+    b += np.dot(u, v)
+    c = 0.5 * np.dot(u, u) + np.dot(g, s0)
+    b += np.dot(s0 * diag, s)
+    c += 0.5 * np.dot(s0 * diag, s0)
+    return a, b, c
+
+
+def _min_quad1d(a, b, lo, hi, c=0.0):
+    t = [lo, hi]
+    if a != 0:
+        ex = -0.5 * b / a
+        if lo < ex < hi:
+            t.append(ex)
+    t = np.asarray(t)
+    yv = t * (a * t + b) + c
+    i = np.argmin(yv)
+    return t[i], yv[i]
+
+
+def _eval_quad(Jh, g, s, diag):
+    Js = Jh.dot(s)
+    return 0.5 * (np.dot(Js, Js) + np.dot(s * diag, s)) + np.dot(s, g)
+
+
+def _solve_tr(n, m, uf, s, V, Delta, alpha0):
+    def phi_d(alpha):
+        denom = s ** 2 + alpha
+        pn = np.linalg.norm(suf / denom)
+        return pn - Delta, -np.sum(suf ** 2 / denom ** 3) / pn
+
+    suf = s * uf
+    full_rank = m >= n and s[-1] > EPS * m * s[0]
+    if full_rank:
+        p = -V.dot(uf / s)
+        if np.linalg.norm(p) <= Delta:
+            return p, 0.0
+    alpha_upper = np.linalg.norm(suf) / Delta
+    if full_rank:
+        phi, phip = phi_d(0.0)
+        alpha_lower = -phi / phip
+    else:
+        alpha_lower = 0.0
+    if not full_rank and alpha0 == 0:
+        alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+    else:
+        alpha = alpha0
+    for _ in range(10):
+        if alpha < alpha_lower or alpha > alpha_upper:
+            alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+        phi, phip = phi_d(alpha)
+        if phi < 0:
+            alpha_upper = alpha
+        ratio = phi / phip
+        alpha_lower = max(alpha_lower, alpha - ratio)
+        alpha -= (phi + Delta) * ratio / Delta
+        if np.abs(phi) < 0.01 * Delta:
+            break
+    p = -V.dot(suf / (s ** 2 + alpha))
+    p *= Delta / np.linalg.norm(p)
+    return p, alpha
+
+
+def _select_step(x, Jh, diag, gh, p, ph, d, Delta, lb, ub, theta):
+    if np.all((x + p >= lb) & (x + p <= ub)):
+        return p, ph, -_eval_quad(Jh, gh, ph, diag)
+    p_stride, hits = _step_to_bound(x, p, lb, ub)
+    rh = np.copy(ph)
+    rh[hits.astype(bool)] *= -1
+    r = d * rh
+    p = p * p_stride; ph = ph * p_stride
+    x_on = x + p
+    a_ = np.dot(rh, rh); b_ = np.dot(ph, rh); c_ = np.dot(ph, ph) - Delta ** 2
+    dd = np.sqrt(b_ * b_ - a_ * c_)
+    q = -(b_ + np.copysign(dd, b_))
+    t1, t2 = q / a_, c_ / q
+    to_tr = max(t1, t2)
+    to_bound, _ = _step_to_bound(x_on, r, lb, ub)
+    r_stride = min(to_bound, to_tr)
+    if r_stride > 0:
+        lo = (1 - theta) * p_stride / r_stride
+        hi = theta * to_bound if r_stride == to_bound else to_tr
+    else:
+        lo, hi = 0, -1
+    if lo <= hi:
+        a, b, c = _quad1d(Jh, gh, rh, diag, s0=ph)
+        r_stride, r_value = _min_quad1d(a, b, lo, hi, c=c)
+        rh = rh * r_stride + ph
+        r = rh * d
+    else:
+        r_value = np.inf
+    p = p * theta; ph = ph * theta
+    p_value = _eval_quad(Jh, gh, ph, diag)
+    agh = -gh
+    ag = d * agh
+    to_tr = Delta / np.linalg.norm(agh)
+    to_bound, _ = _step_to_bound(x, ag, lb, ub)
+    ag_stride = theta * to_bound if to_bound < to_tr else to_tr
+    a, b = _quad1d(Jh, gh, agh, diag)
+    ag_stride, ag_value = _min_quad1d(a, b, 0, ag_stride)
+    agh = agh * ag_stride; ag = ag * ag_stride
+    if p_value < r_value and p_value < ag_value:
+        return p, ph, -p_value
+    if r_value < p_value and r_value < ag_value:
+        return r, rh, -r_value
+    return ag, agh, -ag_value
+
+
+def trf_fit(x, y, w, ub, svd=None, max_nfev=400, ftol=1e-8, xtol=1e-8, gtol=1e-8):
+    """Restated least_squares(..., method='trf', loss='soft_l1', f_scale=20, bounds=(LB, ub)) from ones(4).
+    Returns (theta, status, nfev, cost)."""
+    svd = svd or (lambda A: np.linalg.svd(A, full_matrices=False))
+    lb = LB
+    fun = lambda p: residual(p, x, y, w)
+    jac = lambda p: jacobian(p, x, y, w)
+    xk = _strictly_feasible(np.ones(4), lb, ub, 1e-10)
+    f = fun(xk); nfev = 1
+    J = jac(xk)
+    m, n = J.shape
+    rho0, rho1, rho2 = _soft_l1(f)
+    cost = 0.5 * np.sum(rho0)
+    J, f = _scale_robust(J, f, rho1, rho2)
+    g = J.T.dot(f)
+    v, dv = _cl_scaling(xk, g, lb, ub)
+    Delta = np.linalg.norm(xk / v ** 0.5)
+    if Delta == 0:
+        Delta = 1.0
+    alpha = 0.0
+    status = None
+    while True:
+        v, dv = _cl_scaling(xk, g, lb, ub)
+        g_norm = np.linalg.norm(g * v, ord=np.inf)
+        if g_norm < gtol:
+            status = 1
+        if status is not None or nfev == max_nfev:
+            break
+        d = v ** 0.5
+        diag = g * dv
+        gh = d * g
+        f_aug = np.zeros(m + n); f_aug[:m] = f
+        J_aug = np.empty((m + n, n))
+        J_aug[:m] = J * d
+        Jh = J_aug[:m].copy()
+        J_aug[m:] = np.diag(diag ** 0.5)
+        U, s, Vt = svd(J_aug)
+        V = Vt.T
+        uf = U.T.dot(f_aug)
+        theta = max(0.995, 1 - g_norm)
+        actual = -1
+        while actual <= 0 and nfev < max_nfev:
+            ph, alpha = _solve_tr(n, m, uf, s, V, Delta, alpha)
+            p = d * ph
+            step, step_h, predicted = _select_step(xk, Jh, diag, gh, p, ph, d, Delta, lb, ub, theta)
+            x_new = _strictly_feasible(xk + step, lb, ub, 0)
+            f_new = fun(x_new); nfev += 1
+            shn = np.linalg.norm(step_h)
+            if not np.all(np.isfinite(f_new)):
+                Delta = 0.25 * shn
+                continue
+            cost_new = _soft_l1(f_new, cost_only=True)
+            actual = cost - cost_new
+            if predicted > 0:
+                ratio = actual / predicted
+            elif predicted == actual == 0:
+                ratio = 1
+            else:
+                ratio = 0
+            Delta_new = Delta
+            if ratio < 0.25:
+                Delta_new = 0.25 * shn
+            elif ratio > 0.75 and shn > 0.95 * Delta:
+                Delta_new = Delta * 2.0
+            step_norm = np.linalg.norm(step)
+            ft = actual < ftol * cost and ratio > 0.25
+            xt = step_norm < xtol * (xtol + np.linalg.norm(xk))
+            status = 4 if (ft and xt) else 2 if ft else 3 if xt else None
+            if status is not None:
+                break
+            alpha *= Delta / Delta_new
+            Delta = Delta_new
+        if actual > 0:
+            xk = x_new
+            f = f_new
+            cost = cost_new
+            J = jac(xk)
+            rho0, rho1, rho2 = _soft_l1(f)
+            J, f = _scale_robust(J, f, rho1, rho2)
+            g = J.T.dot(f)
+    if status is None:
+        status = 0
+    return xk, status, nfev, cost
+
+
+def jacobi_svd(A, sweeps=60):
+    """One-sided (Hestenes) Jacobi SVD, the algorithm of the CUDA port: returns (U, s, Vt) with s sorted
+    in descending order like LAPACK."""
+    A = np.array(A, dtype=np.float64)
+    n = A.shape[1]
+    V = np.eye(n)
+    for _ in range(sweeps):
+        rotated = False
+        for p in range(n - 1):
+            for q in range(p + 1, n):
+                al, be, ga = A[:, p] @ A[:, p], A[:, q] @ A[:, q], A[:, p] @ A[:, q]
+                if ga == 0.0 or abs(ga) <= 1e-16 * np.sqrt(al * be):
+                    continue
+                rotated = True
+                zeta = (be - al) / (2.0 * ga)
+                t = np.copysign(1.0, zeta) / (abs(zeta) + np.sqrt(1.0 + zeta * zeta))
+                c = 1.0 / np.sqrt(1.0 + t * t); sn = c * t
+                ap, aq = A[:, p].copy(), A[:, q].copy()
+                A[:, p], A[:, q] = c * ap - sn * aq, sn * ap + c * aq
+                vp, vq = V[:, p].copy(), V[:, q].copy()
+                V[:, p], V[:, q] = c * vp - sn * vq, sn * vp + c * vq
+        if not rotated:
+            break
+    s = np.sqrt((A * A).sum(0))
+    order = np.argsort(-s, kind="stable")
+    s = s[order]; A = A[:, order]; V = V[:, order]
+    U = np.where(s > 0, A / np.where(s > 0, s, 1.0), 0.0)
+    return U, s, V.T

@@ -194,3 +194,32 @@ def select_greedy(ep, cand, alpha, num_tasks):
     nf = int(nfront.item())
     return (best.cpu().numpy().astype(np.int64), hv[:, :C].cpu().numpy(), sp[:, :C].cpu().numpy(),
             front[:nf].cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# K4: batched hyperbolic-model fits (float64)
+# ---------------------------------------------------------------------------------------------
+def fit_hyperbolic(xs, ys, ws, ubs):
+    """Fit F models at once. xs/ys/ws: lists of 1-D arrays (ragged, K_f points each); ubs [F,4].
+    Returns (theta [F,4], status [F], nfev [F], cost [F]) as numpy arrays."""
+    import numpy as np
+    F = len(xs)
+    if F == 0:
+        return np.zeros((0, 4)), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+    klen = np.array([len(v) for v in xs], dtype=np.int32)
+    Kmax = max(int(klen.max()), 1)
+    pack = np.zeros((3, F, Kmax), dtype=np.float64)
+    for f in range(F):
+        k = klen[f]
+        pack[0, f, :k] = xs[f]; pack[1, f, :k] = ys[f]; pack[2, f, :k] = ws[f]
+    dev = torch.device("cuda")
+    d = torch.from_numpy(pack).to(dev)
+    kl = torch.from_numpy(klen).to(dev)
+    ub = _dev_f64(np.asarray(ubs, dtype=np.float64).reshape(F, 4))
+    theta = torch.empty(F, 4, dtype=torch.float64, device=dev)
+    status = torch.empty(F, dtype=torch.int32, device=dev)
+    nfev = torch.empty(F, dtype=torch.int32, device=dev)
+    cost = torch.empty(F, dtype=torch.float64, device=dev)
+    check(lib().pgm_fit_hyperbolic_f64(ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(kl), ptr(ub), ptr(theta), ptr(status),
+                                       ptr(nfev), ptr(cost), F, Kmax, _stream()))
+    return theta.cpu().numpy(), status.cpu().numpy().astype(np.int64), nfev.cpu().numpy().astype(np.int64), cost.cpu().numpy()

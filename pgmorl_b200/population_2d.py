@@ -1,0 +1,144 @@
+"""Performance-buffer population and prediction-guided task selection for 2 objectives
+(mirror of morl/population_2d.py:123-319, same public API).
+
+Host: buffer bookkeeping and candidate-weight generation (tiny, sequential). Device: every model fit
+of the call in one K4 launch, and the whole greedy scoring loop (exact sort-based hypervolume,
+sparsity, Pareto filtering, arg-max) in K5 -- float64, bit-exact with the reference's arithmetic."""
+from copy import deepcopy
+
+import numpy as np
+
+from . import kernels as K
+from .prediction import predict_population
+
+
+class Population:
+    def __init__(self, args):
+        self.sample_batch = []
+        self.pbuffer_num = args.pbuffer_num
+        self.pbuffer_size = args.pbuffer_size
+        self.dtheta = np.pi / 2.0 / self.pbuffer_num
+        self.z_min = np.zeros(args.obj_num)
+        self.pbuffers = None
+        self.pbuffer_dist = None
+        self.last_fits = None          # record of the most recent K4 launch (diagnostics / tests)
+
+    # ------------------------------------------------------------------ performance buffers
+    def insert_pbuffer(self, index, objs):
+        """Angular buffer = floor(arccos(f1/|f|) / dtheta); keep the pbuffer_size farthest points per buffer,
+        strict '<' so earlier samples win ties (population_2d.py:136-165)."""
+        f = objs - self.z_min
+        if np.min(f) < 1e-7:
+            return False
+        dist = np.linalg.norm(f)
+        buffer_id = int(np.arccos(np.clip(f[1] / dist, -1.0, 1.0)) // self.dtheta)
+        if buffer_id < 0 or buffer_id >= self.pbuffer_num:
+            return False
+        ids, dists = self.pbuffers[buffer_id], self.pbuffer_dist[buffer_id]
+        pos = next((i for i, dcur in enumerate(dists) if dcur < dist), None)
+        if pos is not None:
+            ids.insert(pos, index); dists.insert(pos, dist)
+            del ids[self.pbuffer_size:], dists[self.pbuffer_size:]
+            return True
+        if len(ids) < self.pbuffer_size:
+            ids.append(index); dists.append(dist)
+            return True
+        return False
+
+    def update(self, sample_batch):
+        """population = performance-buffer selection over (population + offspring) (population_2d.py:169-183)."""
+        everyone = self.sample_batch + sample_batch
+        self.pbuffers = [[] for _ in range(self.pbuffer_num)]
+        self.pbuffer_dist = [[] for _ in range(self.pbuffer_num)]
+        for i, sample in enumerate(everyone):
+            self.insert_pbuffer(i, sample.objs)
+        self.sample_batch = [everyone[i] for buf in self.pbuffers for i in buf]
+
+    # ------------------------------------------------------------------ metrics (device)
+    def compute_hypervolume(self, objs_batch):
+        return K.front_metrics(np.array(objs_batch, dtype=np.float64))[0]
+
+    def compute_sparsity(self, objs_batch):
+        return K.front_metrics(np.array(objs_batch, dtype=np.float64))[1]
+
+    def _score(self, candidates, mask, virtual_ep_objs_batch):
+        mask = np.asarray(mask, dtype=bool)
+        hv, sp = np.zeros(len(candidates)), np.zeros(len(candidates))
+        if mask.any():
+            pred = np.array([candidates[i]['prediction'] for i in np.nonzero(mask)[0]], dtype=np.float64)
+            _, h, s, _ = K.select_greedy(np.array(virtual_ep_objs_batch, dtype=np.float64).reshape(-1, 2), pred, 0.0, 1)
+            hv[mask], sp[mask] = h[0], s[0]
+        return hv, sp
+
+    def evaluate_hv(self, candidates, mask, virtual_ep_objs_batch):
+        return self._score(candidates, mask, virtual_ep_objs_batch)[0].tolist()
+
+    def evaluate_sparsity(self, candidates, mask, virtual_ep_objs_batch):
+        return self._score(candidates, mask, virtual_ep_objs_batch)[1].tolist()
+
+    # ------------------------------------------------------------------ selection
+    def _test_weights(self, opt_graph, sample, num_weights):
+        """num_weights unit vectors on an arc of +-45 degrees around the sample's last weight; drop those
+        outside the first quadrant or within 1e-3 of an existing successor's weight (population_2d.py:238-254)."""
+        center = opt_graph.weights[sample.optgraph_id]
+        angle_center = np.arctan2(center[1], center[0])
+        lo, hi = angle_center - np.pi / 4., angle_center + np.pi / 4.
+        succ_w = []
+        for s in opt_graph.succ[sample.optgraph_id]:
+            w = deepcopy(opt_graph.weights[s])
+            succ_w.append(w / np.linalg.norm(w))
+        out = []
+        for i in range(num_weights):
+            angle = lo + (hi - lo) / (num_weights - 1) * i
+            weight = np.array([np.cos(angle), np.sin(angle)])
+            if weight[0] >= -1e-7 and weight[1] >= -1e-7:
+                if not any(np.linalg.norm(w - weight) < 1e-3 for w in succ_w):
+                    out.append(weight)
+        return out
+
+    def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
+        """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_2d.py:229-304)."""
+        N = args.num_tasks
+        # ---- prediction: candidates = (sample, weight) pairs with their predicted objectives
+        samples, tests = [], []
+        for sample in self.sample_batch:
+            tw = self._test_weights(opt_graph, sample, args.num_weight_candidates)
+            if len(tw) > 0:
+                samples.append(sample); tests.append(tw)
+        preds, self.last_fits = predict_population(opt_graph, [s.optgraph_id for s in samples], tests, args.obj_num,
+                                                   cap_threshold=False)
+        candidates = []
+        for sample, tw, pr in zip(samples, tests, preds):
+            for w, p in zip(tw, pr):
+                candidates.append({'sample': sample, 'weight': w, 'prediction': p})
+        # ---- optimisation: greedy knapsack on the device
+        virtual_ep = np.array([np.asarray(s.objs, dtype=np.float64) for s in ep.sample_batch]).reshape(-1, args.obj_num)
+        elite_batch, scalarization_batch, predicted_offspring_objs = [], [], []
+        if len(candidates) == 0:
+            print('Too few candidates')
+            return elite_batch, scalarization_batch, predicted_offspring_objs
+        cand_pred = np.array([c['prediction'] for c in candidates], dtype=np.float64)
+        best_ids, self.last_hv, self.last_sparsity, _ = K.select_greedy(virtual_ep, cand_pred, args.sparsity, N)
+        for best_id in best_ids:
+            if best_id == -1:
+                print('Too few candidates')
+                break
+            c = candidates[int(best_id)]
+            elite_batch.append(c['sample'])
+            scalarization = deepcopy(scalarization_template)
+            scalarization.update_weights(c['weight'] / np.sum(c['weight']))
+            scalarization_batch.append(scalarization)
+            predicted_offspring_objs.append(deepcopy(c['prediction']))
+        self.last_candidates = candidates
+        return elite_batch, scalarization_batch, predicted_offspring_objs
+
+    def random_selection(self, args, scalarization_template):
+        """population_2d.py:309-319 (numpy global RNG, like the reference)."""
+        elite_batch, scalarization_batch = [], []
+        for _ in range(args.num_tasks):
+            elite_batch.append(self.sample_batch[np.random.choice(len(self.sample_batch))])
+            weights = np.random.uniform(args.min_weight, args.max_weight, args.obj_num)
+            scalarization = deepcopy(scalarization_template)
+            scalarization.update_weights(weights / np.sum(weights))
+            scalarization_batch.append(scalarization)
+        return elite_batch, scalarization_batch

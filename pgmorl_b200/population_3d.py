@@ -1,0 +1,167 @@
+"""Performance-buffer population and prediction-guided task selection for >= 3 objectives
+(mirror of morl/population_3d.py:115-345, same public API).
+
+The reference scores every candidate in its own OS process (population_3d.py:216-237); here one CTA per
+candidate computes update_ep + the exact slice-based hypervolume + sparsity, and the greedy loop never
+leaves the device (K5). All model fits of the call run in one K4 launch."""
+from copy import deepcopy
+
+import numpy as np
+
+from . import kernels as K
+from .prediction import predict_population
+from .utils import generate_weights_batch_dfs
+
+
+class Population:
+    def __init__(self, args):
+        self.sample_batch = []
+        self.pbuffer_size = args.pbuffer_size
+        self.obj_num = args.obj_num
+        self.z_min = np.zeros(args.obj_num)
+        self.pbuffer_vec = []
+        generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, 1.0 / (args.pbuffer_num - 1), [], self.pbuffer_vec)
+        for i in range(len(self.pbuffer_vec)):
+            self.pbuffer_vec[i] = self.pbuffer_vec[i] / np.linalg.norm(self.pbuffer_vec[i])
+        self.pbuffer_num = len(self.pbuffer_vec)
+        self.pbuffers = [[] for _ in range(self.pbuffer_num)]
+        self.pbuffer_dist = [[] for _ in range(self.pbuffer_num)]
+        self.last_fits = None
+
+    # ------------------------------------------------------------------ performance buffers
+    def find_buffer_id(self, f):
+        """First direction with the largest dot product (population_3d.py:129-135)."""
+        best, buffer_id = -np.inf, -1
+        for i in range(self.pbuffer_num):
+            dot = np.dot(self.pbuffer_vec[i], f)
+            if dot > best:
+                best, buffer_id = dot, i
+        return buffer_id
+
+    def insert_pbuffer(self, index, objs, enforce):
+        """population_3d.py:137-172."""
+        f = objs - self.z_min
+        if np.min(f) < 1e-7:
+            return False
+        dist = np.linalg.norm(f)
+        buffer_id = self.find_buffer_id(f)
+        ids, dists = self.pbuffers[buffer_id], self.pbuffer_dist[buffer_id]
+        pos = next((i for i, dcur in enumerate(dists) if dcur < dist), None)
+        if enforce:
+            if pos is None:
+                ids.append(index); dists.append(dist)
+            else:
+                ids.insert(pos, index); dists.insert(pos, dist)
+            return True
+        if pos is not None:
+            ids.insert(pos, index); dists.insert(pos, dist)
+            del ids[self.pbuffer_size:], dists[self.pbuffer_size:]
+            return True
+        if len(ids) < self.pbuffer_size:
+            ids.append(index); dists.append(dist)
+            return True
+        return False
+
+    def update(self, sample_batch):
+        everyone = self.sample_batch + sample_batch
+        self.pbuffers = [[] for _ in range(self.pbuffer_num)]
+        self.pbuffer_dist = [[] for _ in range(self.pbuffer_num)]
+        for i, sample in enumerate(everyone):
+            self.insert_pbuffer(i, sample.objs, False)
+        self.sample_batch = [everyone[i] for buf in self.pbuffers for i in buf]
+
+    # ------------------------------------------------------------------ metrics (device)
+    def evaluate_hypervolume_sparsity(self, candidates, mask, virtual_ep_objs_batch):
+        mask = np.asarray(mask, dtype=bool)
+        hv, sp = np.zeros(len(candidates)), np.zeros(len(candidates))
+        if mask.any():
+            pred = np.array([candidates[i]['prediction'] for i in np.nonzero(mask)[0]], dtype=np.float64)
+            ep = np.array(virtual_ep_objs_batch, dtype=np.float64).reshape(-1, self.obj_num)
+            _, h, s, _ = K.select_greedy(ep, pred, 0.0, 1)
+            hv[mask], sp[mask] = h[0], s[0]
+        return hv.tolist(), sp.tolist()
+
+    def evaluate_hypervolume_sparsity_parallel(self, args, candidates, mask, virtual_ep_objs_batch):
+        """Same call as the reference's process-per-candidate scorer; candidates are CTAs here."""
+        return self.evaluate_hypervolume_sparsity(candidates, mask, virtual_ep_objs_batch)
+
+    def evaluate_hv(self, candidates, mask, virtual_ep_objs_batch):
+        return self.evaluate_hypervolume_sparsity(candidates, mask, virtual_ep_objs_batch)[0]
+
+    def evaluate_sparsity(self, candidates, mask, virtual_ep_objs_batch):
+        return self.evaluate_hypervolume_sparsity(candidates, mask, virtual_ep_objs_batch)[1]
+
+    # ------------------------------------------------------------------ selection
+    def _test_weights(self, args, opt_graph, sample, grid):
+        """Centre weight + randomly ordered simplex-grid weights within 45 degrees of it, up to
+        num_weight_candidates, skipping weights an existing successor already used (population_3d.py:248-284).
+        Consumes numpy's global RNG exactly like the reference (np.random.shuffle)."""
+        num_weights = args.num_weight_candidates
+        center = opt_graph.weights[sample.optgraph_id]
+        center = center / np.sum(center)
+        succ_w = []
+        for s in opt_graph.succ[sample.optgraph_id]:
+            w = deepcopy(opt_graph.weights[s])
+            succ_w.append(w / np.sum(w))
+        used = lambda weight: any(np.linalg.norm(w - weight) < 1e-3 for w in succ_w)
+        out = []
+        if not used(center):
+            out.append(center)
+        order = np.array([i for i in range(len(grid))])
+        np.random.shuffle(order)
+        for i in range(len(order)):
+            if len(out) >= num_weights:
+                break
+            weight = grid[order[i]]
+            if np.linalg.norm(weight - center) < 1e-3:
+                continue
+            angle = np.arccos(np.clip(np.dot(center, weight) / np.linalg.norm(center) / np.linalg.norm(weight), -1.0, 1.0))
+            if angle < np.pi / 4.0 and not used(weight):
+                out.append(weight)
+        return out
+
+    def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
+        """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_3d.py:239-333)."""
+        N = args.num_tasks
+        samples, tests = [], []
+        for sample in self.sample_batch:
+            grid = []
+            generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
+            tw = self._test_weights(args, opt_graph, sample, grid)
+            if len(tw) > 0:
+                samples.append(sample); tests.append(tw)
+        preds, self.last_fits = predict_population(opt_graph, [s.optgraph_id for s in samples], tests, args.obj_num,
+                                                   cap_threshold=True)
+        candidates = []
+        for sample, tw, pr in zip(samples, tests, preds):
+            for w, p in zip(tw, pr):
+                candidates.append({'sample': sample, 'weight': w, 'prediction': p})
+        virtual_ep = np.array([np.asarray(s.objs, dtype=np.float64) for s in ep.sample_batch]).reshape(-1, args.obj_num)
+        elite_batch, scalarization_batch, predicted_offspring_objs = [], [], []
+        if len(candidates) == 0:
+            print('Too few candidates')
+            return elite_batch, scalarization_batch, predicted_offspring_objs
+        cand_pred = np.array([c['prediction'] for c in candidates], dtype=np.float64)
+        best_ids, self.last_hv, self.last_sparsity, _ = K.select_greedy(virtual_ep, cand_pred, args.sparsity, N)
+        for best_id in best_ids:
+            if best_id == -1:
+                print('Too few candidates')
+                break
+            c = candidates[int(best_id)]
+            elite_batch.append(c['sample'])
+            scalarization = deepcopy(scalarization_template)
+            scalarization.update_weights(c['weight'] / np.sum(c['weight']))
+            scalarization_batch.append(scalarization)
+            predicted_offspring_objs.append(deepcopy(c['prediction']))
+        self.last_candidates = candidates
+        return elite_batch, scalarization_batch, predicted_offspring_objs
+
+    def random_selection(self, args, scalarization_template):
+        elite_batch, scalarization_batch = [], []
+        for _ in range(args.num_tasks):
+            elite_batch.append(self.sample_batch[np.random.choice(len(self.sample_batch))])
+            weights = np.random.uniform(args.min_weight, args.max_weight, args.obj_num)
+            scalarization = deepcopy(scalarization_template)
+            scalarization.update_weights(weights / np.sum(weights))
+            scalarization_batch.append(scalarization)
+        return elite_batch, scalarization_batch

@@ -1,0 +1,101 @@
+"""Hyperbolic prediction model of PG-MORL (mirror of predict_hyperbolic / collect_nearest_data,
+morl/population_2d.py:12-118 and morl/population_3d.py:13-113), batched over the whole population.
+
+Host side (numpy, same expressions as the reference so the fit inputs are bit-identical): neighbourhood
+search in the opt-graph with the widening (threshold, sigma) schedule and the Gaussian point weights.
+Device side: ALL fits of a selection call (n_pop x M bounded robust least-squares problems) in one
+launch of K4 (csrc/k4_fit.cu). Predictions are then objs + f(test weight)."""
+import numpy as np
+
+from . import kernels as K
+
+
+class GraphView:
+    """Flat arrays over an OptGraph for repeated neighbourhood queries."""
+
+    def __init__(self, opt_graph):
+        self.objs = np.array([np.asarray(o, dtype=np.float64) for o in opt_graph.objs])
+        parents, children = [], []
+        for i, succ in enumerate(opt_graph.succ):           # data order of collect_nearest_data: by node, then by successor
+            for s in succ:
+                parents.append(i); children.append(s)
+        self.parent = np.array(parents, dtype=np.int64)
+        self.child = np.array(children, dtype=np.int64)
+        # successor weights normalised to sum 1 (population_2d.py:19) and their objective gains
+        self.edge_w = np.array([np.asarray(opt_graph.weights[s], dtype=np.float64) / np.sum(np.asarray(opt_graph.weights[s], dtype=np.float64))
+                                for s in children]).reshape(len(children), -1)
+        self.edge_dy = np.array([np.asarray(opt_graph.delta_objs[s], dtype=np.float64) for s in children]).reshape(len(children), -1)
+
+    def nearest_edges(self, k, threshold):
+        """Edges (i -> s) whose source node i lies within `threshold` (relative, per objective) of node k."""
+        ok = self.objs[k]
+        near = np.all(np.abs(ok - self.objs) < np.abs(ok) * threshold, axis=1)
+        return np.nonzero(near[self.parent])[0] if len(self.parent) else np.zeros(0, dtype=np.int64)
+
+
+def _enough_distinct(weights):
+    """More than 3 pairwise-distinct weights (L2 distance >= 1e-5), first-occurrence scan (population_2d.py:39-49)."""
+    cnt = 0
+    for i in range(len(weights)):
+        distinct = True
+        for j in range(i):
+            if np.linalg.norm(weights[i] - weights[j]) < 1e-5:
+                distinct = False
+                break
+        if distinct:
+            cnt += 1
+            if cnt > 3:
+                return True
+    return False
+
+
+def fit_inputs(view, k, obj_num, cap_threshold):
+    """Training data of the model of node k: per objective (x, y, w, ub). `cap_threshold` reproduces the
+    3-objective variant's stop at threshold >= 1 (population_3d.py:46); the 2-objective one widens until
+    more than 3 distinct weights are found (population_2d.py:50)."""
+    threshold, sigma = 0.1, 0.03
+    while True:
+        e = view.nearest_edges(k, threshold)
+        wd = view.edge_w[e]
+        if _enough_distinct(wd) or (cap_threshold and threshold >= 1.0):
+            break
+        threshold *= 2.0
+        sigma *= 2.0
+    ok = view.objs[k]
+    src = view.objs[view.parent[e]]
+    coef = np.empty(len(e))
+    for r in range(len(e)):                                   # same scalar expressions as population_2d.py:92-95
+        diff = np.abs(src[r] - ok)
+        dist = np.linalg.norm(diff / np.abs(ok))
+        coef[r] = np.exp(-((dist / sigma) ** 2) / 2.0)
+    out = []
+    for dim in range(obj_num):
+        x = wd[:, dim].copy()
+        y = view.edge_dy[e][:, dim].copy()
+        ub = np.array([np.clip(np.max(y) - np.min(y), 1.0, 500.0), 20.0, 5.0, 500.0])
+        out.append((x, y, coef.copy(), ub))
+    return out
+
+
+def model(x, A, a, b, c):
+    return A * (np.exp(a * (x - b)) - 1) / (np.exp(a * (x - b)) + 1) + c
+
+
+def predict_population(opt_graph, node_ids, test_weights_per_node, obj_num, cap_threshold):
+    """For every node: predicted objectives objs + delta(test weight) for each of its test weights.
+    test_weights_per_node[i] is an array [n_i, M] (any positive scaling; normalised to sum 1 here, as
+    population_2d.py:28-32). Returns (list of [n_i, M] prediction arrays, fit record dict)."""
+    view = GraphView(opt_graph)
+    xs, ys, ws, ubs = [], [], [], []
+    for k in node_ids:
+        for x, y, w, ub in fit_inputs(view, k, obj_num, cap_threshold):
+            xs.append(x); ys.append(y); ws.append(w); ubs.append(ub)
+    theta, status, nfev, cost = K.fit_hyperbolic(xs, ys, ws, ubs)        # all n_pop * M fits in one launch
+    preds = []
+    for i, k in enumerate(node_ids):
+        tw = np.array(test_weights_per_node[i], dtype=np.float64)
+        for row in tw:
+            row /= np.sum(row)
+        delta = np.transpose(np.array([model(tw.T[dim], *theta[i * obj_num + dim]) for dim in range(obj_num)]))
+        preds.append(np.array([view.objs[k] + delta[j] for j in range(len(tw))]))
+    return preds, dict(x=xs, y=ys, w=ws, ub=ubs, theta=theta, status=status, nfev=nfev, cost=cost)

@@ -28,3 +28,27 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def rebuild_selection_state(z, g, M):
+    """Product-side OptGraph / Population / EP holding exactly the state the reference had when it ran
+    prediction_guided_selection in generation g of a golden history."""
+    from pgmorl_b200.ep import EP
+    from pgmorl_b200.opt_graph import OptGraph
+    from pgmorl_b200.synthetic import ObjSample, SelectionArgs
+    from pgmorl_b200 import population_2d, population_3d
+    args = SelectionArgs(M)
+    graph = OptGraph()
+    W, O, prev = z[f"g{g}_graph_w"], z[f"g{g}_graph_objs"], z[f"g{g}_graph_prev"]
+    for i in range(len(O)):
+        graph.weights.append(W[i].copy()); graph.objs.append(O[i].copy()); graph.prev.append(int(prev[i]))
+        graph.delta_objs.append(np.zeros_like(O[i]) if prev[i] == -1 else O[i] - O[int(prev[i])])
+        graph.succ.append([])
+        if prev[i] != -1:
+            graph.succ[int(prev[i])].append(i)
+    pop = (population_2d if M == 2 else population_3d).Population(args)
+    pop.sample_batch = [ObjSample(o.copy(), int(i)) for o, i in zip(z[f"g{g}_pop_objs"], z[f"g{g}_pop_ids"])]
+    ep = EP()
+    ep.obj_batch = z[f"g{g}_ep_objs"].copy()
+    ep.sample_batch = np.array([ObjSample(o.copy()) for o in ep.obj_batch], dtype=object)
+    return args, graph, pop, ep
