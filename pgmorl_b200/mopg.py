@@ -1,0 +1,205 @@
+"""MOPG worker with the reference's contract (morl/mopg.py:25-182) and its population-batched form.
+
+`MOPG_worker(args, task_id, task, device, iteration, num_updates, start_time, results_queue, done_event)`
+keeps the signature and the queue protocol of the reference: every `update_iter` iterations (and at the end)
+it puts {'task_id', 'offspring_batch': np.ndarray[object] of Sample, 'done'} on `results_queue`, then waits on
+`done_event`. Inside, rollout inference, GAE/advantage and the PPO update run on the GPU (K1, K2, K3).
+
+`mopg_population_update(args, task_batch, ...)` advances ALL tasks of this GPU's shard together: one K1 launch
+per environment step for every task's observations, then one K2 and one K3 launch per iteration for the whole
+population -- the form the bench measures. Environment stepping (MuJoCo) stays on the host and is out of scope;
+environments are created through the hooks below (defaults: the reference's own factories when importable).
+"""
+import time
+from collections import deque
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from ._lib import PpoHyper
+from .a2c_ppo_acktr import utils
+from .a2c_ppo_acktr.storage import RolloutStorage
+from .population_state import PopulationMOPG
+from .sample import Sample
+
+_HOOKS = {"make_vec_envs": None, "gym_make": None}
+
+
+def set_env_hooks(make_vec_envs=None, gym_make=None):
+    """Install the environment factories (signature of a2c_ppo_acktr.envs.make_vec_envs / gym.make)."""
+    if make_vec_envs is not None:
+        _HOOKS["make_vec_envs"] = make_vec_envs
+    if gym_make is not None:
+        _HOOKS["gym_make"] = gym_make
+
+
+def _make_vec_envs(**kw):
+    if _HOOKS["make_vec_envs"] is None:
+        from a2c_ppo_acktr.envs import make_vec_envs as ref_factory      # the reference's factory, if installed
+        _HOOKS["make_vec_envs"] = ref_factory
+    return _HOOKS["make_vec_envs"](**kw)
+
+
+def _gym_make(name):
+    if _HOOKS["gym_make"] is None:
+        import gym
+        _HOOKS["gym_make"] = gym.make
+    return _HOOKS["gym_make"](name)
+
+
+def evaluation(args, sample):
+    """Average (optionally discounted) objective vector of `eval_num` deterministic episodes (mopg.py:25-46)."""
+    eval_env = _gym_make(args.env_name)
+    objs = np.zeros(args.obj_num)
+    ob_rms = sample.env_params['ob_rms']
+    policy = sample.actor_critic
+    with torch.no_grad():
+        for eval_id in range(args.eval_num):
+            eval_env.seed(args.seed + eval_id)
+            ob = eval_env.reset()
+            done = False
+            gamma = 1.0
+            while not done:
+                if args.ob_rms:
+                    ob = np.clip((ob - ob_rms.mean) / np.sqrt(ob_rms.var + 1e-8), -10.0, 10.0)
+                _, action, _, _ = policy.act(torch.Tensor(ob).unsqueeze(0), None, None, deterministic=True)
+                ob, _, done, info = eval_env.step(action.cpu())
+                objs += gamma * info['obj']
+                if not args.raw:
+                    gamma *= args.gamma
+    eval_env.close()
+    objs /= args.eval_num
+    return objs
+
+
+def _restore_rms(envs, env_params):
+    for key in ('ob_rms', 'ret_rms', 'obj_rms'):
+        if env_params[key] is not None:
+            setattr(envs.venv, key, deepcopy(env_params[key]))
+
+
+def _snapshot_rms(envs):
+    return {key: (deepcopy(getattr(envs, key)) if getattr(envs, key) is not None else None)
+            for key in ('ob_rms', 'ret_rms', 'obj_rms')}
+
+
+def MOPG_worker(args, task_id, task, device, iteration, num_updates, start_time, results_queue, done_event):
+    """One task, reference contract (mopg.py:60-182)."""
+    scalarization = task.scalarization
+    env_params, actor_critic, agent = task.sample.env_params, task.sample.actor_critic, task.sample.agent
+    envs = _make_vec_envs(env_name=args.env_name, seed=args.seed, num_processes=args.num_processes, gamma=args.gamma,
+                          log_dir=None, device=device, allow_early_resets=False, obj_rms=args.obj_rms, ob_rms=args.ob_rms)
+    _restore_rms(envs, env_params)
+    rollouts = RolloutStorage(num_steps=args.num_steps, num_processes=args.num_processes,
+                              obs_shape=envs.observation_space.shape, action_space=envs.action_space,
+                              recurrent_hidden_state_size=actor_critic.recurrent_hidden_state_size,
+                              obj_num=args.obj_num, device=actor_critic.flat.device)
+    obs = envs.reset()
+    rollouts.obs[0].copy_(torch.as_tensor(obs).to(rollouts.obs.device, torch.float32))
+    episode_rewards = deque(maxlen=10)
+    total_num_updates = int(args.num_env_steps) // args.num_steps // args.num_processes
+    offspring_batch = []
+    start_iter, final_iter = iteration, min(iteration + num_updates, total_num_updates)
+    for j in range(start_iter, final_iter):
+        torch.manual_seed(j)
+        if args.use_linear_lr_decay:
+            utils.update_linear_schedule(agent.optimizer, j * args.lr_decay_ratio, total_num_updates, args.lr)
+        for step in range(args.num_steps):
+            with torch.no_grad():
+                value, action, action_log_prob, rhs = actor_critic.act(rollouts.obs[step], None, rollouts.masks[step])
+            obs, _, done, infos = envs.step(action.cpu())
+            obj_tensor = torch.zeros([args.num_processes, args.obj_num], dtype=torch.float64)
+            for idx, info in enumerate(infos):
+                obj_tensor[idx] = torch.from_numpy(np.asarray(info['obj'], dtype=np.float64))
+                if 'episode' in info.keys():
+                    episode_rewards.append(info['episode']['r'])
+            masks = torch.FloatTensor([[0.0] if done_ else [1.0] for done_ in done])
+            bad_masks = torch.FloatTensor([[0.0] if 'bad_transition' in info.keys() else [1.0] for info in infos])
+            rollouts.insert(obs, rollouts.recurrent_hidden_states[step + 1], action, action_log_prob, value,
+                            obj_tensor, masks, bad_masks)
+        with torch.no_grad():
+            next_value = actor_critic.get_value(rollouts.obs[-1], None, rollouts.masks[-1])
+        rollouts.compute_returns(next_value, args.use_gae, args.gamma, args.gae_lambda, args.use_proper_time_limits)
+        obj_rms_var = envs.obj_rms.var if envs.obj_rms is not None else None
+        agent.update(rollouts, scalarization, obj_rms_var)
+        rollouts.after_update()
+        sample = Sample(_snapshot_rms(envs), deepcopy(actor_critic), deepcopy(agent))
+        sample.objs = evaluation(args, sample)
+        offspring_batch.append(sample)
+        if args.rl_log_interval > 0 and (j + 1) % args.rl_log_interval == 0 and len(episode_rewards) > 1 and task_id == 0:
+            total_num_steps = (j + 1) * args.num_processes * args.num_steps
+            end = time.time()
+            print("[RL] Updates {}, num timesteps {}, FPS {}, time {:.2f} seconds".format(
+                j + 1, total_num_steps, int(total_num_steps / (end - start_time)), end - start_time))
+        if (j + 1) % args.update_iter == 0 or j == final_iter - 1:
+            results_queue.put({'task_id': task_id, 'offspring_batch': np.array(offspring_batch),
+                               'done': j == final_iter - 1})
+            offspring_batch = []
+    envs.close()
+    done_event.wait()
+
+
+def mopg_population_update(args, task_batch, device, iteration, num_updates, start_time=None, cluster=0):
+    """All tasks of this shard advance together; returns offspring[task_id] = list of Samples (one per iteration),
+    the content the reference's workers put on the queue (morl/morl.py:93-99)."""
+    P = len(task_batch)
+    first = task_batch[0].sample.actor_critic
+    dims, dev = first.dims, first.flat.device
+    total_num_updates = int(args.num_env_steps) // args.num_steps // args.num_processes
+    ag0 = task_batch[0].sample.agent
+    g0 = ag0.optimizer.param_groups[0]
+    hyper = PpoHyper(ag0.clip_param, ag0.value_loss_coef, ag0.entropy_coef, ag0.max_grad_norm, g0["betas"][0],
+                     g0["betas"][1], g0["eps"])
+    pop = PopulationMOPG(dims, P, args.num_steps, args.num_processes, ppo_epoch=args.ppo_epoch,
+                         num_mini_batch=args.num_mini_batch, gamma=args.gamma, gae_lambda=args.gae_lambda,
+                         hyper=hyper, device=dev, cluster=cluster)
+    envs_all = []
+    for p, task in enumerate(task_batch):
+        ac, opt = task.sample.actor_critic, task.sample.agent.optimizer
+        pop.params[p].copy_(ac.flat); pop.adam_m[p].copy_(opt.exp_avg); pop.adam_v[p].copy_(opt.exp_avg_sq)
+        pop.adam_step[p] = opt.step_count
+        pop.weights[p].copy_(torch.as_tensor(np.asarray(task.scalarization.weights, dtype=np.float64), dtype=torch.float32))
+        envs = _make_vec_envs(env_name=args.env_name, seed=args.seed, num_processes=args.num_processes, gamma=args.gamma,
+                              log_dir=None, device=device, allow_early_resets=False, obj_rms=args.obj_rms, ob_rms=args.ob_rms)
+        _restore_rms(envs, task.sample.env_params)
+        envs_all.append(envs)
+    T, N, M = args.num_steps, args.num_processes, args.obj_num
+    obs_now = torch.stack([torch.as_tensor(e.reset()).to(torch.float32) for e in envs_all])       # [P,N,O] host
+    offspring = [[] for _ in range(P)]
+    start_iter, final_iter = iteration, min(iteration + num_updates, total_num_updates)
+    for j in range(start_iter, final_iter):
+        eps, perm = None, None
+        torch.manual_seed(j)              # every task of a generation sees the same streams (mopg.py:96)
+        lr = args.lr - (args.lr * ((j * args.lr_decay_ratio) / float(total_num_updates))) if args.use_linear_lr_decay else args.lr
+        pop.set_lr(lr)
+        pop.masks[:, 0] = 1.0 if j == start_iter else pop.masks[:, T]
+        pop.bad_masks[:, 0] = 1.0 if j == start_iter else pop.bad_masks[:, T]
+        for step in range(T):
+            eps_t = torch.empty(N, dims.act, dtype=torch.float64).normal_(0, 1)
+            action = pop.act_step(step, obs_now, eps_t)                                             # K1, per-step mode
+            act_host = action.cpu()
+            for p, envs in enumerate(envs_all):
+                obs, _, done, infos = envs.step(act_host[p])
+                obs_now[p] = torch.as_tensor(obs).to(torch.float32)
+                pop.store_transition(p, step, np.stack([np.asarray(i['obj'], dtype=np.float64) for i in infos]),
+                                     [0.0 if d else 1.0 for d in done],
+                                     [0.0 if 'bad_transition' in i.keys() else 1.0 for i in infos])
+        pop.finish_rollout(obs_now)                                                                 # value of the last obs
+        for p, envs in enumerate(envs_all):
+            var = envs.obj_rms.var if envs.obj_rms is not None else np.ones(M) - 1e-8
+            pop.obj_var[p].copy_(torch.as_tensor(np.asarray(var, dtype=np.float64) * np.ones(M), dtype=torch.float32))
+        pop.perm.copy_(torch.stack([torch.randperm(T * N) for _ in range(args.ppo_epoch)]).to(torch.int32)[None])
+        pop.update_only()                                                                           # K2 + K3
+        for p, (task, envs) in enumerate(zip(task_batch, envs_all)):
+            ac, agent = deepcopy(task.sample.actor_critic), deepcopy(task.sample.agent)
+            ac.flat = pop.params[p].clone()
+            agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
+            agent.optimizer.step_count = int(pop.adam_step[p])
+            agent.optimizer.param_groups[0]['lr'] = lr
+            sample = Sample(_snapshot_rms(envs), ac, agent)
+            sample.objs = evaluation(args, sample)
+            offspring[p].append(sample)
+    for envs in envs_all:
+        envs.close()
+    return offspring

@@ -95,6 +95,48 @@ class PopulationMOPG:
 
     GPU_LAUNCHES_PER_STEP = 4   # K1 forward, K2 GAE/adv, K3 record pack, K3 PPO
 
+    # ------------------------------------------------------------------ per-step mode (real environment loops)
+    def act_step(self, t, obs_host, eps_t):
+        """K1 in per-step mode: obs_host [P,N,O] (host) at time t, eps_t [N,A] float64 shared by all tasks.
+        Stores obs/value/action/logp of step t in the rollout buffers; returns actions [P,N,A] (device)."""
+        P, N, d = self.P, self.N, self.dims
+        if not hasattr(self, "_step_obs"):
+            self._step_obs = torch.empty(P, N, d.obs, device=self.device)
+            self._step_out = (torch.empty(P, N, d.obj, device=self.device), torch.empty(P, N, d.act, device=self.device),
+                              torch.empty(P, N, device=self.device))
+        self._step_obs.copy_(obs_host)
+        eps = eps_t.to(self.device, torch.float32)[None].contiguous()
+        value, action, logp = K.policy_forward(self.params, self._step_obs, d, eps=eps, out=self._step_out)
+        rows = slice(t * N, (t + 1) * N)
+        self.obs[:, rows].copy_(self._step_obs)
+        self.value[:, rows].copy_(value); self.action[:, rows].copy_(action); self.logp[:, rows].copy_(logp)
+        return action
+
+    def store_transition(self, p, t, objs, masks, bad_masks):
+        """Reward vector / termination flags task p observed after step t (host values)."""
+        self.rewards[p, t].copy_(torch.as_tensor(objs, dtype=torch.float32))
+        self.masks[p, t + 1].copy_(torch.as_tensor(masks, dtype=torch.float32))
+        self.bad_masks[p, t + 1].copy_(torch.as_tensor(bad_masks, dtype=torch.float32))
+
+    def finish_rollout(self, obs_host):
+        """Bootstrap value of the observation after the last step (mopg.py:132-135)."""
+        T, N, d = self.T, self.N, self.dims
+        self._step_obs.copy_(obs_host)
+        value, _, _ = K.policy_forward(self.params, self._step_obs, d, rows_a=0, mode=K.ACT_DETERMINISTIC)
+        self.obs[:, T * N:].copy_(self._step_obs)
+        self.value[:, T * N:].copy_(value)
+
+    def update_only(self):
+        """K2 + K3 on the rollout already in the buffers."""
+        T, N, P, d = self.T, self.N, self.P, self.dims
+        K.gae_adv(self.rewards, self.value.view(P, T + 1, N, d.obj), self.masks, self.bad_masks, self.gamma,
+                  self.lam, weights=self.weights, obj_var=self.obj_var, out=(self.returns, self.adv))
+        K.ppo_update(self.params, self.adam_m, self.adam_v, self.adam_step, self.lr, self.obs, self.action,
+                     self.logp, self.value, self.returns.view(P, self.S, d.obj), self.adv.view(P, self.S),
+                     self.perm, self.B, d, hyper=self.hyper, workspace=self.workspace, cluster=self.cluster,
+                     losses=self.losses)
+        return self.losses
+
     def upload(self, obs, rewards, masks, bad_masks, eps, perm):
         """Stage one iteration's host inputs through pinned memory and copy them to HBM (async)."""
         src = dict(obs=obs, rewards=rewards, masks=masks, bad_masks=bad_masks, eps=eps, perm=perm)

@@ -176,3 +176,77 @@ def run_selection_history(classes, args, generations, seed, update_iter=3, warmu
         if len(elite_batch) == 0:
             break
     return ep, population, graph
+
+
+# ---------------------------------------------------------------------------------------------
+# Replay environments: the VecEnv / gym surface MOPG_worker touches, fed from synthetic trajectories
+# ---------------------------------------------------------------------------------------------
+class _Box:
+    def __init__(self, n):
+        self.shape = (n,)
+
+
+_Box.__name__ = "Box"        # the reference dispatches on the class NAME of the action space
+
+
+class _Rms:
+    def __init__(self, mean, var):
+        self.mean, self.var = np.asarray(mean, dtype=np.float64), np.asarray(var, dtype=np.float64)
+
+
+class ReplayVecEnv:
+    """Observations / objective vectors / termination flags replayed from make_trajectories() output of one task
+    (independent of the actions): the stand-in for make_vec_envs() where MuJoCo is not available."""
+
+    def __init__(self, traj_task, dims, obj_var):
+        self.traj, self.t = traj_task, 0
+        self.observation_space = _Box(dims.obs)
+        self.action_space = _Box(dims.act)
+        self.ob_rms = _Rms(np.zeros(dims.obs), np.ones(dims.obs))
+        self.ret_rms = None
+        self.obj_rms = _Rms(np.zeros(dims.obj), obj_var)
+        self.venv = self
+
+    def reset(self):
+        self.t = 0
+        return torch.as_tensor(self.traj["obs"][0])
+
+    def step(self, action):
+        t = self.t
+        self.t += 1
+        obs = torch.as_tensor(self.traj["obs"][t + 1])
+        done = np.asarray(self.traj["masks"][t + 1]) == 0
+        infos = []
+        for n in range(len(done)):
+            info = {"obj": np.asarray(self.traj["rewards"][t, n], dtype=np.float64),
+                    "obj_raw": np.asarray(self.traj["rewards"][t, n], dtype=np.float64)}
+            if self.traj["bad_masks"][t + 1, n] == 0:
+                info["bad_transition"] = True
+            infos.append(info)
+        return obs, None, done, infos
+
+    def close(self):
+        pass
+
+
+class ToyEvalEnv:
+    """Deterministic gym-like evaluation env: objective = smooth function of the policy's mean action."""
+
+    def __init__(self, dims, horizon=5):
+        self.dims, self.horizon = dims, horizon
+
+    def seed(self, s):
+        self.rng = np.random.RandomState(s)
+
+    def reset(self):
+        self.k = 0
+        return self.rng.uniform(-1, 1, self.dims.obs)
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64).reshape(-1)
+        self.k += 1
+        obj = np.array([1.0 + np.tanh(a[:self.dims.act // 2].sum()), 1.0 + np.tanh(a[self.dims.act // 2:].sum()), 1.0][:self.dims.obj])
+        return self.rng.uniform(-1, 1, self.dims.obs), 0.0, self.k >= self.horizon, {"obj": obj}
+
+    def close(self):
+        pass
