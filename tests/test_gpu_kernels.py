@@ -188,3 +188,33 @@ def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
         assert rel_err(gm[p].cpu().numpy(), m) < 1e-4          # Adam first moment
         assert rel_err(gv[p].cpu().numpy(), v) < 1e-4          # Adam second moment
         assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 1e-4
+
+
+@pytest.mark.parametrize("cluster", [0, 8])
+def test_full_size_c2_iteration_matches_reference_golden(cluster):
+    """BASELINE.json configs[1] at full size (2 of the 6 tasks: T=2048, N=4, 10 epochs x 32 minibatches = 320 Adam
+    steps) through the population API, against the UNMODIFIED reference's outputs (mopg_halfcheetah_full.npz).
+    Gate: 1e-4 norm-wise on parameters and returns (north_star), Adam moments 1e-3."""
+    from pgmorl_b200.population_state import PopulationMOPG
+    from tests.helpers import load_mopg_case
+    z, meta = load_mopg_case("mopg_halfcheetah_full.npz")
+    d, P, T, N = meta["dims"], meta["n_tasks"], meta["T"], meta["N"]
+    j = meta["iters"][0]
+    pop = PopulationMOPG(d, P, T, N, ppo_epoch=meta["E"], num_mini_batch=meta["B"], gamma=meta["gamma"],
+                         gae_lambda=meta["lam"], cluster=cluster)
+    for p in range(P):
+        pop.load_task(p, z[f"t{p}_init"], weights=z[f"t{p}_weights"], obj_var=z[f"t{p}_obj_var"])
+    pop.set_lr(synthetic.linear_lr(3e-4, j, 1.0, meta["total_num_updates"]))
+    traj = synthetic.make_trajectories(P, T, N, d, seed=meta["traj_seed"] + j)
+    eps, perm = synthetic.host_rng_streams(j, T, N, d.act, meta["E"])
+    losses = pop.step_from_host(traj["obs"], traj["rewards"], traj["masks"], traj["bad_masks"],
+                                eps.to(torch.float32), perm.to(torch.int32))
+    for p in range(P):
+        pre = f"t{p}_i0_"
+        flat, m, v, step = pop.task_state(p)
+        assert step == int(z[pre + "adam_step"]) == 320
+        assert rel_err(pop.returns[p].cpu().numpy(), z[pre + "returns"]) < 1e-4
+        assert rel_err(pop.adv[p].cpu().numpy(), z[pre + "adv"]) < 1e-4
+        assert rel_err(flat, z[pre + "params"]) < 1e-4
+        assert rel_err(m, z[pre + "adam_m"]) < 1e-3 and rel_err(v, z[pre + "adam_v"]) < 1e-3
+        assert rel_err(losses[p], z[pre + "losses"]) < 1e-3
