@@ -571,8 +571,9 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
         C = 2;      // one CTA per network half is the throughput configuration (large populations)
-        // 16-CTA clusters are non-portable: at most one fits a GPC, so only use them for <= 8 tasks
-        const int cmax = (P <= 8) ? 16 : 8;
+        // 16-CTA clusters are non-portable and at most one fits a GPC (ncu: launch__cluster_max_active = 7 with
+        // this kernel's shared-memory footprint): use them only when every task's cluster is resident at once
+        const int cmax = (P <= 7) ? 16 : 8;
         while (C < cmax && (long long)P * C * 2 <= sms && mb / C >= 32) C *= 2;
     }
     const bool big = (L.OP > 64) || (A > 16) || (M > 16);
