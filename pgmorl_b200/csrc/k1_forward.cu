@@ -12,9 +12,6 @@
 
 namespace pgm {
 
-constexpr int K1_TM = 4;
-constexpr int K1_RC = 16 * K1_TM;   // 64 rows per chunk
-
 struct K1Args {
     const float *params, *obs, *eps;
     float *action, *value, *logp;
@@ -24,15 +21,21 @@ struct K1Args {
 
 __host__ __device__ inline int k1_ldo(const NetLayout &L) { return (L.A > L.M ? L.A : L.M) | 1; }
 
-__host__ inline size_t k1_smem_bytes(const NetLayout &L) {
-    size_t f = halfnet_smem_floats(L, 0) + halfnet_smem_floats(L, 1);
-    f += (size_t)K1_RC * L.ldw1;            // x
-    f += 2 * (size_t)K1_RC * LDH;           // h1, h2
-    f += 2 * (size_t)K1_RC * k1_ldo(L);     // mean, value
+// SPLIT = false: both halves resident (small networks). SPLIT = true: one half resident at a time, the CTA walks
+// its chunks once per half (wide observations, e.g. Humanoid O = 376: one half's W1 alone is 97 KB).
+__host__ inline size_t k1_smem_bytes(const NetLayout &L, int TM, bool split) {
+    const int RC = 16 * TM;
+    const size_t h0 = halfnet_smem_floats(L, 0), h1 = halfnet_smem_floats(L, 1);
+    size_t f = split ? (h0 > h1 ? h0 : h1) : h0 + h1;
+    f += (size_t)RC * L.ldw1;            // x
+    f += 2 * (size_t)RC * LDH;           // h1, h2
+    f += 2 * (size_t)RC * k1_ldo(L);     // mean, value
     return f * sizeof(float);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) k1_forward_kernel(const K1Args a) {
+template <int TM, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) k1_forward_kernel(const K1Args a) {
+    constexpr int RC = 16 * TM;
     extern __shared__ __align__(16) float smem[];
     const NetLayout &L = a.L;
     const int tid = threadIdx.x, tr = tid & 15, tc = tid >> 4;
@@ -41,20 +44,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) k1_forward_kernel(const K1Args a)
 
     HalfNet actor, critic;
     float *p = halfnet_carve(actor, smem, L, 0);
-    p = halfnet_carve(critic, p, L, 1);
-    float *x = p;  p += K1_RC * ldx;
-    float *h1 = p; p += K1_RC * LDH;
-    float *h2 = p; p += K1_RC * LDH;
-    float *mu = p; p += K1_RC * ldo;
+    if (SPLIT) {
+        float *pc = halfnet_carve(critic, smem, L, 1);      // same storage, used in a different pass
+        p = p > pc ? p : pc;
+    } else {
+        p = halfnet_carve(critic, p, L, 1);
+    }
+    float *x = p;  p += RC * ldx;
+    float *h1 = p; p += RC * LDH;
+    float *h2 = p; p += RC * LDH;
+    float *mu = p; p += RC * ldo;
     float *vo = p;
 
     const float *gp = a.params + (size_t)task * L.n_par;
-    halfnet_load<false>(actor, gp, L, 0);
-    halfnet_load<false>(critic, gp, L, 1);
-    // zero the padded columns of x once; chunk loads only touch k < O
-    for (int i = tid; i < K1_RC * ldx; i += NTHREADS) x[i] = 0.f;
-    __syncthreads();
-
     const int O = L.O, A = L.A, M = L.M;
     const float *obs = a.obs + (size_t)task * a.rows_v * O;
     const float *eps = a.eps ? a.eps + (a.eps_shared ? 0 : (size_t)task * a.rows_a * A) : nullptr;
@@ -62,50 +64,62 @@ __global__ void __launch_bounds__(NTHREADS, 2) k1_forward_kernel(const K1Args a)
     float *value = a.value + (size_t)task * a.rows_v * M;
     float *logp = a.logp ? a.logp + (size_t)task * a.rows_a : nullptr;
 
-    const int nchunks = (a.rows_v + K1_RC - 1) / K1_RC;
+    const int nchunks = (a.rows_v + RC - 1) / RC;
     const int c0 = blockIdx.x * a.chunks_per_cta;
     const int c1 = min(nchunks, c0 + a.chunks_per_cta);
-    for (int c = c0; c < c1; ++c) {
-        const int row0 = c * K1_RC;
-        const int nrow = min(K1_RC, a.rows_v - row0);
-        // coalesced copy of the dense [nrow][O] block into padded rows
-        const float *src = obs + (size_t)row0 * O;
-        for (int i = tid; i < K1_RC * O; i += NTHREADS) {
-            int r = i / O, k = i - r * O;
-            x[r * ldx + k] = r < nrow ? __ldg(src + i) : 0.f;
-        }
+
+    // pass 0 = critic (value for every row), pass 1 = actor (rows that carry an action); one pass if !SPLIT
+    for (int pass = 0; pass < (SPLIT ? 2 : 1); ++pass) {
+        if (SPLIT && pass == 1 && (long long)c0 * RC >= a.rows_a) break;      // no action rows in this CTA's range
         __syncthreads();
-        half_forward<K1_TM>(x, ldx, critic, L, h1, h2, vo, ldo, tr, tc);
-        for (int i = tid; i < nrow * M; i += NTHREADS) {
-            int r = i / M, m = i - r * M;
-            value[(size_t)row0 * M + i] = vo[r * ldo + m];
-        }
-        const int nact = min(nrow, a.rows_a - row0);   // rows of this chunk that carry an action
-        if (nact > 0) {   // uniform across the CTA
-            half_forward<K1_TM>(x, ldx, actor, L, h1, h2, mu, ldo, tr, tc);
-            // thread per (row, action dim): action + per-element log-density into mu[][] in place
-            for (int i = tid; i < nact * A; i += NTHREADS) {
-                int r = i / A, d = i - r * A;
-                const float mean = mu[r * ldo + d];
-                const float ls = actor.ls[d];
-                const float sd = expf(ls);
-                float act;
-                if (a.mode == PGM_ACT_SAMPLE) act = fmaf(sd, __ldg(eps + (size_t)row0 * A + i), mean);
-                else if (a.mode == PGM_ACT_DETERMINISTIC) act = mean;
-                else act = __ldg(action + (size_t)row0 * A + i);
-                if (a.mode != PGM_ACT_EVALUATE) action[(size_t)row0 * A + i] = act;
-                const float diff = act - mean;
-                // Normal.log_prob: -(x-mu)^2/(2 var) - log(std) - log(sqrt(2 pi))
-                mu[r * ldo + d] = -(diff * diff) / (2.f * sd * sd) - ls - 0.91893853320467274178f;
+        if (!SPLIT) { halfnet_load<false>(actor, gp, L, 0); halfnet_load<false>(critic, gp, L, 1); }
+        else if (pass == 0) halfnet_load<false>(critic, gp, L, 1);
+        else halfnet_load<false>(actor, gp, L, 0);
+        for (int i = tid; i < RC * ldx; i += NTHREADS) x[i] = 0.f;   // padded columns stay zero; loads touch k < O
+        __syncthreads();
+        for (int c = c0; c < c1; ++c) {
+            const int row0 = c * RC;
+            const int nrow = min(RC, a.rows_v - row0);
+            const float *src = obs + (size_t)row0 * O;
+            for (int i = tid; i < RC * O; i += NTHREADS) {         // coalesced copy of the dense [nrow][O] block
+                int r = i / O, k = i - r * O;
+                x[r * ldx + k] = r < nrow ? __ldg(src + i) : 0.f;
             }
             __syncthreads();
-            for (int r = tid; r < nact; r += NTHREADS) {
-                float s = 0.f;
-                for (int d = 0; d < A; ++d) s += mu[r * ldo + d];
-                logp[row0 + r] = s;
+            if (!SPLIT || pass == 0) {
+                half_forward<TM>(x, ldx, critic, L, h1, h2, vo, ldo, tr, tc);
+                for (int i = tid; i < nrow * M; i += NTHREADS) {
+                    int r = i / M, m = i - r * M;
+                    value[(size_t)row0 * M + i] = vo[r * ldo + m];
+                }
             }
+            const int nact = min(nrow, a.rows_a - row0);   // rows of this chunk that carry an action
+            if ((!SPLIT || pass == 1) && nact > 0) {        // uniform across the CTA
+                half_forward<TM>(x, ldx, actor, L, h1, h2, mu, ldo, tr, tc);
+                // thread per (row, action dim): action + per-element log-density into mu[][] in place
+                for (int i = tid; i < nact * A; i += NTHREADS) {
+                    int r = i / A, d = i - r * A;
+                    const float mean = mu[r * ldo + d];
+                    const float ls = actor.ls[d];
+                    const float sd = expf(ls);
+                    float act;
+                    if (a.mode == PGM_ACT_SAMPLE) act = fmaf(sd, __ldg(eps + (size_t)row0 * A + i), mean);
+                    else if (a.mode == PGM_ACT_DETERMINISTIC) act = mean;
+                    else act = __ldg(action + (size_t)row0 * A + i);
+                    if (a.mode != PGM_ACT_EVALUATE) action[(size_t)row0 * A + i] = act;
+                    const float diff = act - mean;
+                    // Normal.log_prob: -(x-mu)^2/(2 var) - log(std) - log(sqrt(2 pi))
+                    mu[r * ldo + d] = -(diff * diff) / (2.f * sd * sd) - ls - 0.91893853320467274178f;
+                }
+                __syncthreads();
+                for (int r = tid; r < nact; r += NTHREADS) {
+                    float s = 0.f;
+                    for (int d = 0; d < A; ++d) s += mu[r * ldo + d];
+                    logp[row0 + r] = s;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -128,20 +142,27 @@ extern "C" int pgm_policy_forward_f32(const float *params, const float *obs, con
     a.params = params; a.obs = obs; a.eps = eps; a.action = action; a.value = value; a.logp = logp;
     a.eps_shared = eps_shared; a.mode = mode; a.P = P; a.rows_v = rows_v; a.rows_a = rows_a;
     a.L = NetLayout(O, A, M);
-    const size_t smem = k1_smem_bytes(a.L);
+    const bool split = k1_smem_bytes(a.L, 4, false) > 110 * 1024;       // keep two CTAs per SM for small networks
+    const int TM = split ? 2 : 4, RC = 16 * TM;
+    const size_t smem = k1_smem_bytes(a.L, TM, split);
     PGM_REQUIRE(smem <= 227 * 1024, "pgm_policy_forward_f32: obs dim %d needs %zu B shared memory", O, smem);
-    PGM_CUDA(cudaFuncSetAttribute(k1_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     PGM_CUDA(cudaGetDevice(&dev));
     PGM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int nchunks = (rows_v + K1_RC - 1) / K1_RC;
-    const int slots = 2 * sms;                        // 2 resident CTAs per SM
+    const int nchunks = (rows_v + RC - 1) / RC;
+    const int slots = (split ? 1 : 2) * sms;            // resident CTAs
     int ctas_per_task = (slots + P - 1) / P;
     if (ctas_per_task > nchunks) ctas_per_task = nchunks;
     a.chunks_per_cta = (nchunks + ctas_per_task - 1) / ctas_per_task;
     ctas_per_task = (nchunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
     dim3 grid(ctas_per_task, P);
-    k1_forward_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+    if (split) {
+        PGM_CUDA(cudaFuncSetAttribute(k1_forward_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_forward_kernel<2, true><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        PGM_CUDA(cudaFuncSetAttribute(k1_forward_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_forward_kernel<4, false><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+    }
     PGM_CUDA(cudaGetLastError());
     return PGM_OK;
 }

@@ -44,7 +44,8 @@ def make_case(d, P, T, N, seed):
     return params, traj, eps, perm.numpy(), weights, obj_var, out
 
 
-@pytest.mark.parametrize("name,P,T,N", [("walker", 3, 50, 4), ("hopper3", 2, 33, 2), ("walker", 1, 1, 4)])
+@pytest.mark.parametrize("name,P,T,N", [("walker", 3, 50, 4), ("hopper3", 2, 33, 2), ("walker", 1, 1, 4),
+                                         ("humanoid", 2, 21, 8)])
 @pytest.mark.parametrize("shared_eps", [True, False])
 def test_k1_rollout_matches_oracle(name, P, T, N, shared_eps):
     from pgmorl_b200 import kernels as K
@@ -218,3 +219,35 @@ def test_full_size_c2_iteration_matches_reference_golden(cluster):
         assert rel_err(flat, z[pre + "params"]) < 1e-4
         assert rel_err(m, z[pre + "adam_m"]) < 1e-3 and rel_err(v, z[pre + "adam_v"]) < 1e-3
         assert rel_err(losses[p], z[pre + "losses"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["mopg_humanoid_small.npz", "mopg_hopper3_small.npz", "mopg_walker_small.npz"])
+def test_population_iterations_match_reference_goldens(name):
+    """Whole MOPG iterations (K1 -> K2 -> K3) for every task and every recorded iteration of the small goldens,
+    state carried across iterations, through PopulationMOPG. Humanoid dims (O = 376) take the split-half K1 and the
+    generic K3 path. Gate 1e-4 norm-wise (north_star); moments 1e-3."""
+    from pgmorl_b200.population_state import PopulationMOPG
+    from tests.helpers import load_mopg_case
+    z, meta = load_mopg_case(name)
+    d, P, T, N = meta["dims"], meta["n_tasks"], meta["T"], meta["N"]
+    pop = PopulationMOPG(d, P, T, N, ppo_epoch=meta["E"], num_mini_batch=meta["B"], gamma=meta["gamma"],
+                         gae_lambda=meta["lam"])
+    for p in range(P):
+        pop.load_task(p, z[f"t{p}_init"], weights=z[f"t{p}_weights"], obj_var=z[f"t{p}_obj_var"])
+    for k, j in enumerate(meta["iters"]):
+        pop.set_lr(synthetic.linear_lr(3e-4, j, 1.0, meta["total_num_updates"]))
+        traj = synthetic.make_trajectories(P, T, N, d, seed=meta["traj_seed"] + j)
+        eps, perm = synthetic.host_rng_streams(j, T, N, d.act, meta["E"])
+        losses = pop.step_from_host(traj["obs"], traj["rewards"], traj["masks"], traj["bad_masks"],
+                                    eps.to(torch.float32), perm.to(torch.int32))
+        for p in range(P):
+            pre = f"t{p}_i{k}_"
+            flat, m, v, step = pop.task_state(p)
+            assert step == int(z[pre + "adam_step"])
+            assert rel_err(pop.value[p].cpu().numpy().reshape(T + 1, N, -1), z[pre + "value"]) < 1e-4
+            assert rel_err(pop.action[p].cpu().numpy().reshape(T, N, -1), z[pre + "action"]) < 1e-4
+            assert rel_err(pop.returns[p].cpu().numpy(), z[pre + "returns"]) < 1e-4
+            assert rel_err(pop.adv[p].cpu().numpy(), z[pre + "adv"]) < 1e-4
+            assert rel_err(flat, z[pre + "params"]) < 1e-4
+            assert rel_err(m, z[pre + "adam_m"]) < 1e-3 and rel_err(v, z[pre + "adam_v"]) < 1e-3
+            assert rel_err(losses[p], z[pre + "losses"]) < 1e-3
