@@ -144,6 +144,10 @@ def main():
     ap.add_argument("--full-sample", action="store_true",
                     help="reference arm: time the full-size iteration instead of the T/4 bounded sample")
     args = ap.parse_args()
+    if args.impl == "reference":
+        # CPU-only arm: hide the GPUs before torch is imported (fork-based worker pools cannot follow the CUDA
+        # autograd threads torch starts when a device is visible)
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
     from pgmorl_b200.layout import ENV_SHAPES
     env, P, T, N, E, B, gamma = CONFIGS[args.config]
