@@ -132,6 +132,58 @@ def cpu_reference_leg(d, P, T, N, E, B, gamma, steps, warmup):
     return P * T * N / (ms / 1e3), ms, procs
 
 
+def selection_leg(cpu=True):
+    """Secondary BASELINE metric: prediction-guided selection ms/generation on the recorded synthetic histories
+    (tests/golden/selection_{2d,3d}.npz, last generation): product path = host candidate generation + K4 fits + K5
+    greedy loop; CPU = oracle port (scipy least_squares + python scoring; 3-D scoring timed on ONE of the 15 rounds
+    and scaled, stated in `cpu_sample`)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.helpers import rebuild_selection_state
+    from pgmorl_b200.scalarization_methods import WeightedSumScalarization
+    out = {}
+    torch.set_default_dtype(torch.float64)
+    try:
+        for name, M in (("selection_2d.npz", 2), ("selection_3d.npz", 3)):
+            z = np.load(os.path.join(ROOT, "tests", "golden", name))
+            g = int(z["meta"][1]) - 1
+            times = []
+            for rep in range(4):
+                args_s, graph, pop, ep = rebuild_selection_state(z, g, M)
+                np.random.seed(1000 + g)
+                template = WeightedSumScalarization(num_objs=M, weights=np.ones(M) / M)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                elites, scals, pred = pop.prediction_guided_selection(args_s, g, ep, graph, template)
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            key = f"{M}d"
+            out[key] = {"ms_per_generation": 1e3 * min(times[1:]), "n_pop": len(pop.sample_batch),
+                        "candidates": len(pop.last_candidates), "fits": len(pop.last_fits["x"]),
+                        "archive": int(len(ep.obj_batch)), "tasks": args_s.num_tasks}
+            if cpu:
+                from oracle import selection_oracle as so
+                f = pop.last_fits
+                t0 = time.perf_counter()
+                for x, y, w, ub in zip(f["x"], f["y"], f["w"], f["ub"]):
+                    so.fit_scipy(x, y, w, ub)
+                t_fit = time.perf_counter() - t0
+                cand = np.array([c["prediction"] for c in pop.last_candidates])
+                t0 = time.perf_counter()
+                if M == 2:
+                    so.greedy_select_2d(z[f"g{g}_round0_vep"], cand, args_s.sparsity, args_s.num_tasks)
+                    t_sel = time.perf_counter() - t0
+                else:
+                    so.greedy_select_3d(z[f"g{g}_round0_vep"], cand, args_s.sparsity, 1)
+                    t_sel = (time.perf_counter() - t0) * args_s.num_tasks
+                out[key]["cpu_ms_per_generation"] = 1e3 * (t_fit + t_sel)
+                out[key]["cpu_sample"] = ("scipy least_squares on every fit + python scoring, 1 core"
+                                          + ("" if M == 2 else "; scoring timed on 1 of 15 greedy rounds and scaled"))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,6 +193,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--cluster", type=int, default=int(os.environ.get("PGM_PPO_CLUSTER", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selection", action="store_true")
     ap.add_argument("--full-sample", action="store_true",
                     help="reference arm: time the full-size iteration instead of the T/4 bounded sample")
     args = ap.parse_args()
@@ -311,6 +364,11 @@ def main():
                               "k2_gae_adv": P * S * k2b / (stages[1] * 1e-3) / 1e9},
             "ppo_cluster": args.cluster, "finite": finite,
         }
+        if world == 1 and not args.no_selection:
+            try:
+                line["selection"] = selection_leg(cpu=not args.no_cpu_baseline)
+            except Exception as ex:
+                line["selection"] = {"error": repr(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             # fresh CPU-only process: fork-based worker pools cannot follow CUDA/autograd use in this one
             env_cpu = dict(os.environ, CUDA_VISIBLE_DEVICES="")
