@@ -190,10 +190,11 @@ int pgm_tc_selftest(float *out, int n_out, void *stream);
 
 /* Layout-discovery aid for the same building blocks: ONE tf32 MMA (K = 8) with caller-chosen descriptor strides;
  * out [128 * N] receives the raw TMEM accumulator (lane-major). fill 0 = operand words hold their word index,
- * fill 1 = K-major identity image with R rows; ltA/ltB = descriptor layout type; a_tmem: A operand from TMEM. Used by profiles/tc_layout_probe.py only. */
+ * fill 1 = K-major identity image with R rows; ltA/ltB = descriptor layout type; a_tmem: A operand from TMEM; kind 0 = tf32, 1 = f16 (K = 16,
+ * operands filled per halfword); offA/offB = byte offsets added to the operand start addresses. Used by profiles/tc_layout_probe.py only. */
 int pgm_tc_layout_probe(float *out, int M, int N, int a_mn, int b_mn, int fillA, int fillB, int RA, int RB,
                         int lboA, int sboA, int lboB, int sboB, int d_lane_off, int ltA, int ltB, int a_tmem,
-                        void *stream);
+                        int kind, int offA, int offB, void *stream);
 
 #ifdef __cplusplus
 }

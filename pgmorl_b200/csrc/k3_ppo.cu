@@ -35,6 +35,7 @@ struct K3Args {
     float *ssq;             // scratch: squared-norm partials       [P][16]
     float *lpart;           // scratch: loss partial sums           [P][16][4]
     float *grad_out;        // grad mode only: [P][n_par]
+    float *mv;              // tensor-core path: Adam moments in thread-owned float4 slots [P][2 halves][m|v][15][256]
     long long *trace;       // PGM_K3_TRACE builds only: [CTA][4 steps][16 marks] clock64 / globaltimer
     int perm_shared, E, B, mb, S, nsteps, grad_only;
     int Rg;                 // rows per CTA per step (multiple of the chunk size)
@@ -538,6 +539,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 
 }  // namespace pgm
 #include "k3_fast.cuh"
+#include "k3_tc.cuh"
 namespace pgm {
 
 // ------------------------------------------------------------------------------------------
@@ -545,10 +547,10 @@ namespace pgm {
 // ------------------------------------------------------------------------------------------
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
-    bool DB, fast;
+    bool DB, fast, tc;
     int stage_floats;
     size_t smem;
-    size_t off_rec, off_gpart, off_ssq, off_lpart, off_trace, total;
+    size_t off_rec, off_gpart, off_ssq, off_lpart, off_trace, off_mv, total;
 };
 
 static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS) {
@@ -562,12 +564,34 @@ static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS)
     return f * sizeof(float);
 }
 
+// shapes the tensor-core kernel is instantiated for (Walker2d / HalfCheetah and Hopper-v3)
+static bool k3_tc_dims(int O, int A, int M) { return (O == 17 && A == 6 && M == 2) || (O == 11 && A == 3 && M == 3); }
+static size_t k3_tc_mv_bytes(int P) { return (size_t)P * 2 * 2 * TC_SLOT4 * TC_THREADS * sizeof(float4); }
+constexpr int K3_CLUSTER_TC = 32;   // `cluster` value that selects the tensor-core path explicitly
+
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
+    pl.tc = false; pl.off_mv = 0;
+    if (cluster == K3_CLUSTER_TC) {
+        PGM_REQUIRE(k3_tc_dims(O, A, M), "ppo: the tensor-core path is built for (O,A,M) = (17,6,2) and (11,3,3), got (%d,%d,%d)", O, A, M);
+        pl.tc = true; pl.C = 2; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
+        pl.RSG = rec_stride(L); pl.RSS = 0; pl.NHP = 64; pl.DB = false; pl.fast = false; pl.stage_floats = 0;
+        pl.smem = tc_smem_layout(O).total;
+        size_t off = 0;
+        auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        pl.off_rec = seg((size_t)P * S * pl.RSG * sizeof(float));
+        pl.off_gpart = seg((size_t)P * 2 * pl.G * pl.NHP * sizeof(float));
+        pl.off_ssq = seg((size_t)P * 16 * sizeof(float));
+        pl.off_lpart = seg((size_t)P * 16 * 4 * sizeof(float));
+        pl.off_trace = 0;
+        pl.off_mv = seg(k3_tc_mv_bytes(P));
+        pl.total = off;
+        return PGM_OK;
+    }
     PGM_REQUIRE(O >= 1 && O <= 384 && A >= 1 && A <= 32 && M >= 1 && M <= 16,
                 "ppo: unsupported dims O=%d A=%d M=%d (O<=384, A<=32, M<=16)", O, A, M);
     PGM_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16,
-                "ppo: cluster must be 0,1,2,4,8 or 16 (got %d)", cluster);
+                "ppo: cluster must be 0,1,2,4,8,16 or 32 (tensor cores) (got %d)", cluster);
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
         C = 2;      // one CTA per network half is the throughput configuration (large populations)
@@ -620,7 +644,7 @@ static int k3_launch_k(Kern kern, int C, const K3Args &a, const K3Plan &pl, int 
     PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     if (C > 8) PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(P * C); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cfg.gridDim = dim3(P * C); cfg.blockDim = dim3(pl.tc ? TC_THREADS : NTHREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -646,6 +670,10 @@ static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
 }
 
 static int k3_launch(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
+    if (pl.tc) {
+        if (a.L.O == 17) return k3_launch_k(k3_tc_kernel<17, 6, 2>, 2, a, pl, P, st);
+        return k3_launch_k(k3_tc_kernel<11, 3, 3>, 2, a, pl, P, st);
+    }
     switch (pl.C) {
         case 1: return k3_launch_c<1>(a, pl, P, st);
         case 2: return k3_launch_c<2>(a, pl, P, st);
@@ -680,6 +708,7 @@ extern "C" size_t pgm_ppo_workspace_bytes(int P, int S, int O, int A, int M, int
     seg((size_t)P * 2 * G * NHP * sizeof(float));
     seg((size_t)P * 16 * sizeof(float));
     seg((size_t)P * 64 * sizeof(float));
+    if (k3_tc_dims(O, A, M)) seg(k3_tc_mv_bytes(P));
 #ifdef PGM_K3_TRACE
     seg((size_t)P * 16 * 4 * 16 * 2 * sizeof(long long));
 #endif
@@ -714,6 +743,7 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
 #else
     a.trace = nullptr;
 #endif
+    a.mv = (float *)(ws + pl.off_mv);
     a.grad_out = grad_out; a.perm_shared = perm_shared; a.E = E; a.B = B; a.mb = mb; a.S = S;
     a.grad_only = grad_out != nullptr; a.nsteps = a.grad_only ? 1 : E * B;
     a.Rg = pl.Rg; a.RSG = pl.RSG; a.RSS = pl.RSS; a.NHP = pl.NHP; a.stage_floats = pl.stage_floats; a.hy = *hy; a.L = NetLayout(O, A, M);

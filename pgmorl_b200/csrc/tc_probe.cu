@@ -2,6 +2,8 @@
 // view the K3 tensor-core kernel relies on (chunk images as K-major and MN-major A / B, N = 16 / 32 / 64,
 // accumulate flag, 3-way TF32 split) and checks them on the device against plain FP32/FP64 loops.
 // Exposed as pgm_tc_selftest (include/pgmorl_b200.h); tests/test_gpu_tc.py asserts on the result vector.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -323,7 +325,7 @@ namespace pgm {
 __global__ void __launch_bounds__(128, 1) tc_layout_kernel(float *out, int M, int N, int a_mn, int b_mn, int fillA, int fillB,
                                                            int RA, int RB, uint32_t lboA, uint32_t sboA, uint32_t lboB,
                                                            uint32_t sboB, uint32_t d_lane_off, uint32_t ltA, uint32_t ltB,
-                                                           int a_tmem) {
+                                                           int a_tmem, int kind, uint32_t offA, uint32_t offB) {
     extern __shared__ __align__(1024) float sm[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -336,13 +338,24 @@ __global__ void __launch_bounds__(128, 1) tc_layout_kernel(float *out, int M, in
     const uint32_t tmem = tmem_base_s;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     float *A = sm, *B = sm + 8192;   // 32 KB each
-    for (int i = tid; i < 8192; i += 128) {
-        A[i] = fillA == 0 ? (float)(i % 2048) : 0.f;
-        B[i] = fillB == 0 ? (float)(i % 2048) : 0.f;
+    if (kind == 0) {
+        for (int i = tid; i < 8192; i += 128) {
+            A[i] = fillA == 0 ? (float)(i % 2048) : 0.f;
+            B[i] = fillB == 0 ? (float)(i % 2048) : 0.f;
+        }
+        __syncthreads();
+        if (fillA == 1) for (int i = tid; i < 8; i += 128) A[img(i, i, RA)] = 1.f;
+        if (fillB == 1) for (int i = tid; i < 8; i += 128) B[img(i, i, RB)] = 1.f;
+    } else {   // fp16: halfword h holds (h mod 2048); identity = K-major no-swizzle image, 8 halfwords per 16-byte chunk
+        __half *Ah = reinterpret_cast<__half *>(A), *Bh = reinterpret_cast<__half *>(B);
+        for (int i = tid; i < 16384; i += 128) {
+            Ah[i] = __float2half(fillA == 0 ? (float)(i % 2048) : 0.f);
+            Bh[i] = __float2half(fillB == 0 ? (float)(i % 2048) : 0.f);
+        }
+        __syncthreads();
+        if (fillA == 1) for (int i = tid; i < 16; i += 128) Ah[(i >> 3) * RA * 8 + i * 8 + (i & 7)] = __float2half(1.f);
+        if (fillB == 1) for (int i = tid; i < 16; i += 128) Bh[(i >> 3) * RB * 8 + i * 8 + (i & 7)] = __float2half(1.f);
     }
-    __syncthreads();
-    if (fillA == 1) for (int i = tid; i < 8; i += 128) A[img(i, i, RA)] = 1.f;
-    if (fillB == 1) for (int i = tid; i < 8; i += 128) B[img(i, i, RB)] = 1.f;
     {   // pre-fill the accumulator columns with a sentinel; A operand in TMEM columns 256..263
         float z[32];
         for (int i = 0; i < 32; ++i) z[i] = -7.f;
@@ -353,10 +366,11 @@ __global__ void __launch_bounds__(128, 1) tc_layout_kernel(float *out, int M, in
     }
     tc::fence_async_smem(); tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
     if (tid == 0) {
-        const uint64_t db = tc::make_desc(tc::smem_addr(B), lboB, sboB, ltB);
-        const uint32_t id = tc::idesc_tf32(M, N, a_mn, b_mn);
-        if (a_tmem) tc::mma_tf32_ts(tmem + (d_lane_off << 16), tmem + 256, db, id, 0);
-        else tc::mma_tf32(tmem + (d_lane_off << 16), tc::make_desc(tc::smem_addr(A), lboA, sboA, ltA), db, id, 0);
+        const uint64_t db = tc::make_desc(tc::smem_addr(B) + offB, lboB, sboB, ltB);
+        const uint64_t da = tc::make_desc(tc::smem_addr(A) + offA, lboA, sboA, ltA);
+        if (kind == 1) tc::mma_f16(tmem + (d_lane_off << 16), da, db, tc::idesc_f16(M, N, a_mn, b_mn), 0);
+        else if (a_tmem) tc::mma_tf32_ts(tmem + (d_lane_off << 16), tmem + 256, db, tc::idesc_tf32(M, N, a_mn, b_mn), 0);
+        else tc::mma_tf32(tmem + (d_lane_off << 16), da, db, tc::idesc_tf32(M, N, a_mn, b_mn), 0);
         tc::mma_commit(&bar);
     }
     tc::mbar_wait(&bar, 0);
@@ -374,13 +388,14 @@ __global__ void __launch_bounds__(128, 1) tc_layout_kernel(float *out, int M, in
 
 extern "C" int pgm_tc_layout_probe(float *out, int M, int N, int a_mn, int b_mn, int fillA, int fillB, int RA, int RB,
                                    int lboA, int sboA, int lboB, int sboB, int d_lane_off, int ltA, int ltB, int a_tmem,
-                                   void *stream) {
+                                   int kind, int offA, int offB, void *stream) {
     PGM_REQUIRE(out && N % 8 == 0 && N <= 256, "pgm_tc_layout_probe: bad arguments");
     const size_t smem = 2 * 8192 * sizeof(float);
     PGM_CUDA(cudaFuncSetAttribute(pgm::tc_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pgm::tc_layout_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, M, N, a_mn, b_mn, fillA, fillB, RA, RB, (uint32_t)lboA,
                                                                  (uint32_t)sboA, (uint32_t)lboB, (uint32_t)sboB,
-                                                                 (uint32_t)d_lane_off, (uint32_t)ltA, (uint32_t)ltB, a_tmem);
+                                                                 (uint32_t)d_lane_off, (uint32_t)ltA, (uint32_t)ltB, a_tmem, kind,
+                                                                 (uint32_t)offA, (uint32_t)offB);
     PGM_CUDA(cudaGetLastError());
     return PGM_OK;
 }
