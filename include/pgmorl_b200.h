@@ -196,6 +196,12 @@ int pgm_tc_layout_probe(float *out, int M, int N, int a_mn, int b_mn, int fillA,
                         int lboA, int sboA, int lboB, int sboB, int d_lane_off, int ltA, int ltB, int a_tmem,
                         int kind, int offA, int offB, void *stream);
 
+/* MMA pacing microbenchmark (profiles/tc_mma_bench.py): nmma kind::f16 MMAs (M x N x 16) from zero-filled
+ * SWIZZLE_128B images, rotating over nacc accumulators, operand start addresses advancing by a_step / b_step bytes.
+ * out [6] floats: per repetition {cycles issue..complete, cycles spent issuing}. */
+int pgm_tc_mma_bench(float *out, int M, int N, int a_mn, int b_mn, int nmma, int nacc, int a_step, int b_step,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

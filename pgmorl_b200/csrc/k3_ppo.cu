@@ -35,7 +35,7 @@ struct K3Args {
     float *ssq;             // scratch: squared-norm partials       [P][16]
     float *lpart;           // scratch: loss partial sums           [P][16][4]
     float *grad_out;        // grad mode only: [P][n_par]
-    float *mv;              // tensor-core path: Adam moments in thread-owned float4 slots [P][2 halves][m|v][15][256]
+    float *mv;              // tensor-core path: Adam moments per half in reference order [P][2 halves][m|v][TC_NHP]
     long long *trace;       // PGM_K3_TRACE builds only: [CTA][4 steps][16 marks] clock64 / globaltimer
     int perm_shared, E, B, mb, S, nsteps, grad_only;
     int Rg;                 // rows per CTA per step (multiple of the chunk size)
@@ -566,7 +566,7 @@ static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS)
 
 // shapes the tensor-core kernel is instantiated for (Walker2d / HalfCheetah and Hopper-v3)
 static bool k3_tc_dims(int O, int A, int M) { return (O == 17 && A == 6 && M == 2) || (O == 11 && A == 3 && M == 3); }
-static size_t k3_tc_mv_bytes(int P) { return (size_t)P * 2 * 2 * TC_SLOT4 * TC_THREADS * sizeof(float4); }
+static size_t k3_tc_mv_bytes(int P) { return (size_t)P * 2 * 2 * TC_NHP * sizeof(float); }
 constexpr int K3_CLUSTER_TC = 32;   // `cluster` value that selects the tensor-core path explicitly
 
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
@@ -576,15 +576,19 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
         PGM_REQUIRE(k3_tc_dims(O, A, M), "ppo: the tensor-core path is built for (O,A,M) = (17,6,2) and (11,3,3), got (%d,%d,%d)", O, A, M);
         pl.tc = true; pl.C = 2; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
         pl.RSG = rec_stride(L); pl.RSS = 0; pl.NHP = 64; pl.DB = false; pl.fast = false; pl.stage_floats = 0;
-        pl.smem = tc_smem_layout(O).total;
+        pl.smem = tc_smem_layout().total;
         size_t off = 0;
         auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
         pl.off_rec = seg((size_t)P * S * pl.RSG * sizeof(float));
         pl.off_gpart = seg((size_t)P * 2 * pl.G * pl.NHP * sizeof(float));
         pl.off_ssq = seg((size_t)P * 16 * sizeof(float));
         pl.off_lpart = seg((size_t)P * 16 * 4 * sizeof(float));
-        pl.off_trace = 0;
         pl.off_mv = seg(k3_tc_mv_bytes(P));
+#ifdef PGM_K3_TRACE
+        pl.off_trace = seg((size_t)P * 16 * 4 * 16 * 2 * sizeof(long long));
+#else
+        pl.off_trace = 0;
+#endif
         pl.total = off;
         return PGM_OK;
     }

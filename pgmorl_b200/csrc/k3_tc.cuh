@@ -1,31 +1,28 @@
-// K3 tensor-core path: the PPO minibatch loop (a2c/algo/ppo.py:62-107) on tcgen05 (UMMA, FP32 accumulate in TMEM).
-// Included by k3_ppo.cu (shares K3Args, k3_pack_kernel, fast_tanh, the DSMEM helpers).
+// K3 tensor-core path: the PPO minibatch loop (a2c/algo/ppo.py:62-107) on tcgen05 (UMMA kind::f16, FP32 accumulate
+// in TMEM). Included by k3_ppo.cu (shares K3Args, k3_pack_kernel, fast_tanh, the DSMEM helpers).
 //
 // One cluster of two CTAs per task: rank 0 = actor, rank 1 = critic (they share only the global gradient norm).
 // A CTA keeps its half's weights resident in shared memory as UMMA B operands and runs TWO independent 128-thread
 // pipelines ("groups"); group g owns the 128-row tiles t = g, g+2, ... of every minibatch, thread = row = TMEM lane.
 // While one group waits for its MMAs the other runs its epilogue, which hides the issue->complete latency of the
 // dependent GEMM chain.  Per tile:
-//   gather record -> x (tf32 hi|lo) to TMEM, x (fp16 a1|a2) to smem
-//   G1  Z1 = x W1^T (+b1 through a ones column)   kind::tf32, A: TMEM hi/lo, B: smem hi/lo, 3 MMAs per K step
-//   E1  h1 = tanh(Z1) -> TMEM hi/lo (operand of G2) and smem fp16 pair (operand of the weight-gradient GEMMs)
-//   G2/E2 likewise for layer 2;  G3  head = h2 Wh^T (N = 16)
-//   E3  per-row loss, d loss / d head -> smem            (thread owns its row: no cross-thread reduction)
-//   G4  dz2pre = dOut Wh;  GWh  dWh^T += h2^T dOut       kind::f16 from here on, 3 MMAs per K step
-//   E4  dz2 = dz2pre (1 - h2^2), h2 = hi + lo exact from TMEM
-//   G5  dz1pre = dz2 W2;   GW2  dW2 += dz2^T h1
-//   E5  dz1 = dz1pre (1 - h1^2)
+//   gather record (prefetched) -> x pair to the X image
+//   G1  Z1 = x W1^T (+b1 through a ones column);   E1  h1 = tanh(Z1) -> H1 image pair, 1 - h1^2 -> TMEM
+//   G2  Z2 = h1 W2^T;                              E2  h2 = tanh(Z2 + b2) -> H2 image pair, 1 - h2^2 -> TMEM
+//   G3  head = h2 Wh^T (N = 16);                   E3  per-row loss, d loss / d head -> X image (thread owns its row)
+//   G4  dz2pre = dOut Wh;  GWh  dWh^T += h2^T dOut;  E4  dz2 = dz2pre (1 - h2^2) -> H2 image pair (in place)
+//   G5  dz1pre = dz2 W2;   GW2  dW2 += dz2^T h1;     E5  dz1 = dz1pre (1 - h1^2) -> H1 image pair (in place)
 //   G1X [dW1 | db1 ; db2] += [dz1 | dz2]^T [x | 1]
-// Precision. Forward: 3-way TF32 split (hi*hi + lo*hi + hi*lo), measured 1.5e-7 like an FP32 FMA chain. Backward:
-// every operand is an FP16 PAIR a = a1 + a2 (a1 = fp16(a), a2 = fp16(a - a1): 22 significant bits) held in
-// power-of-two scaled form so that neither part underflows (activations x 2^8, backward signals x 2^12, backward
-// weights x 2^8; saturating conversions); a1*b1 + a1*b2 + a2*b1 reproduces the FP32 product to ~2^-21.  A pair
-// costs 4 bytes per element -- the footprint of ONE tf32 copy -- and, unlike tf32 (whose MN-major operands exist
-// only in a special 32-byte-swizzle layout), one [row][64 halfwords] SWIZZLE_128B image serves both as the
-// K-major A operand of G4/G5 and as the MN-major operand of the weight-gradient GEMMs (contraction over rows).
-// Step tail: gradients TMEM -> registers of their owner threads, squared-norm exchange with the peer CTA through
-// DSMEM (one cluster barrier), clip + Adam (moments in an L2-resident workspace, thread-owned float4 slots), new
-// weights re-split into the operand images.
+// Precision. Every GEMM operand is an FP16 PAIR a = a1 + a2 (a1 = a rounded to 11 significant bits, a2 = fp16(a - a1):
+// 22 significant bits), held in power-of-two scaled form so that neither part underflows (activations and weights
+// x 2^8, backward signals x 2^12; saturating conversions); a2*b1 + a1*b2 + a1*b1 with FP32 accumulation reproduces the
+// FP32 product to ~2^-21 (gradients measured 3e-7 norm-wise against the float64 oracle, like the FP32 FFMA path).
+// A pair costs 4 bytes per element, and ONE [row][64 halfwords] SWIZZLE_128B image serves both as a K-major operand
+// (contraction over features: G1..G5) and as an MN-major operand (contraction over rows: the weight-gradient GEMMs).
+// kind::tf32 cannot do that: its MN-major operands exist only in a special 32-byte-swizzle layout (see tc.cuh).
+// Step tail: gradients TMEM -> shared memory in parameter order, squared-norm exchange with the peer CTA through
+// DSMEM (one cluster barrier), clip + Adam on FP32 master parameters in shared memory (moments stream through an
+// L2-resident workspace), new weights re-split into the operand images.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -33,93 +30,94 @@
 
 namespace pgm {
 
-constexpr int TC_SLOT4 = 15;                 // float4 parameter slots per thread
 constexpr int TC_THREADS = 256;
 constexpr uint32_t TC_GROUP_BYTES = 81920;   // H1a | H1b | H2a | H2b | X   (16 KB each, [128 rows][64 halfwords])
 constexpr uint32_t TC_MISC_BYTES = 1280;
-constexpr float TC_SH = 256.f, TC_SD = 4096.f, TC_SW = 256.f;   // scales of activations / backward signals / backward weights
+constexpr int TC_NHP = 6144;                 // padded size of one half's parameter vector (floats)
+constexpr float TC_SH = 256.f, TC_SD = 4096.f, TC_SW = 256.f;   // scales of activations / backward signals / weights
 
 struct TcSmem {   // byte offsets inside dynamic shared memory
-    uint32_t grp[2], W2h, W2l, W2Ta, W2Tb, Whh, Whl, WhTz, WhTa, WhTb, W1h, W1l, misc, total;
+    uint32_t grp[2], W2a, W2b, W1, WhA1, WhA2, WhZ, PM, misc, total;
 };
-__host__ __device__ inline int tc_nch1(int O) { return (O + 1 + 3) / 4; }   // allocated 16-byte K chunks per W1 image
-__host__ __device__ inline TcSmem tc_smem_layout(int O) {
+__host__ __device__ inline TcSmem tc_smem_layout() {
     TcSmem s; uint32_t o = 0;
     s.grp[0] = o; o += TC_GROUP_BYTES; s.grp[1] = o; o += TC_GROUP_BYTES;
-    s.W2h = o; o += 16384; s.W2l = o; o += 16384;
-    s.W2Ta = o; o += 8192; s.W2Tb = o; o += 8192;          // [64 rows k][64 halfwords j], SWIZZLE_128B
-    s.Whh = o; o += 2048; s.Whl = o; o += 2048;
-    s.WhTz = o; o += 1024; s.WhTa = o; o += 1024; s.WhTb = o; o += 1024;   // K chunk of zeros | a1 | a2, [64 rows k][8 halfwords a]
-    // The last K step of G1 may read one chunk past each W1 image (multiplied by the zero padding of x): what
-    // follows must hold finite floats -> W1l follows W1h, the float part of `misc` follows W1l.
-    s.W1h = o; o += tc_nch1(O) * 1024; s.W1l = o; o += tc_nch1(O) * 1024;
+    s.W2a = o; o += 8192; s.W2b = o; o += 8192;               // [64 rows j][64 halfwords k] = W2[j][k] * 2^8 (a1 | a2)
+    s.W1 = o; o += 8192;                                      // [64 rows j][features 0..31 a1 | 32..63 a2], column O = bias
+    s.WhA1 = o; o += 1024; s.WhA2 = o; o += 1024; s.WhZ = o; o += 1024;   // [8 rows a][64 halfwords k]; Z = zero rows 8..15
+    s.PM = o; o += TC_NHP * 4;                                // FP32 master parameters of the half, reference order
     s.misc = o; o += TC_MISC_BYTES; s.total = o;
     return s;
 }
-// misc (floats): b2[64] bh[8] ls[8] red[40] part[8][16] ssq[4] | at byte 1024: double sh_d[4], mbarriers, tmem ptr
-constexpr int TCM_B2 = 0, TCM_BH = 64, TCM_LS = 72, TCM_RED = 80, TCM_PART = 120, TCM_SSQ = 248;
+// misc (floats): red[40] part[8][16] ssq[32] | at byte 1024: double sh_d[4], mbarriers, tmem ptr
+constexpr int TCM_RED = 0, TCM_PART = 40, TCM_SSQ = 168;   // ssq: [2 step parities][2 ranks][8 warps]
 
-// TMEM columns: group g at g*192: ACT [0,128) A operands of the forward GEMMs, ACC [128,192) accumulators;
+// TMEM columns: group g at g*192: D1 [0,64) = 1 - h1^2, D2 [64,128) = 1 - h2^2, ACC [128,192) accumulators;
 // weight-gradient accumulators shared by both groups
-constexpr uint32_t TC_ACT = 0, TC_ACC = 128, TC_GSTRIDE = 192, TC_GW2 = 384, TC_G1X = 448, TC_GWH = 480;
+constexpr uint32_t TC_D1 = 0, TC_D2 = 64, TC_ACC = 128, TC_GSTRIDE = 192, TC_GW2 = 384, TC_G1X = 448, TC_GWH = 480;
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+// loads that must be ISSUED where they are written (prefetches): volatile asm keeps the compiler from sinking them
+__device__ __forceinline__ float4 ld_nc_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_nc_s32(const int32_t *p) {
+    int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {   // two floats -> fp16x2 (a in the low half), saturating
     uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
 }
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
-    float2 r;
-    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(r.x), "=f"(r.y) : "r"(v));
-    return r;
-}
-
-// fp16 pair of (v0, v1): p1 = fp16x2 of the values, p2 = fp16x2 of the residuals
-__device__ __forceinline__ void split_h2(float v0, float v1, uint32_t &p1, uint32_t &p2) {
-    p1 = pack_h2(v0, v1);
-    const float2 f = unpack_h2(p1);
-    p2 = pack_h2(v0 - f.x, v1 - f.y);
-}
-// store 8 consecutive features (chunk c of 16 bytes) of row r into the a1 / a2 images of a [row][64 halfwords] buffer
-// (logical chunks ca / cb; swz8 = row & 7 is the SWIZZLE_128B XOR)
+// a1 = v rounded to 11 significant bits (round half away: integer add + mask, no conversion-pipe instruction);
+// exactly representable in fp16 whenever v is in fp16's normal range
+__device__ __forceinline__ float round11(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+// store 8 consecutive features (logical 16-byte chunks ca / cb of the a1 / a2 destination rows; swz8 = row & 7 is the
+// SWIZZLE_128B XOR) as an fp16 pair
 __device__ __forceinline__ void store_pair8(unsigned char *rowa, uint32_t ca, unsigned char *rowb, uint32_t cb, uint32_t swz8, const float *v) {
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = round11(v[i]);
     uint4 p1, p2;
-    split_h2(v[0], v[1], p1.x, p2.x); split_h2(v[2], v[3], p1.y, p2.y);
-    split_h2(v[4], v[5], p1.z, p2.z); split_h2(v[6], v[7], p1.w, p2.w);
+    p1.x = pack_h2(h[0], h[1]); p1.y = pack_h2(h[2], h[3]); p1.z = pack_h2(h[4], h[5]); p1.w = pack_h2(h[6], h[7]);
+    p2.x = pack_h2(v[0] - h[0], v[1] - h[1]); p2.y = pack_h2(v[2] - h[2], v[3] - h[3]);
+    p2.z = pack_h2(v[4] - h[4], v[5] - h[5]); p2.w = pack_h2(v[6] - h[6], v[7] - h[7]);
     *reinterpret_cast<uint4 *>(rowa + ((ca ^ swz8) << 4)) = p1;
     *reinterpret_cast<uint4 *>(rowb + ((cb ^ swz8) << 4)) = p2;
 }
 // halfword index of (row, feature) inside a [rows][64 halfwords] SWIZZLE_128B image
 __device__ __forceinline__ int sw128_hw(int row, int f) { return row * 64 + ((((f >> 3) ^ (row & 7))) << 3) + (f & 7); }
-
-// half-local parameter index (reference order inside the half: W1, b1, W2, b2, head W, head b, logstd) owned by
-// slot s of thread (q = lane quadrant, h = column half, lane), or -1.
-__device__ __forceinline__ int tc_own(int s, int q, int h, int lane, int tid, int O, int KH, int A, bool actor) {
-    const int oW2 = H * O + H, ob2 = oW2 + H * H, oWh = ob2 + H, obh = oWh + KH * H, ols = obh + KH;
-    if (s < 32) { if (lane >= 16) return -1; return oW2 + (16 * q + lane) * H + 32 * h + s; }
-    if (s < 48) {
-        const int c = 16 * h + (s - 32);
-        if (q < 2) { const int j = 32 * q + lane; return c < O ? j * O + c : (c == O ? H * O + j : -1); }
-        return c == O ? ob2 + 32 * (q - 2) + lane : -1;
-    }
-    if (s < 56) { if (h != 0 || lane >= 16) return -1; const int a = s - 48; return a < KH ? oWh + a * H + 16 * q + lane : -1; }
-    if (s == 56) return tid < KH ? obh + tid : -1;
-    if (s == 57) return (actor && tid < A) ? ols + tid : -1;
-    return -1;
+__device__ __forceinline__ void put_pair(__half *ia, int hwa, __half *ib, int hwb, float v) {
+    const float h = round11(v);
+    ia[hwa] = __float2half_rn(h); ib[hwb] = __float2half_rn(v - h);
 }
+
+// PGM_K3_TRACE builds: clock64 marks of threads r == 0 (MMA issuer) and r == 64 of each group, steps 8 and 9
+// (profiles/k3_tc_trace.py): trace[(((cta*2 + group)*2 + who)*2 + step - 8)*40 + mark]
+#ifdef PGM_K3_TRACE
+#define TCT(i) if (trace_on) a.trace[trace_base + (i)] = clock64();
+#else
+#define TCT(i)
+#endif
 
 template <int O, int A, int M>
 __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     constexpr int OP = (O + 3) / 4 * 4;
-    constexpr int KX = (O + 1 + 7) / 8 * 8;          // layer-1 contraction: x, ones column at index O, zero padding
-    constexpr int NKX = KX / 8;
+    constexpr int NK1 = (O + 1 + 15) / 16;           // K steps of layer 1: x, ones column at index O, zero padding
+    constexpr int NXC = (O + 1 + 7) / 8;             // 16-byte chunks of x (8 features each) written per row
     constexpr int RSG = (OP + A + 2 * M + 2 + 3) / 4 * 4;
-    constexpr int NCH1 = (O + 1 + 3) / 4;
-    static_assert(KX <= 24 && A <= 8 && M <= 8 && RSG <= 32, "k3_tc: dims outside the tensor-core path");
+    static_assert(O + 1 <= 24 && A <= 8 && M <= 8 && RSG <= 32, "k3_tc: dims outside the tensor-core path");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = tid >> 7, r = tid & 127;           // group, row inside the tile (= TMEM lane)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = tc::uniform_warp_idx();         // warp-uniform by construction: MMA operands stay in uniform registers
+    const int g = warp >> 2, r = tid & 127;          // group, row inside the tile (= TMEM lane)
     const int q = warp & 3, hcol = warp >> 2;        // lane quadrant, column half used in the step tail
     const int task = blockIdx.x >> 1;
     const unsigned rank = group_rank<2>();
@@ -127,29 +125,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const int half = (int)rank;
     const int KH = actor ? A : M;
     const NetLayout &L = a.L;
-    const TcSmem sl = tc_smem_layout(O);
+    const TcSmem sl = tc_smem_layout();
+    // half-local parameter offsets (reference order inside the half)
+    constexpr int ob1 = H * O, oW2 = ob1 + H, ob2 = oW2 + H * H, oWh = ob2 + H;
+    const int obh = oWh + KH * H, ols = obh + KH;
+    const int nH = ols + (actor ? A : 0);
+    const int n4 = (nH + 3) >> 2;
 
     unsigned char *sg = smem_raw + sl.grp[g];
-    unsigned char *S_h1 = sg, *S_h2 = sg + 32768, *S_x = sg + 65536;     // each: a1 image | a2 image (X: one image)
-    float *W2h = (float *)(smem_raw + sl.W2h), *W2l = (float *)(smem_raw + sl.W2l);
-    __half *W2Ta = (__half *)(smem_raw + sl.W2Ta), *W2Tb = (__half *)(smem_raw + sl.W2Tb);
-    float *Whh = (float *)(smem_raw + sl.Whh), *Whl = (float *)(smem_raw + sl.Whl);
-    __half *WhTa = (__half *)(smem_raw + sl.WhTa), *WhTb = (__half *)(smem_raw + sl.WhTb);
-    float *W1h = (float *)(smem_raw + sl.W1h), *W1l = (float *)(smem_raw + sl.W1l);
+    unsigned char *S_h1 = sg, *S_h2 = sg + 32768, *S_x = sg + 65536;     // H1a|H1b, H2a|H2b, X
+    __half *W2a = (__half *)(smem_raw + sl.W2a), *W2b = (__half *)(smem_raw + sl.W2b);
+    __half *W1i = (__half *)(smem_raw + sl.W1);
+    __half *WhA1 = (__half *)(smem_raw + sl.WhA1), *WhA2 = (__half *)(smem_raw + sl.WhA2);
+    float *PM = (float *)(smem_raw + sl.PM);
+    float *GR = (float *)(smem_raw + sl.grp[0]);                         // gradient staging (step tail only)
     float *misc = (float *)(smem_raw + sl.misc);
-    float *b2s = misc + TCM_B2, *bhs = misc + TCM_BH, *lss = misc + TCM_LS, *red = misc + TCM_RED;
-    float *part = misc + TCM_PART, *ssqS = misc + TCM_SSQ;
+    float *red = misc + TCM_RED, *part = misc + TCM_PART, *ssqS = misc + TCM_SSQ;
     double *sh_d = (double *)(smem_raw + sl.misc + 1024);
     uint64_t *mbars = (uint64_t *)(smem_raw + sl.misc + 1024 + 32);     // [0..1] chain (A), [2..3] weight grads (B)
     uint32_t *tmem_ptr_s = (uint32_t *)(smem_raw + sl.misc + 1024 + 64);
     uint64_t *mbA = mbars + g, *mbB = mbars + 2 + g;
+    const float *b2s = PM + ob2, *bhs = PM + obh, *lss = PM + ols;
 
     // ---------------- one-time setup ----------------
-    for (int i = tid; i < (int)(TC_MISC_BYTES / 4); i += TC_THREADS) misc[i] = 0.f;
-    for (int i = tid; i < (int)(2 * TC_GROUP_BYTES / 16); i += TC_THREADS)
-        reinterpret_cast<float4 *>(smem_raw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < 1024 / 16; i += TC_THREADS)
-        reinterpret_cast<float4 *>(smem_raw + sl.WhTz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (int)(sl.total / 16); i += TC_THREADS) reinterpret_cast<float4 *>(smem_raw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     if (warp == 0) tc::tmem_alloc(tmem_ptr_s, 512);
     if (tid == 0) {
@@ -157,66 +156,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         tc::fence_mbar_init();
     }
     const float *gpar = a.params + (size_t)task * L.n_par;
-    const float *pbase = gpar + L.half_base(half), *phead = gpar + L.half_head(half);
-    {   // operand images of the half's weights
-        const float *gW1 = pbase, *gb1 = pbase + H * O, *gW2 = gb1 + H, *gb2 = gW2 + H * H;
-        for (int i = tid; i < H * NCH1 * 4; i += TC_THREADS) {            // W1 image: row j, feature f (f == O: bias)
-            const int j = i / (NCH1 * 4), f = i - j * (NCH1 * 4);
-            const float v = f < O ? __ldg(gW1 + j * O + f) : (f == O ? __ldg(gb1 + j) : 0.f);
-            const float hi = tc::tf32_hi(v);
-            const int w = (f >> 2) * 256 + j * 4 + (f & 3);
-            W1h[w] = hi; W1l[w] = v - hi;
-        }
-        for (int i = tid; i < H * H; i += TC_THREADS) {
-            const int j = i >> 6, k = i & 63;
-            const float v = __ldg(gW2 + i), hi = tc::tf32_hi(v);
-            const int w = (k >> 2) * 256 + j * 4 + (k & 3);
-            W2h[w] = hi; W2l[w] = v - hi;
-            const __half t1 = __float2half_rn(v * TC_SW);                   // backward copy: row k, feature j, fp16 pair
-            W2Ta[sw128_hw(k, j)] = t1; W2Tb[sw128_hw(k, j)] = __float2half_rn(v * TC_SW - __half2float(t1));
-        }
-        for (int i = tid; i < 8 * H; i += TC_THREADS) {                    // head: rows a < 8 (zero beyond KH)
-            const int aa = i >> 6, k = i & 63;
-            const float v = aa < KH ? __ldg(phead + aa * H + k) : 0.f, hi = tc::tf32_hi(v);
-            const int w = (k >> 2) * 32 + aa * 4 + (k & 3);
-            Whh[w] = hi; Whl[w] = v - hi;
-            const __half t1 = __float2half_rn(v * TC_SW);                   // backward copy: row k, 8 halfwords a
-            WhTa[k * 8 + aa] = t1; WhTb[k * 8 + aa] = __float2half_rn(v * TC_SW - __half2float(t1));
-        }
-        for (int i = tid; i < H; i += TC_THREADS) b2s[i] = __ldg(gb2 + i);
-        for (int i = tid; i < 8; i += TC_THREADS) {
-            bhs[i] = i < KH ? __ldg(phead + KH * H + i) : 0.f;
-            lss[i] = (actor && i < A) ? __ldg(phead + KH * H + KH + i) : 0.f;
-        }
+    // one parameter (half-local index e, value p) -> its operand images
+    auto put_param = [&](int e, float p) {
+        if (e < ob1) { const int j = e / O, c = e - j * O; put_pair(W1i, sw128_hw(j, c), W1i, sw128_hw(j, 32 + c), p * TC_SW); }
+        else if (e < oW2) { const int j = e - ob1; put_pair(W1i, sw128_hw(j, O), W1i, sw128_hw(j, 32 + O), p * TC_SW); }
+        else if (e < ob2) { const int j = (e - oW2) >> 6, k = (e - oW2) & 63; put_pair(W2a, sw128_hw(j, k), W2b, sw128_hw(j, k), p * TC_SW); }
+        else if (e >= oWh && e < obh) { const int aa = (e - oWh) >> 6, k = (e - oWh) & 63; put_pair(WhA1, sw128_hw(aa, k), WhA2, sw128_hw(aa, k), p * TC_SW); }
+    };
+    for (int e = tid; e < nH; e += TC_THREADS) {
+        const float p = __ldg(gpar + L.to_global(half, e));
+        PM[e] = p;
+        put_param(e, p);
     }
-    // Adam moments: reference order -> thread-owned slots in the workspace; validity mask of my slots
-    float4 *mv4 = reinterpret_cast<float4 *>(a.mv) + ((size_t)(task * 2 + half) * 2) * TC_SLOT4 * TC_THREADS;
-    float4 *mM = mv4, *mV = mv4 + TC_SLOT4 * TC_THREADS;
-    unsigned long long vmask = 0ull;
-    for (int s4 = 0; s4 < TC_SLOT4; ++s4) {
-        float mm[4], vv[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int e = tc_own(4 * s4 + c, q, hcol, lane, tid, O, KH, A, actor);
-            mm[c] = 0.f; vv[c] = 0.f;
-            if (e >= 0) {
-                vmask |= 1ull << (4 * s4 + c);
-                if (!a.grad_only) {
-                    const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
-                    mm[c] = a.adam_m[gi]; vv[c] = a.adam_v[gi];
-                }
-            }
+    // Adam moments: reference order -> half-local order in the workspace
+    float *wM = a.mv + ((size_t)(task * 2 + half) * 2) * TC_NHP, *wV = wM + TC_NHP;
+    if (!a.grad_only)
+        for (int e = tid; e < 4 * n4; e += TC_THREADS) {
+            const bool in = e < nH;
+            const size_t gi = (size_t)task * L.n_par + (in ? L.to_global(half, e) : 0);
+            wM[e] = in ? a.adam_m[gi] : 0.f; wV[e] = in ? a.adam_v[gi] : 0.f;
         }
-        if (!a.grad_only) {
-            mM[s4 * TC_THREADS + tid] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-            mV[s4 * TC_THREADS + tid] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        }
-    }
     tc::fence_async_smem();
     tc::tc_fence_before();
     sync_group<2>();                 // barrier inits + TMEM address visible; peer CTA is alive before any DSMEM store
     tc::tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_s;
+    const uint32_t tmem = tc::uniform_u32(*tmem_ptr_s);
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);          // my lane quadrant
     const uint32_t tg = tq + (uint32_t)g * TC_GSTRIDE;              // + my group's column window
 
@@ -251,30 +215,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const int ntiles = (a.mb + 127) >> 7;
     uint32_t phA = 0, phB = 0;
     bool pendB = false;
-    const bool issuer = r == 0;
+    const bool issue_warp = (warp & 3) == 0;        // first warp of each group issues that group's MMAs (one elected lane)
 
-    // descriptors (constant for the whole launch)
-    const uint64_t dW1h = tc::desc_kmajor(tc::smem_addr(W1h), 64), dW1l = tc::desc_kmajor(tc::smem_addr(W1l), 64);
-    const uint64_t dW2h = tc::desc_kmajor(tc::smem_addr(W2h), 64), dW2l = tc::desc_kmajor(tc::smem_addr(W2l), 64);
-    // backward B operands (fp16): W2^T as a K-major SWIZZLE_128B image; Wh^T as [zero chunk | data chunk], K = 16
-    const uint64_t dW2Ta = tc::make_desc(tc::smem_addr(W2Ta), 16, 1024, 2), dW2Tb = tc::make_desc(tc::smem_addr(W2Tb), 16, 1024, 2);
-    const uint64_t dWhTa = tc::make_desc(tc::smem_addr(smem_raw + sl.WhTz), 1024, 128, 0);
-    const uint64_t dWhTb = tc::make_desc(tc::smem_addr(smem_raw + sl.WhTz), 2048, 128, 0);
-    const uint64_t dWhh = tc::make_desc(tc::smem_addr(Whh), 128, 0), dWhl = tc::make_desc(tc::smem_addr(Whl), 128, 0);
-    // activation images [128 rows][64 halfwords], SWIZZLE_128B.  MN-major view (M/N = feature, K = row): LBO = stride to
-    // the next 64-feature block (H1 -> H2 = 32 KB, used by the stacked G1X operand), SBO = 1024, 2048 B per K step.
-    // K-major view (M = row, K = feature): SBO = 1024, 32 B per K step.
+    // ---- descriptors (constant for the whole launch); images are [rows][64 halfwords], SWIZZLE_128B ----
+    // K-major view (M/N = row, K = feature): SBO = 1024 (next 8 rows), +32 B per K step of 16 features.
+    // MN-major view (M/N = feature, K = row): LBO = stride to the next 64-feature block, SBO = 1024 (next 8 K rows),
+    // +2048 B per K step of 16 rows.
     const uint32_t aH1 = tc::smem_addr(S_h1), aH2 = tc::smem_addr(S_h2), aX = tc::smem_addr(S_x);
-    const uint64_t dH1a_mn = tc::make_desc(aH1, 32768, 1024, 2), dH1b_mn = tc::make_desc(aH1 + 16384, 32768, 1024, 2);
-    const uint64_t dH2a_mn = tc::make_desc(aH2, 32768, 1024, 2), dH2b_mn = tc::make_desc(aH2 + 16384, 32768, 1024, 2);
-    const uint64_t dH2a_k = tc::make_desc(aH2, 16, 1024, 2), dH2b_k = tc::make_desc(aH2 + 16384, 16, 1024, 2);
-    const uint64_t dXa_mn = tc::make_desc(aX, 16384, 1024, 2), dXb_mn = tc::make_desc(aX + 64, 16384, 1024, 2);       // features 0..31 | 32..63
-    const uint64_t dXa_do = tc::make_desc(aX + 48, 16384, 1024, 2), dXb_do = tc::make_desc(aX + 112, 16384, 1024, 2);  // dOut: 24..31 | 56..63
-    const uint64_t dXa_k = tc::make_desc(aX + 32, 16, 1024, 2), dXb_k = tc::make_desc(aX + 96, 16, 1024, 2);           // K window 16..31 | 48..63
-    constexpr uint32_t ID_FWD = tc::idesc_tf32(128, 64, 0, 0), ID_HEAD = tc::idesc_tf32(128, 16, 0, 0);
-    constexpr uint32_t ID_BWD = tc::idesc_f16(128, 64, 0, 0);
+    const uint32_t aW1 = tc::smem_addr(W1i), aW2a = tc::smem_addr(W2a), aW2b = tc::smem_addr(W2b);
+    const uint32_t aWh1 = tc::smem_addr(WhA1), aWh2 = tc::smem_addr(WhA2);
+    auto dK = [](uint32_t addr) { return tc::make_desc(addr, 16, 1024, 2); };
+    auto dMN = [](uint32_t addr, uint32_t lbo) { return tc::make_desc(addr, lbo, 1024, 2); };
+    const uint64_t dXa_k = dK(aX), dXb_k = dK(aX + 64), dW1a_k = dK(aW1), dW1b_k = dK(aW1 + 64);
+    const uint64_t dH1a_k = dK(aH1), dH1b_k = dK(aH1 + 16384), dH2a_k = dK(aH2), dH2b_k = dK(aH2 + 16384);
+    const uint64_t dW2a_k = dK(aW2a), dW2b_k = dK(aW2b);
+    // head weights: 8 real rows; rows 8..15 come from the shared zero block (SBO = distance to WhZ)
+    const uint64_t dWh1_k = tc::make_desc(aWh1, 16, 2048, 2), dWh2_k = tc::make_desc(aWh2, 16, 1024, 2);
+    const uint64_t dWh1_mn = tc::make_desc(aWh1, 16384, 2048, 2), dWh2_mn = tc::make_desc(aWh2, 16384, 1024, 2);
+    const uint64_t dXdo_a = dK(aX + 48), dXdo_b = dK(aX + 112);      // K windows that start at dOut a1 / dOut a2
+    const uint64_t dW2a_mn = dMN(aW2a, 16384), dW2b_mn = dMN(aW2b, 16384);
+    const uint64_t dH1a_mn = dMN(aH1, 32768), dH1b_mn = dMN(aH1 + 16384, 32768);     // [H1 | H2] stacks to M = 128
+    const uint64_t dH2a_mn = dMN(aH2, 32768), dH2b_mn = dMN(aH2 + 16384, 32768);
+    const uint64_t dXa_mn = dMN(aX, 16384), dXb_mn = dMN(aX + 64, 16384);             // features 0..31 | 32..63
+    const uint64_t dXa_do = dMN(aX + 48, 16384), dXb_do = dMN(aX + 112, 16384);       // dOut: 24..31 | 56..63
+    constexpr uint32_t ID_KK = tc::idesc_f16(128, 64, 0, 0), ID_HEAD = tc::idesc_f16(128, 16, 0, 0), ID_KM = tc::idesc_f16(128, 64, 0, 1);
     constexpr uint32_t ID_GWH = tc::idesc_f16(64, 8, 1, 1), ID_GW2 = tc::idesc_f16(64, 64, 1, 1), ID_G1X = tc::idesc_f16(128, 32, 1, 1);
-    const uint32_t tACT = tmem + (uint32_t)g * TC_GSTRIDE + TC_ACT, tACC = tmem + (uint32_t)g * TC_GSTRIDE + TC_ACC;
+    const uint32_t tACC = tmem + (uint32_t)g * TC_GSTRIDE + TC_ACC;
     const uint32_t swz = (uint32_t)(r & 7);
     unsigned char *rowx = S_x + r * 128, *rowh1 = S_h1 + r * 128, *rowh2 = S_h2 + r * 128;   // a2 images at +16384
 
@@ -283,10 +249,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     };
     auto waitA = [&]() { tc::mbar_wait(mbA, phA); phA ^= 1; tc::tc_fence_after(); };
     auto waitB = [&]() { tc::mbar_wait(mbB, phB); phB ^= 1; tc::tc_fence_after(); };
+    // 3 MMAs of one K step: a2*b1 + a1*b2 + a1*b1 (small terms first)
+    auto mma3 = [&](uint32_t d, uint64_t a1, uint64_t a2, uint64_t b1, uint64_t b2, uint32_t id, uint32_t acc) {
+        tc::mma_f16(d, a2, b1, id, acc); tc::mma_f16(d, a1, b2, id, 1); tc::mma_f16(d, a1, b1, id, 1);
+    };
+
+    // record gather: the row index of tile (s, t) and then its packed record, prefetched one tile ahead
+    float rec[RSG];
+    bool valid = false;
+    auto tile_index = [&](int s, int t) -> int {
+        const int ep = s / a.B, bb = s - ep * a.B;
+        const int rowi = t * 128 + r;
+        return rowi < a.mb ? ld_nc_s32(perm + (size_t)ep * a.S + (size_t)bb * a.mb + rowi) : -1;
+    };
+    auto load_rec = [&](int idx) {
+        valid = idx >= 0;
+        const float4 *rp = reinterpret_cast<const float4 *>(recg + (size_t)(valid ? idx : 0) * RSG);
+#pragma unroll
+        for (int i = 0; i < RSG / 4; ++i) {
+            const float4 v = valid ? ld_nc_f4(rp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w;
+        }
+    };
+    int idx_next = g < ntiles ? tile_index(0, g) : -1;
+    if (g < ntiles) load_rec(idx_next);
 
     for (int s = 0; s < a.nsteps; ++s) {
-        const int ep = s / a.B, bb = s - ep * a.B;
-        const int32_t *pb = perm + (size_t)ep * a.S + (size_t)bb * a.mb;
+#ifdef PGM_K3_TRACE
+        const bool trace_on = a.trace && (s == 8 || s == 9) && (r == 0 || r == 64);
+        const size_t trace_base = ((((size_t)blockIdx.x * 2 + g) * 2 + (r == 64)) * 2 + (s - 8)) * 40;
+#endif
         float gbh[8], gls[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { gbh[i] = 0.f; gls[i] = 0.f; }
@@ -297,116 +289,110 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         }
 
         for (int t = g; t < ntiles; t += 2) {
-            const int rowi = t * 128 + r;
-            const bool valid = rowi < a.mb;
-            // ---------------- gather ----------------
-            float rec[RSG];
+            TCT(0)
+            // the tile after this one (same step, or my first tile of the next step): fetch its row index now
             {
-                const int idx = valid ? __ldg(pb + rowi) : 0;
-                const float4 *rp = reinterpret_cast<const float4 *>(recg + (size_t)idx * RSG);
-#pragma unroll
-                for (int i = 0; i < RSG / 4; ++i) {
-                    const float4 v = valid ? __ldg(rp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w;
-                }
+                const int tn = t + 2 < ntiles ? t + 2 : g, sn = t + 2 < ntiles ? s : s + 1;
+                idx_next = (sn < a.nsteps && tn < ntiles) ? tile_index(sn, tn) : -2;     // -2: no further tile
             }
-            if (pendB) { waitB(); pendB = false; }      // previous tile's weight-gradient MMAs released S_x / S_h*
-            {
-                float xh[KX], xl[KX];
+            if (pendB) { waitB(); pendB = false; }      // previous tile's weight-gradient MMAs released X / H1 / H2
+            // stagger the two pipelines: group 1 starts its tile when group 0 has issued G2, so that one group's
+            // epilogues run under the other group's MMAs instead of both waiting on the tensor pipe together
+            if (g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");
+            TCT(1)
+            // ---------------- x (+ ones column) -> X image pair ----------------
 #pragma unroll
-                for (int f = 0; f < KX; ++f) {
-                    const float v = f < O ? rec[f] : ((f == O && valid) ? 1.f : 0.f);
-                    xh[f] = tc::tf32_hi(v); xl[f] = v - xh[f];
-                }
+            for (int c = 0; c < NXC; ++c) {
+                float xv[8];
 #pragma unroll
-                for (int c = 0; c < NKX; ++c) {
-                    tc::tmem_st8(tg + TC_ACT + 8 * c, xh + 8 * c);
-                    tc::tmem_st8(tg + TC_ACT + 32 + 8 * c, xl + 8 * c);
-                    float xv[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) xv[i] = xh[8 * c + i] + xl[8 * c + i];
-                    store_pair8(rowx, (uint32_t)c, rowx, (uint32_t)c + 4u, swz, xv);      // a1 in features 8c.., a2 in features 32+8c..
-                }
+                for (int i = 0; i < 8; ++i) { const int f = 8 * c + i; xv[i] = f < O ? rec[f] : ((f == O && valid) ? 1.f : 0.f); }
+                store_pair8(rowx, (uint32_t)c, rowx, (uint32_t)c + 4u, swz, xv);      // a1: features 8c.., a2: features 32+8c..
             }
+            const bool row_valid = valid;
+            // per-row scalars of this tile (the record registers are re-used for the next tile after E3)
+            float r_act[8], r_vo[8], r_rt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                r_act[i] = i < A ? rec[OP + i] : 0.f;
+                r_vo[i] = i < M ? rec[OP + A + 1 + i] : 0.f;
+                r_rt[i] = i < M ? rec[OP + A + 1 + M + i] : 0.f;
+            }
+            const float r_lpo = rec[OP + A], r_adv = rec[OP + A + 1 + 2 * M];
+            if (idx_next != -2) load_rec(idx_next);       // in flight until the next tile starts
+            TCT(2)
             pre_issue();
-            if (issuer) {
+            TCT(3)
+            if (issue_warp && tc::elect_one()) {
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < NKX; ++ks) {       // small terms first
-                    tc::mma_tf32_ts(tACC, tACT + 32 + 8 * ks, tc::desc_advance(dW1h, ks * 2048), ID_FWD, ks > 0);
-                    tc::mma_tf32_ts(tACC, tACT + 8 * ks, tc::desc_advance(dW1l, ks * 2048), ID_FWD, 1);
-                }
-#pragma unroll
-                for (int ks = 0; ks < NKX; ++ks) tc::mma_tf32_ts(tACC, tACT + 8 * ks, tc::desc_advance(dW1h, ks * 2048), ID_FWD, 1);
+                for (int ks = 0; ks < NK1; ++ks)
+                    mma3(tACC, tc::desc_advance(dXa_k, 32 * ks), tc::desc_advance(dXb_k, 32 * ks), tc::desc_advance(dW1a_k, 32 * ks),
+                         tc::desc_advance(dW1b_k, 32 * ks), ID_KK, ks > 0);
                 tc::mma_commit(mbA);
             }
+            TCT(4)
             // ---------------- E1: h1 = tanh(Z1) ----------------
             waitA();
+            TCT(5)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                float z[32], hi[32];
+                float z[32], dd[32];
                 tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { z[i] = fast_tanh(z[i]); hi[i] = tc::tf32_hi(z[i]); }
-                tc::tmem_st32(tg + TC_ACT + 32 * hh, hi);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) hi[i] = z[i] - hi[i];
-                tc::tmem_st32(tg + TC_ACT + 64 + 32 * hh, hi);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) z[i] *= TC_SH;
+                for (int i = 0; i < 32; ++i) { z[i] = fast_tanh(z[i] * (1.f / TC_SW)); dd[i] = fmaf(-z[i], z[i], 1.f); z[i] *= TC_SH; }
+                tc::tmem_st32(tg + TC_D1 + 32 * hh, dd);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_pair8(rowh1, (uint32_t)(4 * hh + c), rowh1 + 16384, (uint32_t)(4 * hh + c), swz, z + 8 * c);
             }
+            TCT(6)
             pre_issue();
-            if (issuer) {
+            TCT(7)
+            if (issue_warp && tc::elect_one()) {
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    tc::mma_tf32_ts(tACC, tACT + 64 + 8 * ks, tc::desc_advance(dW2h, ks * 2048), ID_FWD, ks > 0);
-                    tc::mma_tf32_ts(tACC, tACT + 8 * ks, tc::desc_advance(dW2l, ks * 2048), ID_FWD, 1);
-                }
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(tACC, tACT + 8 * ks, tc::desc_advance(dW2h, ks * 2048), ID_FWD, 1);
+                for (int ks = 0; ks < 4; ++ks)
+                    mma3(tACC, tc::desc_advance(dH1a_k, 32 * ks), tc::desc_advance(dH1b_k, 32 * ks), tc::desc_advance(dW2a_k, 32 * ks),
+                         tc::desc_advance(dW2b_k, 32 * ks), ID_KK, ks > 0);
                 tc::mma_commit(mbA);
             }
+            if (g == 0 && t + 1 < ntiles) asm volatile("bar.arrive 3, 256;" ::: "memory");   // release group 1's tile t + 1
+            TCT(8)
             // ---------------- E2: h2 = tanh(Z2 + b2) ----------------
             waitA();
+            TCT(9)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                float z[32], lo[32];
+                float z[32], dd[32];
                 tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 bv = *reinterpret_cast<const float4 *>(b2s + 32 * hh + i);
-                    z[i] += bv.x; z[i + 1] += bv.y; z[i + 2] += bv.z; z[i + 3] += bv.w;
+                    z[i] = fmaf(z[i], 1.f / (TC_SH * TC_SW), bv.x); z[i + 1] = fmaf(z[i + 1], 1.f / (TC_SH * TC_SW), bv.y);
+                    z[i + 2] = fmaf(z[i + 2], 1.f / (TC_SH * TC_SW), bv.z); z[i + 3] = fmaf(z[i + 3], 1.f / (TC_SH * TC_SW), bv.w);
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { z[i] = fast_tanh(z[i]); lo[i] = tc::tf32_hi(z[i]); }
-                tc::tmem_st32(tg + TC_ACT + 32 * hh, lo);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) lo[i] = z[i] - lo[i];
-                tc::tmem_st32(tg + TC_ACT + 64 + 32 * hh, lo);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) z[i] *= TC_SH;
+                for (int i = 0; i < 32; ++i) { z[i] = fast_tanh(z[i]); dd[i] = fmaf(-z[i], z[i], 1.f); z[i] *= TC_SH; }
+                tc::tmem_st32(tg + TC_D2 + 32 * hh, dd);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hh + c), rowh2 + 16384, (uint32_t)(4 * hh + c), swz, z + 8 * c);
             }
+            TCT(10)
             pre_issue();
-            if (issuer) {
+            TCT(11)
+            if (issue_warp && tc::elect_one()) {
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    tc::mma_tf32_ts(tACC, tACT + 64 + 8 * ks, tc::desc_advance(dWhh, ks * 256), ID_HEAD, ks > 0);
-                    tc::mma_tf32_ts(tACC, tACT + 8 * ks, tc::desc_advance(dWhl, ks * 256), ID_HEAD, 1);
-                }
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(tACC, tACT + 8 * ks, tc::desc_advance(dWhh, ks * 256), ID_HEAD, 1);
+                for (int ks = 0; ks < 4; ++ks)
+                    mma3(tACC, tc::desc_advance(dH2a_k, 32 * ks), tc::desc_advance(dH2b_k, 32 * ks), tc::desc_advance(dWh1_k, 32 * ks),
+                         tc::desc_advance(dWh2_k, 32 * ks), ID_HEAD, ks > 0);
                 tc::mma_commit(mbA);
             }
+            TCT(12)
             // ---------------- E3: per-row loss and d loss / d head ----------------
             waitA();
+            TCT(13)
             {
                 float ho[8], dq[8];
                 tc::tmem_ld8(tg + TC_ACC, ho);
@@ -419,21 +405,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                         if (d < A) {
                             const float ls = lss[d];
                             const float iv = expf(-2.f * ls);
-                            const float diff = rec[OP + d] - (ho[d] + bhs[d]);
+                            const float diff = r_act[d] - fmaf(ho[d], 1.f / (TC_SH * TC_SW), bhs[d]);
                             lp += -0.5f * (diff * diff * iv) - ls - 0.91893853320467274178f;
                             diffv[d] = diff; ivv[d] = iv;
                         }
                     }
-                    const float ratio = expf(lp - rec[OP + A]);
-                    const float adv = rec[OP + A + 1 + 2 * M];
+                    const float ratio = expf(lp - r_lpo);
+                    const float adv = r_adv;
                     const float surr1 = ratio * adv;
                     const float rcl = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
                     const float surr2 = rcl * adv;
                     const float w1 = surr1 < surr2 ? 1.f : (surr1 == surr2 ? 0.5f : 0.f);
                     const float inr = (ratio >= 1.f - clip && ratio <= 1.f + clip) ? 1.f : 0.f;
                     const float dmin = w1 * adv + (1.f - w1) * adv * inr;
-                    const float dlp = valid ? -inv_mb * dmin * ratio : 0.f;
-                    if (valid) loss_act -= fminf(surr1, surr2);
+                    const float dlp = row_valid ? -inv_mb * dmin * ratio : 0.f;
+                    if (row_valid) loss_act -= fminf(surr1, surr2);
 #pragma unroll
                     for (int d = 0; d < 8; ++d) {
                         const float go = dlp * diffv[d] * ivv[d];                 // d loss / d mean
@@ -446,14 +432,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                     for (int m = 0; m < 8; ++m) {
                         float go = 0.f;
                         if (m < M) {
-                            const float V = ho[m] + bhs[m], vo = rec[OP + A + 1 + m], R = rec[OP + A + 1 + M + m];
+                            const float V = fmaf(ho[m], 1.f / (TC_SH * TC_SW), bhs[m]), vo = r_vo[m], R = r_rt[m];
                             const float dlt = V - vo;
                             const float vcl = vo + fminf(fmaxf(dlt, -clip), clip);
                             const float ea = V - R, eb = vcl - R;
                             const float la = ea * ea, lb = eb * eb;
                             const float wa = la > lb ? 1.f : (la == lb ? 0.5f : 0.f);
                             const float pas = (dlt >= -clip && dlt <= clip) ? 1.f : 0.f;
-                            if (valid) { loss_val += fmaxf(la, lb); go = vscale * (wa * 2.f * ea + (1.f - wa) * 2.f * eb * pas); }
+                            if (row_valid) { loss_val += fmaxf(la, lb); go = vscale * (wa * 2.f * ea + (1.f - wa) * 2.f * eb * pas); }
                         }
                         gbh[m] += go;
                         dq[m] = go * TC_SD;
@@ -461,127 +447,138 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                 }
                 store_pair8(rowx, 3u, rowx, 7u, swz, dq);          // a1 in features 24..31, a2 in features 56..63
             }
+            TCT(14)
             pre_issue();
-            if (issuer) {
+            TCT(15)
+            if (issue_warp && tc::elect_one()) {
                 tc::tc_fence_after();
-                // dz2pre = dOut Wh: K window = X features 16..31 (x16.., ones, padding | dOut) against [zeros | Wh^T]
-                tc::mma_f16(tACC, dXb_k, dWhTa, ID_BWD, 0);
-                tc::mma_f16(tACC, dXa_k, dWhTb, ID_BWD, 1);
-                tc::mma_f16(tACC, dXa_k, dWhTa, ID_BWD, 1);
+                // dz2pre = dOut Wh: K window of 16 X features starting at dOut against [Wh rows 0..7 | zero rows]
+                mma3(tACC, dXdo_a, dXdo_b, dWh1_mn, dWh2_mn, ID_KM, 0);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {                                               // dWh^T += h2^T dOut
-                    tc::mma_f16(tmem + TC_GWH, tc::desc_advance(dH2b_mn, ks * 2048), tc::desc_advance(dXa_do, ks * 2048), ID_GWH, 1);
-                    tc::mma_f16(tmem + TC_GWH, tc::desc_advance(dH2a_mn, ks * 2048), tc::desc_advance(dXb_do, ks * 2048), ID_GWH, 1);
-                    tc::mma_f16(tmem + TC_GWH, tc::desc_advance(dH2a_mn, ks * 2048), tc::desc_advance(dXa_do, ks * 2048), ID_GWH, 1);
-                }
+                for (int ks = 0; ks < 8; ++ks)                                                 // dWh^T += h2^T dOut
+                    mma3(tmem + TC_GWH, tc::desc_advance(dH2a_mn, 2048 * ks), tc::desc_advance(dH2b_mn, 2048 * ks),
+                         tc::desc_advance(dXa_do, 2048 * ks), tc::desc_advance(dXb_do, 2048 * ks), ID_GWH, 1);
                 tc::mma_commit(mbA);
             }
+            TCT(16)
             // ---------------- E4: dz2 = dz2pre (1 - h2^2) ----------------
             waitA();
+            TCT(17)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                float z[32], hi[32], lo[32];
+                float z[32], dd[32];
                 tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
-                tc::tmem_ld32(tg + TC_ACT + 32 * hh, hi);
-                tc::tmem_ld32(tg + TC_ACT + 64 + 32 * hh, lo);
+                tc::tmem_ld32(tg + TC_D2 + 32 * hh, dd);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float hv = hi[i] + lo[i];
-                    z[i] = z[i] * (1.f / TC_SW) * fmaf(-hv, hv, 1.f);      // dz2 (still x 2^12)
-                }
+                for (int i = 0; i < 32; ++i) z[i] = z[i] * (1.f / TC_SW) * dd[i];           // dz2 (still x 2^12)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hh + c), rowh2 + 16384, (uint32_t)(4 * hh + c), swz, z + 8 * c);
             }
+            TCT(18)
             pre_issue();
-            if (issuer) {
+            TCT(19)
+            if (issue_warp && tc::elect_one()) {
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {                                               // dz1pre = dz2 W2
-                    tc::mma_f16(tACC, tc::desc_advance(dH2b_k, ks * 32), tc::desc_advance(dW2Ta, ks * 32), ID_BWD, ks > 0);
-                    tc::mma_f16(tACC, tc::desc_advance(dH2a_k, ks * 32), tc::desc_advance(dW2Tb, ks * 32), ID_BWD, 1);
-                }
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) tc::mma_f16(tACC, tc::desc_advance(dH2a_k, ks * 32), tc::desc_advance(dW2Ta, ks * 32), ID_BWD, 1);
+                for (int ks = 0; ks < 4; ++ks)                                                 // dz1pre = dz2 W2
+                    mma3(tACC, tc::desc_advance(dH2a_k, 32 * ks), tc::desc_advance(dH2b_k, 32 * ks), tc::desc_advance(dW2a_mn, 2048 * ks),
+                         tc::desc_advance(dW2b_mn, 2048 * ks), ID_KM, ks > 0);
                 tc::mma_commit(mbA);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {                                               // dW2 += dz2^T h1
-                    tc::mma_f16(tmem + TC_GW2, tc::desc_advance(dH2b_mn, ks * 2048), tc::desc_advance(dH1a_mn, ks * 2048), ID_GW2, 1);
-                    tc::mma_f16(tmem + TC_GW2, tc::desc_advance(dH2a_mn, ks * 2048), tc::desc_advance(dH1b_mn, ks * 2048), ID_GW2, 1);
-                    tc::mma_f16(tmem + TC_GW2, tc::desc_advance(dH2a_mn, ks * 2048), tc::desc_advance(dH1a_mn, ks * 2048), ID_GW2, 1);
-                }
+                for (int ks = 0; ks < 8; ++ks)                                                 // dW2 += dz2^T h1
+                    mma3(tmem + TC_GW2, tc::desc_advance(dH2a_mn, 2048 * ks), tc::desc_advance(dH2b_mn, 2048 * ks),
+                         tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks), ID_GW2, 1);
                 tc::mma_commit(mbB);
             }
-            // ---------------- E5: dz1 = dz1pre (1 - h1^2), h1 = (a1 + a2) / 2^8 from its smem pair ----------------
+            TCT(20)
+            // ---------------- E5: dz1 = dz1pre (1 - h1^2) ----------------
             waitA();
+            TCT(21)
             {
                 float dz[64];
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    float z[32];
-                    tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
+                    float dd[32];
+                    tc::tmem_ld32(tg + TC_ACC + 32 * hh, dz + 32 * hh);
+                    tc::tmem_ld32(tg + TC_D1 + 32 * hh, dd);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t off = (((uint32_t)(4 * hh + c)) ^ swz) << 4;
-                        const uint4 u1 = *reinterpret_cast<const uint4 *>(rowh1 + off);
-                        const uint4 u2 = *reinterpret_cast<const uint4 *>(rowh1 + 16384 + off);
-                        const uint32_t w1[4] = {u1.x, u1.y, u1.z, u1.w}, w2[4] = {u2.x, u2.y, u2.z, u2.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 fa = unpack_h2(w1[i]), fb = unpack_h2(w2[i]);
-                            const float ha = (fa.x + fb.x) * (1.f / TC_SH), hb = (fa.y + fb.y) * (1.f / TC_SH);
-                            dz[32 * hh + 8 * c + 2 * i] = z[8 * c + 2 * i] * (1.f / TC_SW) * fmaf(-ha, ha, 1.f);
-                            dz[32 * hh + 8 * c + 2 * i + 1] = z[8 * c + 2 * i + 1] * (1.f / TC_SW) * fmaf(-hb, hb, 1.f);
-                        }
-                    }
+                    for (int i = 0; i < 32; ++i) dz[32 * hh + i] = dz[32 * hh + i] * (1.f / TC_SW) * dd[i];
                 }
+                TCT(22)
                 waitB();                                   // dW2 MMAs are done reading h1
+                TCT(23)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) store_pair8(rowh1, (uint32_t)c, rowh1 + 16384, (uint32_t)c, swz, dz + 8 * c);
             }
+            TCT(24)
             pre_issue();
-            if (issuer) {
+            TCT(25)
+            if (issue_warp && tc::elect_one()) {
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {            // [dW1 | db1 ; db2] += [dz1 | dz2]^T [x | 1 | dOut]
-                    tc::mma_f16(tmem + TC_G1X, tc::desc_advance(dH1b_mn, ks * 2048), tc::desc_advance(dXa_mn, ks * 2048), ID_G1X, 1);
-                    tc::mma_f16(tmem + TC_G1X, tc::desc_advance(dH1a_mn, ks * 2048), tc::desc_advance(dXb_mn, ks * 2048), ID_G1X, 1);
-                    tc::mma_f16(tmem + TC_G1X, tc::desc_advance(dH1a_mn, ks * 2048), tc::desc_advance(dXa_mn, ks * 2048), ID_G1X, 1);
-                }
+                for (int ks = 0; ks < 8; ++ks)              // [dW1 | db1 ; db2] += [dz1 | dz2]^T [x | 1 | dOut]
+                    mma3(tmem + TC_G1X, tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks),
+                         tc::desc_advance(dXa_mn, 2048 * ks), tc::desc_advance(dXb_mn, 2048 * ks), ID_G1X, 1);
                 tc::mma_commit(mbB);
             }
+            TCT(26)
             pendB = true;
         }   // tiles
+        TCT(27)
 
         // ================= step tail =================
         if (pendB) { waitB(); pendB = false; }
+        TCT(28)
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
-
-        float gr[60];
-        tc::tmem_ld32(tq + TC_GW2 + 32 * hcol, gr);
-        tc::tmem_ld16(tq + TC_G1X + 16 * hcol, gr + 32);
-        if (hcol == 0) tc::tmem_ld8(tq + TC_GWH, gr + 48);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) gr[i] *= 1.f / (TC_SD * TC_SH);            // dW2   = (dz2 2^12)^T (h1 2^8)
-#pragma unroll
-        for (int i = 32; i < 48; ++i) gr[i] *= 1.f / TC_SD;                     // dW1.. = (dz 2^12)^T x
-#pragma unroll
-        for (int i = 48; i < 56; ++i) gr[i] *= 1.f / (TC_SD * TC_SH);           // dWh^T = (h2 2^8)^T (dOut 2^12)
-        {   // hand the accumulator cells I own back zeroed for the next step
-            float z[32];
+        TCT(29)
+        {   // gradients: TMEM -> GR (shared memory, parameter order), accumulator cells handed back zeroed
+            float gw[32], gx[16], gh[8], z[32];
+            tc::tmem_ld32(tq + TC_GW2 + 32 * hcol, gw);
+            tc::tmem_ld16(tq + TC_G1X + 16 * hcol, gx);
+            if (hcol == 0) tc::tmem_ld8(tq + TC_GWH, gh);
+            tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) z[i] = 0.f;
             tc::tmem_st32(tq + TC_GW2 + 32 * hcol, z);
             tc::tmem_st16(tq + TC_G1X + 16 * hcol, z);
             if (hcol == 0) tc::tmem_st8(tq + TC_GWH, z);
+            if (lane < 16) {                               // dW2 rows: (dz2 2^12)^T (h1 2^8)
+                float *dst = GR + oW2 + (16 * q + lane) * H + 32 * hcol;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(gw[i] * (1.f / (TC_SD * TC_SH)), gw[i + 1] * (1.f / (TC_SD * TC_SH)),
+                                                                         gw[i + 2] * (1.f / (TC_SD * TC_SH)), gw[i + 3] * (1.f / (TC_SD * TC_SH)));
+                if (hcol == 0) {                           // dWh^T rows: (h2 2^8)^T (dOut 2^12)
+                    const int k = 16 * q + lane;
+#pragma unroll
+                    for (int aa = 0; aa < 8; ++aa)
+                        if (aa < KH) GR[oWh + aa * H + k] = gh[aa] * (1.f / (TC_SD * TC_SH));
+                }
+            }
+            if (q < 2) {                                   // dW1 | db1 rows: (dz1 2^12)^T [x | 1]
+                const int j = 32 * q + lane;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = 16 * hcol + i;
+                    if (c < O) GR[j * O + c] = gx[i] * (1.f / TC_SD);
+                    else if (c == O) GR[ob1 + j] = gx[i] * (1.f / TC_SD);
+                }
+            } else if (hcol == O / 16) {                   // db2: (dz2 2^12)^T 1
+                GR[ob2 + 32 * (q - 2) + lane] = gx[O % 16] * (1.f / TC_SD);
+            }
         }
         // head bias / logstd gradients: per-thread row sums -> warp -> CTA
+        constexpr int KHM = A > M ? A : M;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { gbh[i] = warp_sum(gbh[i]); gls[i] = warp_sum(gls[i]); }
+        for (int i = 0; i < KHM; ++i) gbh[i] = warp_sum(gbh[i]);
+        if (actor) {
+#pragma unroll
+            for (int i = 0; i < A; ++i) gls[i] = warp_sum(gls[i]);
+        }
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { part[warp * 16 + i] = gbh[i]; part[warp * 16 + 8 + i] = gls[i]; }
@@ -592,170 +589,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             sh_d[1] = 1.0 / sqrt(1.0 - b2pow);
         }
         __syncthreads();
-        gr[56] = 0.f; gr[57] = 0.f; gr[58] = 0.f; gr[59] = 0.f;
         if (tid < 8) {
             float sb = 0.f, sl_ = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { sb += part[w * 16 + tid]; sl_ += part[w * 16 + 8 + tid]; }
-            gr[56] = sb; gr[57] = sl_ - ecoef;          // d(-ecoef * entropy) / d logstd = -ecoef
+            if (tid < KH) GR[obh + tid] = sb;
+            if (actor && tid < A) GR[ols + tid] = sl_ - ecoef;          // d(-ecoef * entropy) / d logstd = -ecoef
         }
-        float sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 58; ++i) {
-            if (!((vmask >> i) & 1ull)) gr[i] = 0.f;
-            sq = fmaf(gr[i], gr[i], sq);
-        }
-        sq = block_sum(sq, red);
+        if (tid < 4 && nH + tid < 4 * n4) GR[nH + tid] = 0.f;            // padding of the last float4
+        __syncthreads();
+        TCT(30)
 
         if (a.grad_only) {
-#pragma unroll
-            for (int i = 0; i < 58; ++i) {
-                const int e = tc_own(i, q, hcol, lane, tid, O, KH, A, actor);
-                if (e >= 0) a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gr[i];
-            }
+            for (int e = tid; e < nH; e += TC_THREADS) a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = GR[e];
             break;
         }
 
-        float *ssq2 = ssqS + 2 * (s & 1);     // slots alternate by step parity: the peer may still be reading the last ones
-        if (tid == 0) {
-            ssq2[rank] = sq;
-            st_dsmem1(mapa_u32(smem_u32(ssq2 + rank), rank ^ 1u), sq);
-        }
-        // moments of my slots: in flight across the cluster barrier
-        float4 m4[TC_SLOT4], v4[TC_SLOT4];
+        // my float4 slices of the half: gradient from GR, moments from the workspace (in flight across the barrier)
+        constexpr int NS = (TC_NHP / 4 + TC_THREADS - 1) / TC_THREADS;      // 6
+        float4 g4[NS], m4[NS], v4[NS];
+        float sq = 0.f;
 #pragma unroll
-        for (int s4 = 0; s4 < TC_SLOT4; ++s4) {
-            if ((vmask >> (4 * s4)) & 0xFull) { m4[s4] = __ldcg(mM + s4 * TC_THREADS + tid); v4[s4] = __ldcg(mV + s4 * TC_THREADS + tid); }
-            else { m4[s4] = make_float4(0.f, 0.f, 0.f, 0.f); v4[s4] = m4[s4]; }
+        for (int u = 0; u < NS; ++u) {
+            const int i4 = tid + u * TC_THREADS;
+            if (i4 < n4) {
+                g4[u] = reinterpret_cast<const float4 *>(GR)[i4];
+                m4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wM) + i4);
+                v4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wV) + i4);
+                sq = fmaf(g4[u].x, g4[u].x, sq); sq = fmaf(g4[u].y, g4[u].y, sq);
+                sq = fmaf(g4[u].z, g4[u].z, sq); sq = fmaf(g4[u].w, g4[u].w, sq);
+            }
         }
+        // squared norm: per-warp partials go to my own slots and straight to the peer CTA; the cluster barrier is the
+        // only synchronisation, every thread then adds the 16 partials in one fixed order
+        sq = warp_sum(sq);
+        float *ssq2 = ssqS + 16 * (s & 1);    // slots alternate by step parity: the peer may still be reading the last ones
+        if (lane == 0) {
+            ssq2[rank * 8 + warp] = sq;
+            st_dsmem1(mapa_u32(smem_u32(ssq2 + rank * 8 + warp), rank ^ 1u), sq);
+        }
+        TCT(31)
         sync_group<2>();
-        const float tot = ssq2[0] + ssq2[1];
+        TCT(32)
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tot += ssq2[i];
         const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
         const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
-
-#define TC_ADAM(P_, G_, M_, V_)                                                         \
-        {                                                                               \
-            const float gq = (G_) * coef;                                               \
-            M_ = fmaf(gq - M_, omb1, M_);                                               \
-            V_ = fmaf(omb2 * gq, gq, V_ * b2f);                                         \
-            const float denom = fmaf(fast_sqrt(V_), ibc2, aeps);                        \
-            P_ -= step_size * __fdividef(M_, denom);                                    \
-        }
-        // ---- W2 rows: slots 0..31 (lanes < 16): row j, features 32h .. 32h+31 ----
-        if (lane < 16) {
-            const int j = 16 * q + lane;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int w = (8 * hcol + c) * 256 + j * 4;
-                const float4 ph = *reinterpret_cast<const float4 *>(W2h + w), pl = *reinterpret_cast<const float4 *>(W2l + w);
-                float p0 = ph.x + pl.x, p1 = ph.y + pl.y, p2 = ph.z + pl.z, p3 = ph.w + pl.w;
-                TC_ADAM(p0, gr[4 * c], m4[c].x, v4[c].x) TC_ADAM(p1, gr[4 * c + 1], m4[c].y, v4[c].y)
-                TC_ADAM(p2, gr[4 * c + 2], m4[c].z, v4[c].z) TC_ADAM(p3, gr[4 * c + 3], m4[c].w, v4[c].w)
-                const float4 nh = make_float4(tc::tf32_hi(p0), tc::tf32_hi(p1), tc::tf32_hi(p2), tc::tf32_hi(p3));
-                *reinterpret_cast<float4 *>(W2h + w) = nh;
-                *reinterpret_cast<float4 *>(W2l + w) = make_float4(p0 - nh.x, p1 - nh.y, p2 - nh.z, p3 - nh.w);
-                const int k0 = 32 * hcol + 4 * c;
-                const float pv[4] = {p0, p1, p2, p3};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {                 // backward copy: row k, feature j, fp16 pair x 2^8
-                    const __half t1 = __float2half_rn(pv[e] * TC_SW);
-                    const int hw = sw128_hw(k0 + e, j);
-                    W2Ta[hw] = t1; W2Tb[hw] = __float2half_rn(pv[e] * TC_SW - __half2float(t1));
+        for (int u = 0; u < NS; ++u) {
+            const int i4 = tid + u * TC_THREADS;
+            if (i4 < n4) {
+                float4 p4 = reinterpret_cast<const float4 *>(PM)[i4];
+#define TC_ADAM(cc)                                                                     \
+                {                                                                       \
+                    const float gq = g4[u].cc * coef;                                   \
+                    m4[u].cc = fmaf(gq - m4[u].cc, omb1, m4[u].cc);                     \
+                    v4[u].cc = fmaf(omb2 * gq, gq, v4[u].cc * b2f);                     \
+                    const float denom = fmaf(fast_sqrt(v4[u].cc), ibc2, aeps);          \
+                    p4.cc -= step_size * __fdividef(m4[u].cc, denom);                   \
                 }
-            }
-        }
-        // ---- slots 32..47: W1 | b1 rows (quadrants 0,1) or b2 (quadrants 2,3), columns 16h .. 16h+15 ----
-        if (q < 2) {
-            const int j = 32 * q + lane;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int ch = 4 * hcol + c;
-                if (ch < NCH1) {
-                    const int w = ch * 256 + j * 4;
-                    const float4 ph = *reinterpret_cast<const float4 *>(W1h + w), pl = *reinterpret_cast<const float4 *>(W1l + w);
-                    float p0 = ph.x + pl.x, p1 = ph.y + pl.y, p2 = ph.z + pl.z, p3 = ph.w + pl.w;
-                    TC_ADAM(p0, gr[32 + 4 * c], m4[8 + c].x, v4[8 + c].x) TC_ADAM(p1, gr[33 + 4 * c], m4[8 + c].y, v4[8 + c].y)
-                    TC_ADAM(p2, gr[34 + 4 * c], m4[8 + c].z, v4[8 + c].z) TC_ADAM(p3, gr[35 + 4 * c], m4[8 + c].w, v4[8 + c].w)
-                    // columns past the bias keep gradient 0 and moments 0: the update leaves their zeros in place
-                    const float4 nh = make_float4(tc::tf32_hi(p0), tc::tf32_hi(p1), tc::tf32_hi(p2), tc::tf32_hi(p3));
-                    *reinterpret_cast<float4 *>(W1h + w) = nh;
-                    *reinterpret_cast<float4 *>(W1l + w) = make_float4(p0 - nh.x, p1 - nh.y, p2 - nh.z, p3 - nh.w);
-                }
-            }
-        } else if (hcol == O / 16) {
-            const int j = 32 * (q - 2) + lane;
-            constexpr int c = (O % 16) / 4, e = O % 4;
-            float p = b2s[j];
-            float gg = e == 0 ? gr[32 + 4 * c] : (e == 1 ? gr[33 + 4 * c] : (e == 2 ? gr[34 + 4 * c] : gr[35 + 4 * c]));
-            float mm = e == 0 ? m4[8 + c].x : (e == 1 ? m4[8 + c].y : (e == 2 ? m4[8 + c].z : m4[8 + c].w));
-            float vv = e == 0 ? v4[8 + c].x : (e == 1 ? v4[8 + c].y : (e == 2 ? v4[8 + c].z : v4[8 + c].w));
-            TC_ADAM(p, gg, mm, vv)
-            b2s[j] = p;
-            if (e == 0) { m4[8 + c].x = mm; v4[8 + c].x = vv; } else if (e == 1) { m4[8 + c].y = mm; v4[8 + c].y = vv; }
-            else if (e == 2) { m4[8 + c].z = mm; v4[8 + c].z = vv; } else { m4[8 + c].w = mm; v4[8 + c].w = vv; }
-        }
-        // ---- slots 48..55: head weights Wh[a][k], k = 16q + lane (column half 0, lanes < 16) ----
-        if (hcol == 0 && lane < 16) {
-            const int k = 16 * q + lane;
-            float pn[8];
-#pragma unroll
-            for (int aa = 0; aa < 8; ++aa) {
-                const int w = (k >> 2) * 32 + aa * 4 + (k & 3);
-                float p = Whh[w] + Whl[w];
-                float mm = aa < 4 ? (&m4[12].x)[aa] : (&m4[13].x)[aa - 4];
-                float vv = aa < 4 ? (&v4[12].x)[aa] : (&v4[13].x)[aa - 4];
-                TC_ADAM(p, gr[48 + aa], mm, vv)
-                if (aa < 4) { (&m4[12].x)[aa] = mm; (&v4[12].x)[aa] = vv; } else { (&m4[13].x)[aa - 4] = mm; (&v4[13].x)[aa - 4] = vv; }
-                const float nh = tc::tf32_hi(p);
-                Whh[w] = nh; Whl[w] = p - nh;
-                pn[aa] = p * TC_SW;
-            }
-            uint4 q1, q2;                                     // backward copy: row k, 8 halfwords a, fp16 pair x 2^8
-            split_h2(pn[0], pn[1], q1.x, q2.x); split_h2(pn[2], pn[3], q1.y, q2.y);
-            split_h2(pn[4], pn[5], q1.z, q2.z); split_h2(pn[6], pn[7], q1.w, q2.w);
-            *reinterpret_cast<uint4 *>(WhTa + k * 8) = q1;
-            *reinterpret_cast<uint4 *>(WhTb + k * 8) = q2;
-        }
-        // ---- slots 56, 57: head bias and logstd ----
-        if (tid < 8) {
-            if (tid < KH) { float p = bhs[tid]; TC_ADAM(p, gr[56], m4[14].x, v4[14].x) bhs[tid] = p; }
-            if (actor && tid < A) { float p = lss[tid]; TC_ADAM(p, gr[57], m4[14].y, v4[14].y) lss[tid] = p; }
-        }
+                TC_ADAM(x) TC_ADAM(y) TC_ADAM(z) TC_ADAM(w)
 #undef TC_ADAM
-#pragma unroll
-        for (int s4 = 0; s4 < TC_SLOT4; ++s4)
-            if ((vmask >> (4 * s4)) & 0xFull) { __stcg(mM + s4 * TC_THREADS + tid, m4[s4]); __stcg(mV + s4 * TC_THREADS + tid, v4[s4]); }
+                reinterpret_cast<float4 *>(PM)[i4] = p4;
+                __stcg(reinterpret_cast<float4 *>(wM) + i4, m4[u]);
+                __stcg(reinterpret_cast<float4 *>(wV) + i4, v4[u]);
+                const int e0 = 4 * i4;
+                if (e0 >= oW2 && e0 < ob2) {           // W2[j][k0..k0+3]: four consecutive halfwords of each image
+                    const int j = (e0 - oW2) >> 6, k0 = (e0 - oW2) & 63;
+                    const float w0 = p4.x * TC_SW, w1 = p4.y * TC_SW, w2 = p4.z * TC_SW, w3 = p4.w * TC_SW;
+                    const float h0 = round11(w0), h1 = round11(w1), h2 = round11(w2), h3 = round11(w3);
+                    const int hw = sw128_hw(j, k0);
+                    *reinterpret_cast<uint2 *>(W2a + hw) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                    *reinterpret_cast<uint2 *>(W2b + hw) = make_uint2(pack_h2(w0 - h0, w1 - h1), pack_h2(w2 - h2, w3 - h3));
+                } else {
+                    put_param(e0, p4.x);
+                    if (e0 + 1 < nH) put_param(e0 + 1, p4.y);
+                    if (e0 + 2 < nH) put_param(e0 + 2, p4.z);
+                    if (e0 + 3 < nH) put_param(e0 + 3, p4.w);
+                }
+            }
+        }
+        TCT(33)
         tc::tmem_st_wait();
         tc::fence_async_smem();
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
+        TCT(34)
     }   // steps
 
     // ---------------- write back ----------------
     if (!a.grad_only) {
-        __threadfence_block();
-        for (int s4 = 0; s4 < TC_SLOT4; ++s4) {
-            if (!((vmask >> (4 * s4)) & 0xFull)) continue;
-            const float4 mq = __ldcg(mM + s4 * TC_THREADS + tid), vq = __ldcg(mV + s4 * TC_THREADS + tid);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int sidx = 4 * s4 + c;
-                const int e = tc_own(sidx, q, hcol, lane, tid, O, KH, A, actor);
-                if (e < 0) continue;
-                const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
-                a.adam_m[gi] = (&mq.x)[c]; a.adam_v[gi] = (&vq.x)[c];
-                float p;
-                if (sidx < 32) { const int j = 16 * q + lane, k = 32 * hcol + sidx, w = (k >> 2) * 256 + j * 4 + (k & 3); p = W2h[w] + W2l[w]; }
-                else if (sidx < 48) {
-                    const int cc = 16 * hcol + sidx - 32;
-                    if (q < 2) { const int j = 32 * q + lane, w = (cc >> 2) * 256 + j * 4 + (cc & 3); p = W1h[w] + W1l[w]; }
-                    else p = b2s[32 * (q - 2) + lane];
-                } else if (sidx < 56) { const int k = 16 * q + lane, aa = sidx - 48, w = (k >> 2) * 32 + aa * 4 + (k & 3); p = Whh[w] + Whl[w]; }
-                else if (sidx == 56) p = bhs[tid];
-                else p = lss[tid];
-                a.params[gi] = p;
-            }
+        for (int e = tid; e < nH; e += TC_THREADS) {
+            const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
+            a.params[gi] = PM[e];
+            a.adam_m[gi] = __ldcg(wM + e); a.adam_v[gi] = __ldcg(wV + e);
         }
     }
     {   // losses: the critic CTA reports the value loss, the actor CTA the action loss and the entropy

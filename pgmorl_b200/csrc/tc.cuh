@@ -41,6 +41,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"(a), "r"(parity) : "memory");
 }
 
+// one lane of a fully active warp (the MMA issuer). The operands of tcgen05.mma live in UNIFORM registers: every value
+// that feeds a descriptor must be provably warp-uniform (derive it from uniform_warp_idx(), kernel arguments and
+// constants), otherwise the compiler wraps each MMA in a lane-serialising R2UR loop (~70 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- proxy / tcgen05 fences -------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

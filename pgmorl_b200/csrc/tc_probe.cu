@@ -399,3 +399,60 @@ extern "C" int pgm_tc_layout_probe(float *out, int M, int N, int a_mn, int b_mn,
     PGM_CUDA(cudaGetLastError());
     return PGM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// MMA pacing microbenchmark (profiles/tc_mma_bench.py): 48 kind::f16 MMAs of shape M x N x 16 from SWIZZLE_128B
+// images (zeros), rotating over NACC accumulators; every descriptor input is warp-uniform (see tc::elect_one).
+// out[2*rep] = cycles from the first issue to completion, out[2*rep+1] = cycles spent issuing.
+namespace pgm {
+template <int NACC>
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(float *out, int M, int N, int a_mn, int b_mn, int a_step, int b_step) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    for (int i = tid; i < 49152; i += 128) sm[i] = 0.f;      // 192 KB of zero operands
+    tc::fence_async_smem(); tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t tmem = tc::uniform_u32(tmem_base_s);
+    uint32_t phase = 0;
+    const uint32_t aA = tc::smem_addr(sm), aB = tc::smem_addr(sm) + 98304;
+    const uint64_t da = a_mn ? tc::make_desc(aA, 16384, 1024, 2) : tc::make_desc(aA, 16, 1024, 2);
+    const uint64_t db = b_mn ? tc::make_desc(aB, 16384, 1024, 2) : tc::make_desc(aB, 16, 1024, 2);
+    const uint32_t id = tc::idesc_f16(M, N, a_mn, b_mn);
+    for (int rep = 0; rep < 3; ++rep) {
+        tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+        const long long t0 = clock64();
+        if (warp == 0 && tc::elect_one()) {
+#pragma unroll
+            for (int i = 0; i < 48; ++i)
+                tc::mma_f16(tmem + (uint32_t)(i % NACC) * 128u, tc::desc_advance(da, (uint32_t)((i & 7) * a_step)),
+                            tc::desc_advance(db, (uint32_t)((i & 7) * b_step)), id, 1);
+            tc::mma_commit(&bar);
+        }
+        const long long t1 = clock64();
+        tc::mbar_wait(&bar, phase); phase ^= 1;
+        tc::tc_fence_after();
+        const long long t2 = clock64();
+        if (tid == 0) { out[2 * rep] = (float)(t2 - t0); out[2 * rep + 1] = (float)(t1 - t0); }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace pgm
+
+extern "C" int pgm_tc_mma_bench(float *out, int M, int N, int a_mn, int b_mn, int nmma, int nacc, int a_step, int b_step, void *stream) {
+    PGM_REQUIRE(out && nmma == 48 && nacc >= 1 && nacc <= 3 && N * nacc <= 512, "pgm_tc_mma_bench: nmma must be 48, nacc 1..3");
+    const size_t smem = 49152 * sizeof(float);
+    auto go = [&](auto kern) -> int {
+        PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, 128, smem, (cudaStream_t)stream>>>(out, M, N, a_mn, b_mn, a_step, b_step);
+        PGM_CUDA(cudaGetLastError());
+        return PGM_OK;
+    };
+    if (nacc == 1) return go(pgm::tc_mma_bench_kernel<1>);
+    if (nacc == 2) return go(pgm::tc_mma_bench_kernel<2>);
+    return go(pgm::tc_mma_bench_kernel<3>);
+}

@@ -53,3 +53,15 @@ D = run(64, 16, 1, 0, 0, 1, 64, 16, 4096, 1024, 256, 128, ltA=2)
 lanes = [32 * (j // 16) + j % 16 for j in range(64)]
 exp = np.array([[hw(k, m, 4096) for k in range(16)] for m in range(64)], dtype=np.float32)
 print("M=64 A MN-major SW128 f16: match", np.array_equal(exp, D[lanes, :16]))
+# (6) K-major A windows that start at 16-byte (not 32-byte) offsets, and one that runs past the 128-byte row
+for off in (48, 80, 112):
+    D = run(128, 16, 0, 0, 0, 1, 128, 16, 16, 1024, 256, 128, ltA=2, offA=off)
+    exp = np.array([[hw(m, off // 2 + k, 0) if off // 2 + k < 64 else -1 for k in range(16)] for m in range(128)], dtype=np.float32)
+    ok = (exp == D[:, :16]) | (exp < 0)
+    print(f"A K-major SW128 f16 off={off}: in-row part matches:", bool(ok.all()), " row0:", D[0, :16])
+# (7) B K-major SW128 N=16 whose second 8-row group lives elsewhere (SBO = 2048): rows 8..15 = words at +2048 B
+D = run(128, 16, 0, 0, 1, 0, 128, 16, 2048, 128, 16, 2048, ltB=2)
+print("B K-major N=16 sbo=2048: k=0 n=0..15:", D[0, :16], " expect n>=8 ->", [hw(n - 8, 0, 0) + 1024 for n in range(8, 16)])
+# (8) B MN-major SW128 (N = 64 features, K = 16 rows) whose second 8-K-row group lives at +2048 B
+D = run(128, 64, 0, 1, 1, 0, 128, 64, 2048, 128, 16384, 2048, ltB=2)
+print("B MN-major sbo=2048: n=0 k=0..15:", D[:16, 0], " expect k>=8 ->", [(hw(k - 8, 0, 0) + 1024) % 2048 for k in range(8, 16)])
