@@ -572,6 +572,9 @@ constexpr int K3_CLUSTER_TC = 32;   // `cluster` value that selects the tensor-c
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
     pl.tc = false; pl.off_mv = 0;
+    // auto: the tensor-core path (2 CTAs per task) wins as soon as the FFMA path can no longer give every task a 16-CTA
+    // cluster (measured on a B200, profiles/k3_sweep.py: parity at P = 8..12, 2x at 18, 3.1x from 37 tasks on)
+    if (cluster == 0 && k3_tc_dims(O, A, M) && P >= 8) cluster = K3_CLUSTER_TC;
     if (cluster == K3_CLUSTER_TC) {
         PGM_REQUIRE(k3_tc_dims(O, A, M), "ppo: the tensor-core path is built for (O,A,M) = (17,6,2) and (11,3,3), got (%d,%d,%d)", O, A, M);
         pl.tc = true; pl.C = 2; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
@@ -595,7 +598,7 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     PGM_REQUIRE(O >= 1 && O <= 384 && A >= 1 && A <= 32 && M >= 1 && M <= 16,
                 "ppo: unsupported dims O=%d A=%d M=%d (O<=384, A<=32, M<=16)", O, A, M);
     PGM_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16,
-                "ppo: cluster must be 0,1,2,4,8,16 or 32 (tensor cores) (got %d)", cluster);
+                "ppo: cluster must be 0 (auto), 1, 2, 4, 8, 16 (FP32 FFMA paths) or 32 (tensor-core path) (got %d)", cluster);
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
         C = 2;      // one CTA per network half is the throughput configuration (large populations)

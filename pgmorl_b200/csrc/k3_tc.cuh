@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     double *sh_d = (double *)(smem_raw + sl.misc + 1024);
     uint64_t *mbars = (uint64_t *)(smem_raw + sl.misc + 1024 + 32);     // [0..1] chain (A), [2..3] weight grads (B)
     uint32_t *tmem_ptr_s = (uint32_t *)(smem_raw + sl.misc + 1024 + 64);
-    uint64_t *mbA = mbars + g, *mbB = mbars + 2 + g;
     const float *b2s = PM + ob2, *bhs = PM + obh, *lss = PM + ols;
 
     // ---------------- one-time setup ----------------
@@ -213,15 +212,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const int32_t *perm = a.perm + ((a.perm_shared || a.grad_only) ? 0 : (size_t)task * a.E * a.S);
     const float *recg = a.rec + (size_t)task * a.S * RSG;
     const int ntiles = (a.mb + 127) >> 7;
-    uint32_t phA = 0, phB = 0;
-    bool pendB = false;
-    const bool issue_warp = (warp & 3) == 0;        // first warp of each group issues that group's MMAs (one elected lane)
+    uint32_t phA[2] = {0u, 0u}, phB[2] = {0u, 0u};    // mbarrier phase parities (per tile of the pair)
+    bool pendB[2] = {false, false};
 
-    // ---- descriptors (constant for the whole launch); images are [rows][64 halfwords], SWIZZLE_128B ----
+    // ---- descriptors of tile 0 (tile 1: + TC_GROUP_BYTES); images are [rows][64 halfwords], SWIZZLE_128B ----
     // K-major view (M/N = row, K = feature): SBO = 1024 (next 8 rows), +32 B per K step of 16 features.
     // MN-major view (M/N = feature, K = row): LBO = stride to the next 64-feature block, SBO = 1024 (next 8 K rows),
     // +2048 B per K step of 16 rows.
-    const uint32_t aH1 = tc::smem_addr(S_h1), aH2 = tc::smem_addr(S_h2), aX = tc::smem_addr(S_x);
+    const uint32_t aH1 = tc::smem_addr(smem_raw + sl.grp[0]), aH2 = aH1 + 32768, aX = aH1 + 65536;
     const uint32_t aW1 = tc::smem_addr(W1i), aW2a = tc::smem_addr(W2a), aW2b = tc::smem_addr(W2b);
     const uint32_t aWh1 = tc::smem_addr(WhA1), aWh2 = tc::smem_addr(WhA2);
     auto dK = [](uint32_t addr) { return tc::make_desc(addr, 16, 1024, 2); };
@@ -240,15 +238,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const uint64_t dXa_do = dMN(aX + 48, 16384), dXb_do = dMN(aX + 112, 16384);       // dOut: 24..31 | 56..63
     constexpr uint32_t ID_KK = tc::idesc_f16(128, 64, 0, 0), ID_HEAD = tc::idesc_f16(128, 16, 0, 0), ID_KM = tc::idesc_f16(128, 64, 0, 1);
     constexpr uint32_t ID_GWH = tc::idesc_f16(64, 8, 1, 1), ID_GW2 = tc::idesc_f16(64, 64, 1, 1), ID_G1X = tc::idesc_f16(128, 32, 1, 1);
-    const uint32_t tACC = tmem + (uint32_t)g * TC_GSTRIDE + TC_ACC;
     const uint32_t swz = (uint32_t)(r & 7);
-    unsigned char *rowx = S_x + r * 128, *rowh1 = S_h1 + r * 128, *rowh2 = S_h2 + r * 128;   // a2 images at +16384
+    unsigned char *rowx = S_x + r * 128;             // my row of my group's X image (gather, E3)
 
-    auto pre_issue = [&]() {      // my TMEM / smem writes are done and ordered before the group's MMA issue
-        tc::tmem_st_wait(); tc::tmem_ld_wait(); tc::fence_async_smem(); tc::tc_fence_before(); group_bar(g);
-    };
-    auto waitA = [&]() { tc::mbar_wait(mbA, phA); phA ^= 1; tc::tc_fence_after(); };
-    auto waitB = [&]() { tc::mbar_wait(mbB, phB); phB ^= 1; tc::tc_fence_after(); };
+    // everything I wrote (TMEM, smem images) is complete and ordered before the MMAs issued after the barrier
+    auto sync_all = [&]() { tc::tmem_st_wait(); tc::tmem_ld_wait(); tc::fence_async_smem(); tc::tc_fence_before(); __syncthreads(); };
     // 3 MMAs of one K step: a2*b1 + a1*b2 + a1*b1 (small terms first)
     auto mma3 = [&](uint32_t d, uint64_t a1, uint64_t a2, uint64_t b1, uint64_t b2, uint32_t id, uint32_t acc) {
         tc::mma_f16(d, a2, b1, id, acc); tc::mma_f16(d, a1, b2, id, 1); tc::mma_f16(d, a1, b1, id, 1);
@@ -288,112 +282,127 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             loss_ent += ent;
         }
 
-        for (int t = g; t < ntiles; t += 2) {
+        // Tiles are processed in PAIRS (tile tp by group 0, tile tp + 1 by group 1 for the per-row phases). The 64-column
+        // epilogues of EACH tile are done by all 8 warps (warp = lane quadrant x column half), tile 0 then tile 1, so an
+        // epilogue takes half as long and always runs under the other tile's MMAs:
+        //   E(0) | issue G(0) | E(1) [G(0) runs] | issue G(1) | next E(0) [G(1) runs] ...
+        for (int tp = 0; tp < ntiles; tp += 2) {
+            const bool hasB = tp + 1 < ntiles;
+            const int nt = hasB ? 2 : 1;
+            const bool mine = g < nt;                      // my group's tile tp + g exists
             TCT(0)
-            // the tile after this one (same step, or my first tile of the next step): fetch its row index now
-            {
+            if (mine) {   // the tile after mine (same step, or my first tile of the next step): fetch its row index now
+                const int t = tp + g;
                 const int tn = t + 2 < ntiles ? t + 2 : g, sn = t + 2 < ntiles ? s : s + 1;
                 idx_next = (sn < a.nsteps && tn < ntiles) ? tile_index(sn, tn) : -2;     // -2: no further tile
             }
-            if (pendB) { waitB(); pendB = false; }      // previous tile's weight-gradient MMAs released X / H1 / H2
-            // stagger the two pipelines: group 1 starts its tile when group 0 has issued G2, so that one group's
-            // epilogues run under the other group's MMAs instead of both waiting on the tensor pipe together
-            if (g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 2; ++i)                    // previous pair's weight-gradient MMAs released X / H1 / H2
+                if (pendB[i]) { tc::mbar_wait(mbars + 2 + i, phB[i]); phB[i] ^= 1; pendB[i] = false; }
+            tc::tc_fence_after();
+            // ---------------- x (+ ones column) -> X image pair; per-row scalars ----------------
+            bool row_valid = false;
+            float r_act[8], r_vo[8], r_rt[8], r_lpo = 0.f, r_adv = 0.f;
+            if (mine) {
+#pragma unroll
+                for (int c = 0; c < NXC; ++c) {
+                    float xv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int f = 8 * c + i; xv[i] = f < O ? rec[f] : ((f == O && valid) ? 1.f : 0.f); }
+                    store_pair8(rowx, (uint32_t)c, rowx, (uint32_t)c + 4u, swz, xv);      // a1: features 8c.., a2: features 32+8c..
+                }
+                row_valid = valid;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    r_act[i] = i < A ? rec[OP + i] : 0.f;
+                    r_vo[i] = i < M ? rec[OP + A + 1 + i] : 0.f;
+                    r_rt[i] = i < M ? rec[OP + A + 1 + M + i] : 0.f;
+                }
+                r_lpo = rec[OP + A]; r_adv = rec[OP + A + 1 + 2 * M];
+                if (idx_next != -2) load_rec(idx_next);       // in flight until the next pair starts
+            }
             TCT(1)
-            // ---------------- x (+ ones column) -> X image pair ----------------
+            sync_all();
+            if (warp == 0 && tc::elect_one()) {
+                tc::tc_fence_after();
+                for (int i = 0; i < nt; ++i) {
+                    const uint32_t so = (uint32_t)i * TC_GROUP_BYTES, acc = tmem + (uint32_t)i * TC_GSTRIDE + TC_ACC;
 #pragma unroll
-            for (int c = 0; c < NXC; ++c) {
-                float xv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const int f = 8 * c + i; xv[i] = f < O ? rec[f] : ((f == O && valid) ? 1.f : 0.f); }
-                store_pair8(rowx, (uint32_t)c, rowx, (uint32_t)c + 4u, swz, xv);      // a1: features 8c.., a2: features 32+8c..
+                    for (int ks = 0; ks < NK1; ++ks)
+                        mma3(acc, tc::desc_advance(dXa_k, so + 32 * ks), tc::desc_advance(dXb_k, so + 32 * ks),
+                             tc::desc_advance(dW1a_k, 32 * ks), tc::desc_advance(dW1b_k, 32 * ks), ID_KK, ks > 0);
+                    tc::mma_commit(mbars + i);
+                }
             }
-            const bool row_valid = valid;
-            // per-row scalars of this tile (the record registers are re-used for the next tile after E3)
-            float r_act[8], r_vo[8], r_rt[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                r_act[i] = i < A ? rec[OP + i] : 0.f;
-                r_vo[i] = i < M ? rec[OP + A + 1 + i] : 0.f;
-                r_rt[i] = i < M ? rec[OP + A + 1 + M + i] : 0.f;
-            }
-            const float r_lpo = rec[OP + A], r_adv = rec[OP + A + 1 + 2 * M];
-            if (idx_next != -2) load_rec(idx_next);       // in flight until the next tile starts
             TCT(2)
-            pre_issue();
-            TCT(3)
-            if (issue_warp && tc::elect_one()) {
-                tc::tc_fence_after();
+            // ---------------- E1: h1 = tanh(Z1) -> H1 pair, 1 - h1^2 -> TMEM ----------------
 #pragma unroll
-                for (int ks = 0; ks < NK1; ++ks)
-                    mma3(tACC, tc::desc_advance(dXa_k, 32 * ks), tc::desc_advance(dXb_k, 32 * ks), tc::desc_advance(dW1a_k, 32 * ks),
-                         tc::desc_advance(dW1b_k, 32 * ks), ID_KK, ks > 0);
-                tc::mma_commit(mbA);
-            }
-            TCT(4)
-            // ---------------- E1: h1 = tanh(Z1) ----------------
-            waitA();
-            TCT(5)
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            for (int i = 0; i < 2; ++i) {
+                if (i >= nt) break;
+                unsigned char *rowh1 = smem_raw + sl.grp[i] + r * 128;
+                const uint32_t tt = tq + (uint32_t)i * TC_GSTRIDE;
+                tc::mbar_wait(mbars + i, phA[i]); phA[i] ^= 1; tc::tc_fence_after();
+                TCT(3 + 3 * i)
                 float z[32], dd[32];
-                tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
+                tc::tmem_ld32(tt + TC_ACC + 32 * hcol, z);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { z[i] = fast_tanh(z[i] * (1.f / TC_SW)); dd[i] = fmaf(-z[i], z[i], 1.f); z[i] *= TC_SH; }
-                tc::tmem_st32(tg + TC_D1 + 32 * hh, dd);
+                for (int k = 0; k < 32; ++k) { z[k] = fast_tanh(z[k] * (1.f / TC_SW)); dd[k] = fmaf(-z[k], z[k], 1.f); z[k] *= TC_SH; }
+                tc::tmem_st32(tt + TC_D1 + 32 * hcol, dd);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_pair8(rowh1, (uint32_t)(4 * hh + c), rowh1 + 16384, (uint32_t)(4 * hh + c), swz, z + 8 * c);
+                for (int c = 0; c < 4; ++c) store_pair8(rowh1, (uint32_t)(4 * hcol + c), rowh1 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
+                TCT(4 + 3 * i)
+                sync_all();
+                if (warp == 0 && tc::elect_one()) {
+                    tc::tc_fence_after();
+                    const uint32_t so = (uint32_t)i * TC_GROUP_BYTES, acc = tmem + (uint32_t)i * TC_GSTRIDE + TC_ACC;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma3(acc, tc::desc_advance(dH1a_k, so + 32 * ks), tc::desc_advance(dH1b_k, so + 32 * ks),
+                             tc::desc_advance(dW2a_k, 32 * ks), tc::desc_advance(dW2b_k, 32 * ks), ID_KK, ks > 0);
+                    tc::mma_commit(mbars + i);
+                }
+                TCT(5 + 3 * i)
             }
-            TCT(6)
-            pre_issue();
-            TCT(7)
-            if (issue_warp && tc::elect_one()) {
-                tc::tc_fence_after();
+            // ---------------- E2: h2 = tanh(Z2 + b2) -> H2 pair, 1 - h2^2 -> TMEM ----------------
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma3(tACC, tc::desc_advance(dH1a_k, 32 * ks), tc::desc_advance(dH1b_k, 32 * ks), tc::desc_advance(dW2a_k, 32 * ks),
-                         tc::desc_advance(dW2b_k, 32 * ks), ID_KK, ks > 0);
-                tc::mma_commit(mbA);
-            }
-            if (g == 0 && t + 1 < ntiles) asm volatile("bar.arrive 3, 256;" ::: "memory");   // release group 1's tile t + 1
-            TCT(8)
-            // ---------------- E2: h2 = tanh(Z2 + b2) ----------------
-            waitA();
-            TCT(9)
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            for (int i = 0; i < 2; ++i) {
+                if (i >= nt) break;
+                unsigned char *rowh2 = smem_raw + sl.grp[i] + 32768 + r * 128;
+                const uint32_t tt = tq + (uint32_t)i * TC_GSTRIDE;
+                tc::mbar_wait(mbars + i, phA[i]); phA[i] ^= 1; tc::tc_fence_after();
+                TCT(9 + 3 * i)
                 float z[32], dd[32];
-                tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
+                tc::tmem_ld32(tt + TC_ACC + 32 * hcol, z);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bv = *reinterpret_cast<const float4 *>(b2s + 32 * hh + i);
-                    z[i] = fmaf(z[i], 1.f / (TC_SH * TC_SW), bv.x); z[i + 1] = fmaf(z[i + 1], 1.f / (TC_SH * TC_SW), bv.y);
-                    z[i + 2] = fmaf(z[i + 2], 1.f / (TC_SH * TC_SW), bv.z); z[i + 3] = fmaf(z[i + 3], 1.f / (TC_SH * TC_SW), bv.w);
+                for (int k = 0; k < 32; k += 4) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(b2s + 32 * hcol + k);
+                    z[k] = fmaf(z[k], 1.f / (TC_SH * TC_SW), bv.x); z[k + 1] = fmaf(z[k + 1], 1.f / (TC_SH * TC_SW), bv.y);
+                    z[k + 2] = fmaf(z[k + 2], 1.f / (TC_SH * TC_SW), bv.z); z[k + 3] = fmaf(z[k + 3], 1.f / (TC_SH * TC_SW), bv.w);
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { z[i] = fast_tanh(z[i]); dd[i] = fmaf(-z[i], z[i], 1.f); z[i] *= TC_SH; }
-                tc::tmem_st32(tg + TC_D2 + 32 * hh, dd);
+                for (int k = 0; k < 32; ++k) { z[k] = fast_tanh(z[k]); dd[k] = fmaf(-z[k], z[k], 1.f); z[k] *= TC_SH; }
+                tc::tmem_st32(tt + TC_D2 + 32 * hcol, dd);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hh + c), rowh2 + 16384, (uint32_t)(4 * hh + c), swz, z + 8 * c);
-            }
-            TCT(10)
-            pre_issue();
-            TCT(11)
-            if (issue_warp && tc::elect_one()) {
-                tc::tc_fence_after();
+                for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hcol + c), rowh2 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
+                TCT(10 + 3 * i)
+                sync_all();
+                if (warp == 0 && tc::elect_one()) {
+                    tc::tc_fence_after();
+                    const uint32_t so = (uint32_t)i * TC_GROUP_BYTES, acc = tmem + (uint32_t)i * TC_GSTRIDE + TC_ACC;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma3(tACC, tc::desc_advance(dH2a_k, 32 * ks), tc::desc_advance(dH2b_k, 32 * ks), tc::desc_advance(dWh1_k, 32 * ks),
-                         tc::desc_advance(dWh2_k, 32 * ks), ID_HEAD, ks > 0);
-                tc::mma_commit(mbA);
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma3(acc, tc::desc_advance(dH2a_k, so + 32 * ks), tc::desc_advance(dH2b_k, so + 32 * ks),
+                             tc::desc_advance(dWh1_k, 32 * ks), tc::desc_advance(dWh2_k, 32 * ks), ID_HEAD, ks > 0);
+                    tc::mma_commit(mbars + i);
+                }
+                TCT(11 + 3 * i)
             }
-            TCT(12)
-            // ---------------- E3: per-row loss and d loss / d head ----------------
-            waitA();
-            TCT(13)
-            {
+            // ---------------- E3: per-row loss and d loss / d head (each group its own tile) ----------------
+            if (mine) {
+                tc::mbar_wait(mbars + g, g == 0 ? phA[0] : phA[1]); tc::tc_fence_after();
+                TCT(15)
                 float ho[8], dq[8];
                 tc::tmem_ld8(tg + TC_ACC, ho);
                 tc::tmem_ld_wait();
@@ -447,94 +456,101 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                 }
                 store_pair8(rowx, 3u, rowx, 7u, swz, dq);          // a1 in features 24..31, a2 in features 56..63
             }
-            TCT(14)
-            pre_issue();
-            TCT(15)
-            if (issue_warp && tc::elect_one()) {
-                tc::tc_fence_after();
-                // dz2pre = dOut Wh: K window of 16 X features starting at dOut against [Wh rows 0..7 | zero rows]
-                mma3(tACC, dXdo_a, dXdo_b, dWh1_mn, dWh2_mn, ID_KM, 0);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)                                                 // dWh^T += h2^T dOut
-                    mma3(tmem + TC_GWH, tc::desc_advance(dH2a_mn, 2048 * ks), tc::desc_advance(dH2b_mn, 2048 * ks),
-                         tc::desc_advance(dXa_do, 2048 * ks), tc::desc_advance(dXb_do, 2048 * ks), ID_GWH, 1);
-                tc::mma_commit(mbA);
-            }
+            for (int i = 0; i < 2; ++i) if (i < nt) phA[i] ^= 1;   // both head GEMMs are complete once the barrier below is passed
             TCT(16)
-            // ---------------- E4: dz2 = dz2pre (1 - h2^2) ----------------
-            waitA();
-            TCT(17)
+            sync_all();
+            if (warp == 0 && tc::elect_one()) {
+                tc::tc_fence_after();
+                for (int i = 0; i < nt; ++i) {
+                    const uint32_t so = (uint32_t)i * TC_GROUP_BYTES, acc = tmem + (uint32_t)i * TC_GSTRIDE + TC_ACC;
+                    // dz2pre = dOut Wh: K window of 16 X features starting at dOut against [Wh rows 0..7 | zero rows]
+                    mma3(acc, tc::desc_advance(dXdo_a, so), tc::desc_advance(dXdo_b, so), dWh1_mn, dWh2_mn, ID_KM, 0);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+                    for (int ks = 0; ks < 8; ++ks)                                                 // dWh^T += h2^T dOut
+                        mma3(tmem + TC_GWH, tc::desc_advance(dH2a_mn, so + 2048 * ks), tc::desc_advance(dH2b_mn, so + 2048 * ks),
+                             tc::desc_advance(dXa_do, so + 2048 * ks), tc::desc_advance(dXb_do, so + 2048 * ks), ID_GWH, 1);
+                    tc::mma_commit(mbars + i);
+                }
+            }
+            TCT(17)
+            // ---------------- E4: dz2 = dz2pre (1 - h2^2) -> H2 pair (in place) ----------------
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i >= nt) break;
+                unsigned char *rowh2 = smem_raw + sl.grp[i] + 32768 + r * 128;
+                const uint32_t tt = tq + (uint32_t)i * TC_GSTRIDE;
+                tc::mbar_wait(mbars + i, phA[i]); phA[i] ^= 1; tc::tc_fence_after();
+                TCT(18 + 3 * i)
                 float z[32], dd[32];
-                tc::tmem_ld32(tg + TC_ACC + 32 * hh, z);
-                tc::tmem_ld32(tg + TC_D2 + 32 * hh, dd);
+                tc::tmem_ld32(tt + TC_ACC + 32 * hcol, z);
+                tc::tmem_ld32(tt + TC_D2 + 32 * hcol, dd);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) z[i] = z[i] * (1.f / TC_SW) * dd[i];           // dz2 (still x 2^12)
+                for (int k = 0; k < 32; ++k) z[k] = z[k] * (1.f / TC_SW) * dd[k];           // dz2 (still x 2^12)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hh + c), rowh2 + 16384, (uint32_t)(4 * hh + c), swz, z + 8 * c);
-            }
-            TCT(18)
-            pre_issue();
-            TCT(19)
-            if (issue_warp && tc::elect_one()) {
-                tc::tc_fence_after();
+                for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hcol + c), rowh2 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
+                TCT(19 + 3 * i)
+                sync_all();
+                if (warp == 0 && tc::elect_one()) {
+                    tc::tc_fence_after();
+                    const uint32_t so = (uint32_t)i * TC_GROUP_BYTES, acc = tmem + (uint32_t)i * TC_GSTRIDE + TC_ACC;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)                                                 // dz1pre = dz2 W2
-                    mma3(tACC, tc::desc_advance(dH2a_k, 32 * ks), tc::desc_advance(dH2b_k, 32 * ks), tc::desc_advance(dW2a_mn, 2048 * ks),
-                         tc::desc_advance(dW2b_mn, 2048 * ks), ID_KM, ks > 0);
-                tc::mma_commit(mbA);
+                    for (int ks = 0; ks < 4; ++ks)                                                 // dz1pre = dz2 W2
+                        mma3(acc, tc::desc_advance(dH2a_k, so + 32 * ks), tc::desc_advance(dH2b_k, so + 32 * ks),
+                             tc::desc_advance(dW2a_mn, 2048 * ks), tc::desc_advance(dW2b_mn, 2048 * ks), ID_KM, ks > 0);
+                    tc::mma_commit(mbars + i);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)                                                 // dW2 += dz2^T h1
-                    mma3(tmem + TC_GW2, tc::desc_advance(dH2a_mn, 2048 * ks), tc::desc_advance(dH2b_mn, 2048 * ks),
-                         tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks), ID_GW2, 1);
-                tc::mma_commit(mbB);
-            }
-            TCT(20)
-            // ---------------- E5: dz1 = dz1pre (1 - h1^2) ----------------
-            waitA();
-            TCT(21)
-            {
-                float dz[64];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float dd[32];
-                    tc::tmem_ld32(tg + TC_ACC + 32 * hh, dz + 32 * hh);
-                    tc::tmem_ld32(tg + TC_D1 + 32 * hh, dd);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) dz[32 * hh + i] = dz[32 * hh + i] * (1.f / TC_SW) * dd[i];
+                    for (int ks = 0; ks < 8; ++ks)                                                 // dW2 += dz2^T h1
+                        mma3(tmem + TC_GW2, tc::desc_advance(dH2a_mn, so + 2048 * ks), tc::desc_advance(dH2b_mn, so + 2048 * ks),
+                             tc::desc_advance(dH1a_mn, so + 2048 * ks), tc::desc_advance(dH1b_mn, so + 2048 * ks), ID_GW2, 1);
+                    tc::mma_commit(mbars + 2 + i);
                 }
-                TCT(22)
-                waitB();                                   // dW2 MMAs are done reading h1
-                TCT(23)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) store_pair8(rowh1, (uint32_t)c, rowh1 + 16384, (uint32_t)c, swz, dz + 8 * c);
+                TCT(20 + 3 * i)
             }
-            TCT(24)
-            pre_issue();
-            TCT(25)
-            if (issue_warp && tc::elect_one()) {
-                tc::tc_fence_after();
+            // ---------------- E5: dz1 = dz1pre (1 - h1^2) -> H1 pair (in place) ----------------
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)              // [dW1 | db1 ; db2] += [dz1 | dz2]^T [x | 1 | dOut]
-                    mma3(tmem + TC_G1X, tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks),
-                         tc::desc_advance(dXa_mn, 2048 * ks), tc::desc_advance(dXb_mn, 2048 * ks), ID_G1X, 1);
-                tc::mma_commit(mbB);
+            for (int i = 0; i < 2; ++i) {
+                if (i >= nt) break;
+                unsigned char *rowh1 = smem_raw + sl.grp[i] + r * 128;
+                const uint32_t tt = tq + (uint32_t)i * TC_GSTRIDE;
+                tc::mbar_wait(mbars + i, phA[i]); phA[i] ^= 1; tc::tc_fence_after();
+                TCT(24 + 4 * i)
+                float z[32], dd[32];
+                tc::tmem_ld32(tt + TC_ACC + 32 * hcol, z);
+                tc::tmem_ld32(tt + TC_D1 + 32 * hcol, dd);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) z[k] = z[k] * (1.f / TC_SW) * dd[k];
+                TCT(25 + 4 * i)
+                tc::mbar_wait(mbars + 2 + i, phB[i]); phB[i] ^= 1;     // dW2 MMAs are done reading h1
+                TCT(26 + 4 * i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_pair8(rowh1, (uint32_t)(4 * hcol + c), rowh1 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
+                sync_all();
+                if (warp == 0 && tc::elect_one()) {
+                    tc::tc_fence_after();
+                    const uint32_t so = (uint32_t)i * TC_GROUP_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)              // [dW1 | db1 ; db2] += [dz1 | dz2]^T [x | 1 | dOut]
+                        mma3(tmem + TC_G1X, tc::desc_advance(dH1a_mn, so + 2048 * ks), tc::desc_advance(dH1b_mn, so + 2048 * ks),
+                             tc::desc_advance(dXa_mn, so + 2048 * ks), tc::desc_advance(dXb_mn, so + 2048 * ks), ID_G1X, 1);
+                    tc::mma_commit(mbars + 2 + i);
+                }
+                pendB[i] = true;
+                TCT(27 + 4 * i)
             }
-            TCT(26)
-            pendB = true;
-        }   // tiles
-        TCT(27)
+        }   // tile pairs
 
         // ================= step tail =================
-        if (pendB) { waitB(); pendB = false; }
-        TCT(28)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (pendB[i]) { tc::mbar_wait(mbars + 2 + i, phB[i]); phB[i] ^= 1; pendB[i] = false; }
+        TCT(32)
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
-        TCT(29)
+        TCT(33)
         {   // gradients: TMEM -> GR (shared memory, parameter order), accumulator cells handed back zeroed
             float gw[32], gx[16], gh[8], z[32];
             tc::tmem_ld32(tq + TC_GW2 + 32 * hcol, gw);
@@ -598,7 +614,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         }
         if (tid < 4 && nH + tid < 4 * n4) GR[nH + tid] = 0.f;            // padding of the last float4
         __syncthreads();
-        TCT(30)
+        TCT(34)
 
         if (a.grad_only) {
             for (int e = tid; e < nH; e += TC_THREADS) a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = GR[e];
@@ -628,9 +644,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             ssq2[rank * 8 + warp] = sq;
             st_dsmem1(mapa_u32(smem_u32(ssq2 + rank * 8 + warp), rank ^ 1u), sq);
         }
-        TCT(31)
+        TCT(35)
         sync_group<2>();
-        TCT(32)
+        TCT(36)
         float tot = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) tot += ssq2[i];
@@ -670,13 +686,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                 }
             }
         }
-        TCT(33)
+        TCT(37)
         tc::tmem_st_wait();
         tc::fence_async_smem();
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
-        TCT(34)
+        TCT(38)
     }   // steps
 
     // ---------------- write back ----------------

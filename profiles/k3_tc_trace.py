@@ -36,16 +36,18 @@ off = (-pop.workspace.data_ptr()) % 256
 n = P * 2 * 2 * 2 * 2 * 40
 raw = pop.workspace[off + off_tr: off + off_tr + n * 8].cpu().numpy().view(np.int64)
 tr = raw.reshape(P * 2, 2, 2, 2, 40)      # cta, group, who, step, mark
-names = {0: "tile0", 1: "rec+waitB", 2: "x->tmem/smem", 3: "bar", 4: "issueG1", 5: "waitG1", 6: "E1", 7: "bar", 8: "issueG2",
-         9: "waitG2", 10: "E2", 11: "bar", 12: "issueG3", 13: "waitG3", 14: "E3", 15: "bar", 16: "issueG4+GWh", 17: "waitG4",
-         18: "E4", 19: "bar", 20: "issueG5+GW2", 21: "waitG5", 22: "E5a", 23: "waitGW2", 24: "E5b", 25: "bar",
-         26: "issueG1X", 27: "-", 28: "waitG1X", 29: "sync", 30: "readout+ssq", 31: "ldmv", 32: "clusterbar", 33: "adam",
-         34: "sync"}
+names = {1: "waitB+X", 2: "sync+issueG1", 3: "waitG1(0)", 4: "E1(0)", 5: "sync+issueG2(0)", 6: "waitG1(1)", 7: "E1(1)",
+         8: "sync+issueG2(1)", 9: "waitG2(0)", 10: "E2(0)", 11: "sync+issueG3(0)", 12: "waitG2(1)", 13: "E2(1)",
+         14: "sync+issueG3(1)", 15: "waitG3", 16: "E3", 17: "sync+issueG4,GWh", 18: "waitG4(0)", 19: "E4(0)",
+         20: "sync+issueG5,GW2(0)", 21: "waitG4(1)", 22: "E4(1)", 23: "sync+issueG5,GW2(1)", 24: "waitG5(0)", 25: "E5a(0)",
+         26: "waitGW2(0)", 27: "E5b+sync+issueG1X(0)", 28: "waitG5(1)", 29: "E5a(1)", 30: "waitGW2(1)",
+         31: "E5b+sync+issueG1X(1)", 32: "waitG1X", 33: "sync", 34: "readout", 35: "ssq+ldmv", 36: "clusterbar", 37: "adam",
+         38: "sync"}
 for cta in (0, 1):
     for g in (0, 1):
         for who in (0, 1):
-            c = tr[cta, g, who, 1, :35].astype(np.int64)
+            c = tr[cta, g, who, 1, :39].astype(np.int64)
             dur = np.diff(c)
             print(f"cta {cta} ({'actor' if cta == 0 else 'critic'}) group {g} thread r={'0 (issuer)' if who == 0 else '64'}:"
-                  f" step = {int(tr[cta, g, who, 1, 34] - tr[cta, g, who, 0, 34])} cycles")
+                  f" step = {int(tr[cta, g, who, 1, 38] - tr[cta, g, who, 0, 38])} cycles")
             print("   ", " ".join(f"{names[i + 1]}={int(x)}" for i, x in enumerate(dur)))
