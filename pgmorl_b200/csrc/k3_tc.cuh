@@ -6,7 +6,7 @@
 // pipelines ("groups"); group g owns the 128-row tiles t = g, g+2, ... of every minibatch, thread = row = TMEM lane.
 // While one group waits for its MMAs the other runs its epilogue, which hides the issue->complete latency of the
 // dependent GEMM chain.  Per tile:
-//   gather record (prefetched) -> x pair to the X image
+//   gather (coalesced, 8 lanes per 128-byte record, prefetched one pair ahead) -> x pair to the X image, scalars to smem
 //   G1  Z1 = x W1^T (+b1 through a ones column);   E1  h1 = tanh(Z1) -> H1 image pair, 1 - h1^2 -> TMEM
 //   G2  Z2 = h1 W2^T;                              E2  h2 = tanh(Z2 + b2) -> H2 image pair, 1 - h2^2 -> TMEM
 //   G3  head = h2 Wh^T (N = 16);                   E3  per-row loss, d loss / d head -> X image (thread owns its row)
@@ -37,7 +37,7 @@ constexpr int TC_NHP = 6144;                 // padded size of one half's parame
 constexpr float TC_SH = 256.f, TC_SD = 4096.f, TC_SW = 256.f;   // scales of activations / backward signals / weights
 
 struct TcSmem {   // byte offsets inside dynamic shared memory
-    uint32_t grp[2], W2a, W2b, W1, WhA1, WhA2, WhZ, PM, misc, total;
+    uint32_t grp[2], W2a, W2b, W1, WhA1, WhA2, WhZ, PM, SC, misc, total;
 };
 __host__ __device__ inline TcSmem tc_smem_layout() {
     TcSmem s; uint32_t o = 0;
@@ -46,6 +46,7 @@ __host__ __device__ inline TcSmem tc_smem_layout() {
     s.W1 = o; o += 8192;                                      // [64 rows j][features 0..31 a1 | 32..63 a2], column O = bias
     s.WhA1 = o; o += 1024; s.WhA2 = o; o += 1024; s.WhZ = o; o += 1024;   // [8 rows a][64 halfwords k]; Z = zero rows 8..15
     s.PM = o; o += TC_NHP * 4;                                // FP32 master parameters of the half, reference order
+    s.SC = o; o += 2 * 128 * 48;                              // per-row scalars of the two tiles in flight (<= 12 floats per row)
     s.misc = o; o += TC_MISC_BYTES; s.total = o;
     return s;
 }
@@ -99,7 +100,7 @@ __device__ __forceinline__ void put_pair(__half *ia, int hwa, __half *ib, int hw
 }
 
 // PGM_K3_TRACE builds: clock64 marks of threads r == 0 (MMA issuer) and r == 64 of each group, steps 8 and 9
-// (profiles/k3_tc_trace.py): trace[(((cta*2 + group)*2 + who)*2 + step - 8)*40 + mark]
+// (profiles/k3_tc_trace.py): trace[(((cta*2 + group)*2 + who)*2 + step - 8)*48 + mark]
 #ifdef PGM_K3_TRACE
 #define TCT(i) if (trace_on) a.trace[trace_base + (i)] = clock64();
 #else
@@ -112,7 +113,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     constexpr int NK1 = (O + 1 + 15) / 16;           // K steps of layer 1: x, ones column at index O, zero padding
     constexpr int NXC = (O + 1 + 7) / 8;             // 16-byte chunks of x (8 features each) written per row
     constexpr int RSG = (OP + A + 2 * M + 2 + 3) / 4 * 4;
-    static_assert(O + 1 <= 24 && A <= 8 && M <= 8 && RSG <= 32, "k3_tc: dims outside the tensor-core path");
+    constexpr int NP = RSG / 4, NPX = OP / 4;        // 16-byte pieces per record; pieces that hold x
+    constexpr int NIT = (128 * NP + TC_THREADS - 1) / TC_THREADS;    // gather items per thread per tile
+    static_assert(O + 1 <= 24 && A <= 8 && M <= 8 && RSG <= 32 && O % 4 != 0 && RSG - OP <= 12, "k3_tc: dims outside the tensor-core path");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     __half *W1i = (__half *)(smem_raw + sl.W1);
     __half *WhA1 = (__half *)(smem_raw + sl.WhA1), *WhA2 = (__half *)(smem_raw + sl.WhA2);
     float *PM = (float *)(smem_raw + sl.PM);
+    float *SC = (float *)(smem_raw + sl.SC);                            // [2 tiles][128 rows][12]
     float *GR = (float *)(smem_raw + sl.grp[0]);                         // gradient staging (step tail only)
     float *misc = (float *)(smem_raw + sl.misc);
     float *red = misc + TCM_RED, *part = misc + TCM_PART, *ssqS = misc + TCM_SSQ;
@@ -248,30 +252,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         tc::mma_f16(d, a2, b1, id, acc); tc::mma_f16(d, a1, b2, id, 1); tc::mma_f16(d, a1, b1, id, 1);
     };
 
-    // record gather: the row index of tile (s, t) and then its packed record, prefetched one tile ahead
-    float rec[RSG];
-    bool valid = false;
-    auto tile_index = [&](int s, int t) -> int {
-        const int ep = s / a.B, bb = s - ep * a.B;
-        const int rowi = t * 128 + r;
-        return rowi < a.mb ? ld_nc_s32(perm + (size_t)ep * a.S + (size_t)bb * a.mb + rowi) : -1;
-    };
-    auto load_rec = [&](int idx) {
-        valid = idx >= 0;
-        const float4 *rp = reinterpret_cast<const float4 *>(recg + (size_t)(valid ? idx : 0) * RSG);
+    // Record gather, cooperative and coalesced: item f = tid + 256 k of a tile is (row f / NP, 16-byte piece f % NP), so a
+    // warp instruction reads whole 128-byte lines. x pieces go straight into the X image (fp16 pair), scalar pieces into
+    // SC for the row's owner (E3). The records of the NEXT pair and the row indices of the pair after it are in flight.
+    float4 rcv[2][NIT];
+    int ridx[2][NIT];
+    auto pair_after = [&](int &ss, int &tt) { if (tt + 2 < ntiles) tt += 2; else { ss += 1; tt = 0; } };
+    // Loads are issued unconditionally from clamped addresses and masked when CONSUMED: a select on a load's result
+    // would make the issuing thread wait for it (8 serialised L2 round trips instead of 8 loads in flight).
+    uint32_t vm_idx = 0u, vm_rec = 0u;             // bit (i * NIT + k): item k of tile i is a real row (indices / records in flight)
+    auto load_idx = [&](int ss, int tt) {
+        const bool sv = ss < a.nsteps;
+        const int sc_ = sv ? ss : 0;
+        const int ep = sc_ / a.B, bb = sc_ - ep * a.B;
+        const int32_t *pb = perm + (size_t)ep * a.S + (size_t)bb * a.mb;
+        vm_idx = 0u;
 #pragma unroll
-        for (int i = 0; i < RSG / 4; ++i) {
-            const float4 v = valid ? ld_nc_f4(rp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w;
-        }
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int f = tid + TC_THREADS * k, rowi = (tt + i) * 128 + f / NP;
+                const bool ok = sv && tt + i < ntiles && f < 128 * NP && rowi < a.mb;
+                ridx[i][k] = ld_nc_s32(pb + (ok ? rowi : 0));
+                vm_idx |= (ok ? 1u : 0u) << (i * NIT + k);
+            }
     };
-    int idx_next = g < ntiles ? tile_index(0, g) : -1;
-    if (g < ntiles) load_rec(idx_next);
+    auto load_recs = [&]() {
+        vm_rec = vm_idx;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int f = tid + TC_THREADS * k;
+                rcv[i][k] = ld_nc_f4(reinterpret_cast<const float4 *>(recg + (size_t)ridx[i][k] * RSG) + f % NP);
+            }
+    };
+    load_idx(0, 0);
+    load_recs();
+    {
+        int ss = 0, tt = 0;
+        pair_after(ss, tt);
+        load_idx(ss, tt);
+    }
 
     for (int s = 0; s < a.nsteps; ++s) {
 #ifdef PGM_K3_TRACE
         const bool trace_on = a.trace && (s == 8 || s == 9) && (r == 0 || r == 64);
-        const size_t trace_base = ((((size_t)blockIdx.x * 2 + g) * 2 + (r == 64)) * 2 + (s - 8)) * 40;
+        const size_t trace_base = ((((size_t)blockIdx.x * 2 + g) * 2 + (r == 64)) * 2 + (s - 8)) * 48;
 #endif
         float gbh[8], gls[8];
 #pragma unroll
@@ -291,36 +318,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             const int nt = hasB ? 2 : 1;
             const bool mine = g < nt;                      // my group's tile tp + g exists
             TCT(0)
-            if (mine) {   // the tile after mine (same step, or my first tile of the next step): fetch its row index now
-                const int t = tp + g;
-                const int tn = t + 2 < ntiles ? t + 2 : g, sn = t + 2 < ntiles ? s : s + 1;
-                idx_next = (sn < a.nsteps && tn < ntiles) ? tile_index(sn, tn) : -2;     // -2: no further tile
-            }
 #pragma unroll
             for (int i = 0; i < 2; ++i)                    // previous pair's weight-gradient MMAs released X / H1 / H2
                 if (pendB[i]) { tc::mbar_wait(mbars + 2 + i, phB[i]); phB[i] ^= 1; pendB[i] = false; }
             tc::tc_fence_after();
-            // ---------------- x (+ ones column) -> X image pair; per-row scalars ----------------
-            bool row_valid = false;
-            float r_act[8], r_vo[8], r_rt[8], r_lpo = 0.f, r_adv = 0.f;
-            if (mine) {
+            TCT(39)
+            // ---------------- records -> X image pair (x, ones column) and SC (per-row scalars) ----------------
+            const uint32_t vm_now = vm_rec;
 #pragma unroll
-                for (int c = 0; c < NXC; ++c) {
-                    float xv[8];
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { const int f = 8 * c + i; xv[i] = f < O ? rec[f] : ((f == O && valid) ? 1.f : 0.f); }
-                    store_pair8(rowx, (uint32_t)c, rowx, (uint32_t)c + 4u, swz, xv);      // a1: features 8c.., a2: features 32+8c..
+                for (int k = 0; k < NIT; ++k) {
+                    const int f = tid + TC_THREADS * k;
+                    if (i < nt && f < 128 * NP) {
+                        const int row = f / NP, pc = f % NP;
+                        const bool ok = (vm_now >> (i * NIT + k)) & 1u;
+                        const float4 v = ok ? rcv[i][k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pc < NPX) {
+                            float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (4 * pc + e >= O) xv[e] = (4 * pc + e == O && ok) ? 1.f : 0.f;
+                            const float h0 = round11(xv[0]), h1 = round11(xv[1]), h2 = round11(xv[2]), h3 = round11(xv[3]);
+                            unsigned char *xr = smem_raw + sl.grp[i] + 65536 + row * 128 + (pc & 1) * 8;
+                            const uint32_t c = (uint32_t)(pc >> 1), sw = (uint32_t)(row & 7);
+                            *reinterpret_cast<uint2 *>(xr + ((c ^ sw) << 4)) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                            *reinterpret_cast<uint2 *>(xr + (((c + 4u) ^ sw) << 4)) =
+                                make_uint2(pack_h2(xv[0] - h0, xv[1] - h1), pack_h2(xv[2] - h2, xv[3] - h3));
+                        } else {
+                            *reinterpret_cast<float4 *>(SC + (i * 128 + row) * 12 + 4 * (pc - NPX)) = v;
+                        }
+                    }
                 }
-                row_valid = valid;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    r_act[i] = i < A ? rec[OP + i] : 0.f;
-                    r_vo[i] = i < M ? rec[OP + A + 1 + i] : 0.f;
-                    r_rt[i] = i < M ? rec[OP + A + 1 + M + i] : 0.f;
-                }
-                r_lpo = rec[OP + A]; r_adv = rec[OP + A + 1 + 2 * M];
-                if (idx_next != -2) load_rec(idx_next);       // in flight until the next pair starts
+            TCT(40)
+            // prefetch: records of the next pair (their row indices arrived long ago), row indices of the pair after it
+            load_recs();
+            TCT(41)
+            {
+                int ss = s, tt = tp;
+                pair_after(ss, tt); pair_after(ss, tt);
+                load_idx(ss, tt);
             }
+            TCT(42)
             TCT(1)
             sync_all();
             if (warp == 0 && tc::elect_one()) {
@@ -405,6 +443,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                 TCT(15)
                 float ho[8], dq[8];
                 tc::tmem_ld8(tg + TC_ACC, ho);
+                // my row's scalars: action[A] | logp_old | value_old[M] | return[M] | advantage
+                float sc[12];
+                {
+                    const float4 *sp = reinterpret_cast<const float4 *>(SC + (g * 128 + r) * 12);
+                    const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                    sc[8] = s2.x; sc[9] = s2.y; sc[10] = s2.z; sc[11] = s2.w;
+                }
+                const bool row_valid = (tp + g) * 128 + r < a.mb;
                 tc::tmem_ld_wait();
                 if (actor) {
                     float lp = 0.f, diffv[8], ivv[8];
@@ -414,13 +461,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                         if (d < A) {
                             const float ls = lss[d];
                             const float iv = expf(-2.f * ls);
-                            const float diff = r_act[d] - fmaf(ho[d], 1.f / (TC_SH * TC_SW), bhs[d]);
+                            const float diff = sc[d] - fmaf(ho[d], 1.f / (TC_SH * TC_SW), bhs[d]);
                             lp += -0.5f * (diff * diff * iv) - ls - 0.91893853320467274178f;
                             diffv[d] = diff; ivv[d] = iv;
                         }
                     }
-                    const float ratio = expf(lp - r_lpo);
-                    const float adv = r_adv;
+                    const float ratio = expf(lp - sc[A]);
+                    const float adv = sc[A + 1 + 2 * M];
                     const float surr1 = ratio * adv;
                     const float rcl = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
                     const float surr2 = rcl * adv;
@@ -441,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                     for (int m = 0; m < 8; ++m) {
                         float go = 0.f;
                         if (m < M) {
-                            const float V = fmaf(ho[m], 1.f / (TC_SH * TC_SW), bhs[m]), vo = r_vo[m], R = r_rt[m];
+                            const float V = fmaf(ho[m], 1.f / (TC_SH * TC_SW), bhs[m]), vo = sc[A + 1 + m], R = sc[A + 1 + M + m];
                             const float dlt = V - vo;
                             const float vcl = vo + fminf(fmaxf(dlt, -clip), clip);
                             const float ea = V - R, eb = vcl - R;

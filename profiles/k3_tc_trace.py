@@ -33,9 +33,9 @@ torch.cuda.synchronize()
 r256 = lambda b: (b + 255) // 256 * 256
 off_tr = r256(P * S * 32 * 4) + r256(P * 2 * 64 * 4) + r256(P * 16 * 4) + r256(P * 64 * 4) + r256(P * 2 * 2 * 6144 * 4)
 off = (-pop.workspace.data_ptr()) % 256
-n = P * 2 * 2 * 2 * 2 * 40
+n = P * 2 * 2 * 2 * 2 * 48
 raw = pop.workspace[off + off_tr: off + off_tr + n * 8].cpu().numpy().view(np.int64)
-tr = raw.reshape(P * 2, 2, 2, 2, 40)      # cta, group, who, step, mark
+tr = raw.reshape(P * 2, 2, 2, 2, 48)      # cta, group, who, step, mark
 names = {1: "waitB+X", 2: "sync+issueG1", 3: "waitG1(0)", 4: "E1(0)", 5: "sync+issueG2(0)", 6: "waitG1(1)", 7: "E1(1)",
          8: "sync+issueG2(1)", 9: "waitG2(0)", 10: "E2(0)", 11: "sync+issueG3(0)", 12: "waitG2(1)", 13: "E2(1)",
          14: "sync+issueG3(1)", 15: "waitG3", 16: "E3", 17: "sync+issueG4,GWh", 18: "waitG4(0)", 19: "E4(0)",
@@ -51,3 +51,6 @@ for cta in (0, 1):
             print(f"cta {cta} ({'actor' if cta == 0 else 'critic'}) group {g} thread r={'0 (issuer)' if who == 0 else '64'}:"
                   f" step = {int(tr[cta, g, who, 1, 38] - tr[cta, g, who, 0, 38])} cycles")
             print("   ", " ".join(f"{names[i + 1]}={int(x)}" for i, x in enumerate(dur)))
+            x = tr[cta, g, who, 1]
+            print("    X phase detail: waits", int(x[39] - x[0]), "x-stores", int(x[40] - x[39]), "scalars", int(x[41] - x[40]),
+                  "load_rec", int(x[42] - x[41]), "index+rest", int(x[1] - x[42]))
