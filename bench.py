@@ -342,6 +342,25 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         k3_ms = float(stages[2])
         k3_tflops = P * S * upd / (k3_ms * 1e-3) / 1e12
+        # which K3 kernel ran: the tensor-core path (tcgen05 on FP16 operand pairs) is chosen explicitly (cluster 32) or by
+        # the library from 8 tasks on for the shapes it is built for; otherwise the FP32 FFMA cluster kernels
+        tc = args.cluster == 32 or (args.cluster == 0 and P >= 8 and (d.obs, d.act, d.obj) in ((17, 6, 2), (11, 3, 3)))
+        common = {"unit": "TFLOP/s", "achieved": k3_tflops, "traffic": None, "algorithmic_flops_per_launch": P * S * upd,
+                  "launch_ms": k3_ms, "hbm_achieved_gbs": P * S * k3b / (k3_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                  "hbm_peak_source": "measured" if peaks else "fallback",
+                  "fp32_ffma_peak_tflops": ffma_peak, "frac_of_fp32_ffma_peak": k3_tflops / ffma_peak}
+        if tc:
+            tpeak = peaks.get("bf16_tflops_sustained", 1400.0)    # FP16 and BF16 UMMA run at the same rate
+            roofline = dict(common, kernel="k3_tc_kernel", bound="tensor", peak=tpeak, frac=k3_tflops / tpeak,
+                            peak_source=("measured" if peaks else "fallback") + " dense 16-bit tensor peak (sustained)",
+                            note="algorithmic FLOPs; the kernel executes 3 MMAs per product (FP16 operand pairs, FP32-level "
+                                 "accuracy) on 128xNx16 tiles with N <= 64, which are shared-memory-operand bound (113 B/clk "
+                                 "measured, profiles/tc_mma_bench.py), and its tanh epilogues are XU-pipe bound: see "
+                                 "profiles/README_r01.md")
+        else:
+            roofline = dict(common, kernel="k3_ppo_fast_kernel", bound="fp32-ffma", peak=ffma_peak, frac=k3_tflops / ffma_peak,
+                            peak_source=f"2*128 lanes*148 SMs*{sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json)",
+                            note="small populations are latency/occupancy bound: 6 chains of 320 dependent Adam steps")
         line = {
             "metric": metric, "value": env_steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -350,19 +369,11 @@ def main():
             "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pop.h2d_bytes, "d2h_bytes_per_step": pop.d2h_bytes},
             "gpu_launches": pop.GPU_LAUNCHES_PER_STEP * args.steps * 2,
-            "roofline": {
-                "kernel": "k3_ppo_kernel", "bound": "fp32-ffma", "achieved": k3_tflops, "peak": ffma_peak,
-                "unit": "TFLOP/s", "frac": k3_tflops / ffma_peak, "traffic": None,
-                "peak_source": f"2*128 lanes*148 SMs*{sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json)",
-                "algorithmic_flops_per_launch": P * S * upd, "launch_ms": k3_ms,
-                "hbm_achieved_gbs": P * S * k3b / (k3_ms * 1e-3) / 1e9,
-                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "measured" if peaks else "fallback",
-                "note": "small populations are latency/occupancy bound: 6 chains of 320 dependent Adam steps",
-            },
+            "roofline": roofline,
             "stages_ms": {"k1_forward": float(stages[0]), "k2_gae_adv": float(stages[1]), "k3_pack_ppo": k3_ms},
             "stage_hbm_gbs": {"k1_forward": P * (S + N) * k1b / (stages[0] * 1e-3) / 1e9,
                               "k2_gae_adv": P * S * k2b / (stages[1] * 1e-3) / 1e9},
-            "ppo_cluster": args.cluster, "finite": finite,
+            "ppo_cluster": args.cluster, "k3_path": "tensor-core" if tc else "fp32-ffma", "finite": finite,
         }
         if world == 1 and not args.no_selection:
             try:

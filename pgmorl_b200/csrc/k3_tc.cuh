@@ -30,7 +30,8 @@
 
 namespace pgm {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 256;              // 8 warps = lane quadrant (w & 3) x column half (w >> 2). 16 warps were measured
+                                             // no faster: the tanh epilogues are bound by the XU pipe (MUFU ex2/rcp + fp16 packs)
 constexpr uint32_t TC_GROUP_BYTES = 81920;   // H1a | H1b | H2a | H2b | X   (16 KB each, [128 rows][64 halfwords])
 constexpr uint32_t TC_MISC_BYTES = 1280;
 constexpr int TC_NHP = 6144;                 // padded size of one half's parameter vector (floats)
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const int nH = ols + (actor ? A : 0);
     const int n4 = (nH + 3) >> 2;
 
-    unsigned char *sg = smem_raw + sl.grp[g];
+    unsigned char *sg = smem_raw + sl.grp[g & 1];
     unsigned char *S_h1 = sg, *S_h2 = sg + 32768, *S_x = sg + 65536;     // H1a|H1b, H2a|H2b, X
     __half *W2a = (__half *)(smem_raw + sl.W2a), *W2b = (__half *)(smem_raw + sl.W2b);
     __half *W1i = (__half *)(smem_raw + sl.W1);
