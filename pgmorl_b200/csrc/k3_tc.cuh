@@ -591,24 +591,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         }   // tile pairs
 
         // ================= step tail =================
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (pendB[i]) { tc::mbar_wait(mbars + 2 + i, phB[i]); phB[i] ^= 1; pendB[i] = false; }
-        TCT(32)
-        tc::tc_fence_before();
-        __syncthreads();
+        // Gradients: TMEM -> GR (shared memory, parameter order); every accumulator cell is handed back zeroed by the thread
+        // that read it. GR aliases tile 0's buffers, free once ITS last weight-gradient MMAs are done; the dW2 / dWh
+        // accumulators are complete by then (their commits were waited for in E5), so they are drained while tile 1's
+        // last GEMM (G1X) is still running.
+        if (pendB[0]) { tc::mbar_wait(mbars + 2, phB[0]); phB[0] ^= 1; pendB[0] = false; }
         tc::tc_fence_after();
-        TCT(33)
-        {   // gradients: TMEM -> GR (shared memory, parameter order), accumulator cells handed back zeroed
-            float gw[32], gx[16], gh[8], z[32];
+        TCT(32)
+        {
+            float gw[32], gh[8], z[32];
             tc::tmem_ld32(tq + TC_GW2 + 32 * hcol, gw);
-            tc::tmem_ld16(tq + TC_G1X + 16 * hcol, gx);
             if (hcol == 0) tc::tmem_ld8(tq + TC_GWH, gh);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) z[i] = 0.f;
             tc::tmem_st32(tq + TC_GW2 + 32 * hcol, z);
-            tc::tmem_st16(tq + TC_G1X + 16 * hcol, z);
             if (hcol == 0) tc::tmem_st8(tq + TC_GWH, z);
             if (lane < 16) {                               // dW2 rows: (dz2 2^12)^T (h1 2^8)
                 float *dst = GR + oW2 + (16 * q + lane) * H + 32 * hcol;
@@ -622,17 +619,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                     for (int aa = 0; aa < 8; ++aa)
                         if (aa < KH) GR[oWh + aa * H + k] = gh[aa] * (1.f / (TC_SD * TC_SH));
                 }
-            }
-            if (q < 2) {                                   // dW1 | db1 rows: (dz1 2^12)^T [x | 1]
-                const int j = 32 * q + lane;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = 16 * hcol + i;
-                    if (c < O) GR[j * O + c] = gx[i] * (1.f / TC_SD);
-                    else if (c == O) GR[ob1 + j] = gx[i] * (1.f / TC_SD);
-                }
-            } else if (hcol == O / 16) {                   // db2: (dz2 2^12)^T 1
-                GR[ob2 + 32 * (q - 2) + lane] = gx[O % 16] * (1.f / TC_SD);
             }
         }
         // head bias / logstd gradients: per-thread row sums -> warp -> CTA
@@ -651,6 +637,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             b1pow *= a.hy.beta1; b2pow *= a.hy.beta2;
             sh_d[0] = lr / (1.0 - b1pow);
             sh_d[1] = 1.0 / sqrt(1.0 - b2pow);
+        }
+        if (pendB[1]) { tc::mbar_wait(mbars + 3, phB[1]); phB[1] ^= 1; pendB[1] = false; }
+        tc::tc_fence_after();
+        TCT(33)
+        {
+            float gx[16], z[16];
+            tc::tmem_ld16(tq + TC_G1X + 16 * hcol, gx);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = 0.f;
+            tc::tmem_st16(tq + TC_G1X + 16 * hcol, z);
+            if (q < 2) {                                   // dW1 | db1 rows: (dz1 2^12)^T [x | 1]
+                const int j = 32 * q + lane;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = 16 * hcol + i;
+                    if (c < O) GR[j * O + c] = gx[i] * (1.f / TC_SD);
+                    else if (c == O) GR[ob1 + j] = gx[i] * (1.f / TC_SD);
+                }
+            } else if (hcol == O / 16) {                   // db2: (dz2 2^12)^T 1
+                GR[ob2 + 32 * (q - 2) + lane] = gx[O % 16] * (1.f / TC_SD);
+            }
         }
         __syncthreads();
         if (tid < 8) {

@@ -41,7 +41,7 @@ names = {1: "waitB+X", 2: "sync+issueG1", 3: "waitG1(0)", 4: "E1(0)", 5: "sync+i
          14: "sync+issueG3(1)", 15: "waitG3", 16: "E3", 17: "sync+issueG4,GWh", 18: "waitG4(0)", 19: "E4(0)",
          20: "sync+issueG5,GW2(0)", 21: "waitG4(1)", 22: "E4(1)", 23: "sync+issueG5,GW2(1)", 24: "waitG5(0)", 25: "E5a(0)",
          26: "waitGW2(0)", 27: "E5b+sync+issueG1X(0)", 28: "waitG5(1)", 29: "E5a(1)", 30: "waitGW2(1)",
-         31: "E5b+sync+issueG1X(1)", 32: "waitG1X", 33: "sync", 34: "readout", 35: "ssq+ldmv", 36: "clusterbar", 37: "adam",
+         31: "E5b+sync+issueG1X(1)", 32: "waitG1X(0)", 33: "drain dW2,dWh + waitG1X(1)", 34: "drain G1X + sums", 35: "ssq+ldmv", 36: "clusterbar", 37: "adam",
          38: "sync"}
 for cta in (0, 1):
     for g in (0, 1):
