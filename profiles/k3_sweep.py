@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""K3 time per MOPG iteration vs population size for the FFMA paths (cluster 0 = auto) and the tensor-core path (32).
+"""K3 time per MOPG iteration vs population size: best FP32 FFMA cluster configuration (the library's rule before the
+tensor-core path existed) against the tensor-core path (cluster 32).
     gpurun -- python profiles/k3_sweep.py [P ...]"""
 import os
 import sys
@@ -15,10 +16,20 @@ from pgmorl_b200.population_state import PopulationMOPG  # noqa: E402
 Ps = [int(x) for x in sys.argv[1:]] or [6, 8, 12, 18, 24, 37, 64, 74, 128, 148, 256]
 d = ENV_SHAPES["walker2d"]
 T, N, E, B = 2048, 4, 10, 32
+
+
+def ffma_cluster(P, sms=148):
+    """CTAs per task the FFMA planner picks (csrc/k3_ppo.cu k3_plan)"""
+    C, cmax = 2, (16 if P <= 7 else 8)
+    while C < cmax and P * C * 2 <= sms:
+        C *= 2
+    return C
+
+
 for P in Ps:
     traj, eps, perm, w, ov, flats = synthetic_inputs(d, P, T, N, E, 1)
     row = []
-    for cluster in (0, 32):
+    for cluster in (ffma_cluster(P), 32):
         pop = PopulationMOPG(d, P, T, N, cluster=cluster)
         for p in range(P):
             pop.load_task(p, flats[p], weights=w[p], obj_var=ov[p])
@@ -39,5 +50,5 @@ for P in Ps:
             ts.append(e0.elapsed_time(e1))
         row.append(min(ts))
         del pop
-    print(f"P={P:4d}  ffma(auto) {row[0]:8.3f} ms   tensor-core {row[1]:8.3f} ms   ratio {row[0] / row[1]:.2f}   "
+    print(f"P={P:4d}  ffma(cluster {ffma_cluster(P):2d}) {row[0]:8.3f} ms   tensor-core {row[1]:8.3f} ms   ratio {row[0] / row[1]:.2f}   "
           f"TC env-steps/s (K3 only) {P * T * N / row[1] * 1e3 / 1e6:.1f} M")
