@@ -97,6 +97,13 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// tanh(x) = 1 - 2 / (exp(2x) + 1); absolute error ~1e-7 (2 MUFU + 3 FP32 ops instead of ~25 for tanhf)
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = fast_ex2(x * 2.8853900817779268f);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
 #endif
 
 }  // namespace pgm

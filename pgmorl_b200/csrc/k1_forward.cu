@@ -124,8 +124,33 @@ __global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) k1_forward_kernel(con
 }
 
 }  // namespace pgm
+#include "k1_tc.cuh"
 
 using namespace pgm;
+
+// bulk forward over trajectories on the tensor-core kernel (shapes it is instantiated for, enough rows to amortise the
+// per-CTA weight-image setup); per-step inference (a few rows) stays on the FFMA kernel
+static bool k1_tc_wanted(int O, int A, int M, int rows_v) {
+    return ((O == 17 && A == 6 && M == 2) || (O == 11 && A == 3 && M == 3)) && rows_v >= 1024;
+}
+
+template <typename Kern>
+static int k1_tc_launch(Kern kern, K1Args &a, int P, int O, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    PGM_CUDA(cudaGetDevice(&dev));
+    PGM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = (a.rows_v + 127) / 128;
+    int nblk = (sms + 2 * P - 1) / (2 * P);                 // CTAs per (task, half): fill the SMs once
+    if (nblk > (ntiles + 1) / 2) nblk = (ntiles + 1) / 2;
+    if (nblk < 1) nblk = 1;
+    a.chunks_per_cta = ((ntiles + nblk - 1) / nblk + 1) / 2 * 2;   // whole pairs of tiles
+    nblk = (ntiles + a.chunks_per_cta - 1) / a.chunks_per_cta;
+    const size_t smem = k1t_smem_layout(O).total;
+    PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(nblk, 2, P), K1T_THREADS, smem, st>>>(a);
+    PGM_CUDA(cudaGetLastError());
+    return PGM_OK;
+}
 
 extern "C" int pgm_policy_forward_f32(const float *params, const float *obs, const float *eps, int eps_shared,
                                       float *action, float *value, float *logp, int mode, int P, int rows_v,
@@ -142,6 +167,10 @@ extern "C" int pgm_policy_forward_f32(const float *params, const float *obs, con
     a.params = params; a.obs = obs; a.eps = eps; a.action = action; a.value = value; a.logp = logp;
     a.eps_shared = eps_shared; a.mode = mode; a.P = P; a.rows_v = rows_v; a.rows_a = rows_a;
     a.L = NetLayout(O, A, M);
+    if (k1_tc_wanted(O, A, M, rows_v)) {
+        if (O == 17) return k1_tc_launch(k1_tc_kernel<17, 6, 2>, a, P, O, (cudaStream_t)stream);
+        return k1_tc_launch(k1_tc_kernel<11, 3, 3>, a, P, O, (cudaStream_t)stream);
+    }
     const bool split = k1_smem_bytes(a.L, 4, false) > 110 * 1024;       // keep two CTAs per SM for small networks
     const int TM = split ? 2 : 4, RC = 16 * TM;
     const size_t smem = k1_smem_bytes(a.L, TM, split);

@@ -15,12 +15,6 @@
 
 namespace pgm {
 
-__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-// tanh(x) = 1 - 2 / (exp(2x) + 1); absolute error ~1e-7 (2 MUFU + 3 FP32 ops instead of ~25 for tanhf)
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float e = fast_ex2(x * 2.8853900817779268f);
-    return 1.f - __fdividef(2.f, e + 1.f);
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {

@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 
 #include "tc.cuh"
+#include "tc_pair.cuh"
 
 namespace pgm {
 
@@ -35,7 +36,6 @@ constexpr int TC_THREADS = 256;              // 8 warps = lane quadrant (w & 3) 
 constexpr uint32_t TC_GROUP_BYTES = 81920;   // H1a | H1b | H2a | H2b | X   (16 KB each, [128 rows][64 halfwords])
 constexpr uint32_t TC_MISC_BYTES = 1280;
 constexpr int TC_NHP = 6144;                 // padded size of one half's parameter vector (floats)
-constexpr float TC_SH = 256.f, TC_SD = 4096.f, TC_SW = 256.f;   // scales of activations / backward signals / weights
 
 struct TcSmem {   // byte offsets inside dynamic shared memory
     uint32_t grp[2], W2a, W2b, W1, WhA1, WhA2, WhZ, PM, SC, misc, total;
@@ -57,48 +57,6 @@ constexpr int TCM_RED = 0, TCM_PART = 40, TCM_SSQ = 168;   // ssq: [2 step parit
 // TMEM columns: group g at g*192: D1 [0,64) = 1 - h1^2, D2 [64,128) = 1 - h2^2, ACC [128,192) accumulators;
 // weight-gradient accumulators shared by both groups
 constexpr uint32_t TC_D1 = 0, TC_D2 = 64, TC_ACC = 128, TC_GSTRIDE = 192, TC_GW2 = 384, TC_G1X = 448, TC_GWH = 480;
-
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-// loads that must be ISSUED where they are written (prefetches): volatile asm keeps the compiler from sinking them
-__device__ __forceinline__ float4 ld_nc_f4(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float4 ld_cg_f4(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ld_nc_s32(const int32_t *p) {
-    int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {   // two floats -> fp16x2 (a in the low half), saturating
-    uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
-}
-// a1 = v rounded to 11 significant bits (round half away: integer add + mask, no conversion-pipe instruction);
-// exactly representable in fp16 whenever v is in fp16's normal range
-__device__ __forceinline__ float round11(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
-// store 8 consecutive features (logical 16-byte chunks ca / cb of the a1 / a2 destination rows; swz8 = row & 7 is the
-// SWIZZLE_128B XOR) as an fp16 pair
-__device__ __forceinline__ void store_pair8(unsigned char *rowa, uint32_t ca, unsigned char *rowb, uint32_t cb, uint32_t swz8, const float *v) {
-    float h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = round11(v[i]);
-    uint4 p1, p2;
-    p1.x = pack_h2(h[0], h[1]); p1.y = pack_h2(h[2], h[3]); p1.z = pack_h2(h[4], h[5]); p1.w = pack_h2(h[6], h[7]);
-    p2.x = pack_h2(v[0] - h[0], v[1] - h[1]); p2.y = pack_h2(v[2] - h[2], v[3] - h[3]);
-    p2.z = pack_h2(v[4] - h[4], v[5] - h[5]); p2.w = pack_h2(v[6] - h[6], v[7] - h[7]);
-    *reinterpret_cast<uint4 *>(rowa + ((ca ^ swz8) << 4)) = p1;
-    *reinterpret_cast<uint4 *>(rowb + ((cb ^ swz8) << 4)) = p2;
-}
-// halfword index of (row, feature) inside a [rows][64 halfwords] SWIZZLE_128B image
-__device__ __forceinline__ int sw128_hw(int row, int f) { return row * 64 + ((((f >> 3) ^ (row & 7))) << 3) + (f & 7); }
-__device__ __forceinline__ void put_pair(__half *ia, int hwa, __half *ib, int hwb, float v) {
-    const float h = round11(v);
-    ia[hwa] = __float2half_rn(h); ib[hwb] = __float2half_rn(v - h);
-}
 
 // PGM_K3_TRACE builds: clock64 marks of threads r == 0 (MMA issuer) and r == 64 of each group, steps 8 and 9
 // (profiles/k3_tc_trace.py): trace[(((cta*2 + group)*2 + who)*2 + step - 8)*48 + mark]
