@@ -101,9 +101,9 @@ int pgm_gae_adv_f32(const float *rewards, const float *value, const float *masks
  *   perm [P or 1, E, S] int32 : minibatch b of epoch e = perm[e, b*mb:(b+1)*mb], mb = S / B
  *   losses [P,3] out: mean over E*B updates of (value_loss, action_loss, entropy)
  *   workspace: >= pgm_ppo_workspace_bytes(...) bytes, 256-byte aligned
- *   cluster: 1,2,4,8,16 = CTAs per task of the FP32 FFMA kernels; 32 = the tensor-core kernel (tcgen05 UMMA on FP16
- *            operand pairs, FP32 accumulate, FP32-level accuracy; 2 CTAs per task; built for the (O,A,M) shapes
- *            (17,6,2) and (11,3,3)); 0 = choose from P, the shape and the SM count (tensor cores from 8 tasks on)
+ *   cluster: 1,2,4,8,16 = CTAs per task of the FP32 FFMA kernels; 32 / 64 = the tensor-core kernel (tcgen05 UMMA on FP16
+ *            operand pairs, FP32 accumulate, FP32-level accuracy) with 2 / 4 CTAs per task, built for the (O,A,M)
+ *            shapes (17,6,2) and (11,3,3); 0 = choose from P, the shape and the SM count (tensor cores from 8 tasks on)
  */
 typedef struct {
     double clip_param;      /* 0.2  a2c/algo/ppo.py:83-84  */

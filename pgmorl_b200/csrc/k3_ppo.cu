@@ -41,6 +41,7 @@ struct K3Args {
     int Rg;                 // rows per CTA per step (multiple of the chunk size)
     int RSG, RSS, NHP;      // record stride in global / shared memory; padded half size
     int stage_floats;       // fast path: staging floats for row-split partials
+    int rs;                 // tensor-core path: CTAs per network half (row split), 1 or 2
     pgm_ppo_hyper hy;
     NetLayout L;
 };
@@ -548,6 +549,7 @@ namespace pgm {
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
     bool DB, fast, tc;
+    int rs;
     int stage_floats;
     size_t smem;
     size_t off_rec, off_gpart, off_ssq, off_lpart, off_trace, off_mv, total;
@@ -566,18 +568,25 @@ static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS)
 
 // shapes the tensor-core kernel is instantiated for (Walker2d / HalfCheetah and Hopper-v3)
 static bool k3_tc_dims(int O, int A, int M) { return (O == 17 && A == 6 && M == 2) || (O == 11 && A == 3 && M == 3); }
-static size_t k3_tc_mv_bytes(int P) { return (size_t)P * 2 * 2 * TC_NHP * sizeof(float); }
-constexpr int K3_CLUSTER_TC = 32;   // `cluster` value that selects the tensor-core path explicitly
+static size_t k3_tc_mv_bytes(int P) { return (size_t)P * 2 * 2 * 2 * TC_NHP * sizeof(float); }   // [P][half][rs <= 2][m|v]
+constexpr int K3_CLUSTER_TC = 32;   // `cluster` values that select the tensor-core path explicitly: 32 = 2 CTAs per task,
+constexpr int K3_CLUSTER_TC2 = 64;  // 64 = 4 CTAs per task (row tiles split over two CTAs per network half)
 
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
     pl.tc = false; pl.off_mv = 0;
-    // auto: the tensor-core path (2 CTAs per task) wins as soon as the FFMA path can no longer give every task a 16-CTA
-    // cluster (measured on a B200, profiles/k3_sweep.py: parity at P = 8..12, 2x at 18, 3.1x from 37 tasks on)
-    if (cluster == 0 && k3_tc_dims(O, A, M) && P >= 8) cluster = K3_CLUSTER_TC;
-    if (cluster == K3_CLUSTER_TC) {
+    // auto: the tensor-core path wins as soon as the FFMA path can no longer give every task a 16-CTA cluster (measured on
+    // a B200, profiles/k3_sweep.py: 1.2x at P = 8, 2.4x at 16, 3.3x from 37 tasks on; below 8 tasks FFMA is 6 % faster)
+    if (cluster == 0 && k3_tc_dims(O, A, M) && P >= 8) {
+        // 4 CTAs per task (row tiles split over two CTAs per half) while they fit in one wave: 4-CTA clusters tile the 148
+        // SMs less densely than pairs (measured: 32 clusters run in one wave, 37 need two)
+        cluster = (mb > 128 && 4 * P <= sms - 20) ? K3_CLUSTER_TC2 : K3_CLUSTER_TC;
+    }
+    pl.rs = 1;
+    if (cluster == K3_CLUSTER_TC || cluster == K3_CLUSTER_TC2) {
+        pl.rs = cluster == K3_CLUSTER_TC2 ? 2 : 1;
         PGM_REQUIRE(k3_tc_dims(O, A, M), "ppo: the tensor-core path is built for (O,A,M) = (17,6,2) and (11,3,3), got (%d,%d,%d)", O, A, M);
-        pl.tc = true; pl.C = 2; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
+        pl.tc = true; pl.C = 2 * pl.rs; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
         pl.RSG = rec_stride(L); pl.RSS = 0; pl.NHP = 64; pl.DB = false; pl.fast = false; pl.stage_floats = 0;
         pl.smem = tc_smem_layout().total;
         size_t off = 0;
@@ -598,7 +607,7 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     PGM_REQUIRE(O >= 1 && O <= 384 && A >= 1 && A <= 32 && M >= 1 && M <= 16,
                 "ppo: unsupported dims O=%d A=%d M=%d (O<=384, A<=32, M<=16)", O, A, M);
     PGM_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16,
-                "ppo: cluster must be 0 (auto), 1, 2, 4, 8, 16 (FP32 FFMA paths) or 32 (tensor-core path) (got %d)", cluster);
+                "ppo: cluster must be 0 (auto), 1, 2, 4, 8, 16 (FP32 FFMA paths), 32 or 64 (tensor-core path) (got %d)", cluster);
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
         C = 2;      // one CTA per network half is the throughput configuration (large populations)
@@ -678,8 +687,8 @@ static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
 
 static int k3_launch(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
     if (pl.tc) {
-        if (a.L.O == 17) return k3_launch_k(k3_tc_kernel<17, 6, 2>, 2, a, pl, P, st);
-        return k3_launch_k(k3_tc_kernel<11, 3, 3>, 2, a, pl, P, st);
+        if (a.L.O == 17) return k3_launch_k(k3_tc_kernel<17, 6, 2>, pl.C, a, pl, P, st);
+        return k3_launch_k(k3_tc_kernel<11, 3, 3>, pl.C, a, pl, P, st);
     }
     switch (pl.C) {
         case 1: return k3_launch_c<1>(a, pl, P, st);
@@ -753,7 +762,7 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
     a.mv = (float *)(ws + pl.off_mv);
     a.grad_out = grad_out; a.perm_shared = perm_shared; a.E = E; a.B = B; a.mb = mb; a.S = S;
     a.grad_only = grad_out != nullptr; a.nsteps = a.grad_only ? 1 : E * B;
-    a.Rg = pl.Rg; a.RSG = pl.RSG; a.RSS = pl.RSS; a.NHP = pl.NHP; a.stage_floats = pl.stage_floats; a.hy = *hy; a.L = NetLayout(O, A, M);
+    a.Rg = pl.Rg; a.RSG = pl.RSG; a.RSS = pl.RSS; a.NHP = pl.NHP; a.stage_floats = pl.stage_floats; a.rs = pl.rs; a.hy = *hy; a.L = NetLayout(O, A, M);
     {
         const size_t total = (size_t)P * S * pl.RSG;
         int blocks = (int)((total + 255) / 256);

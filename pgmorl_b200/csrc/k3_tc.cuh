@@ -1,7 +1,9 @@
 // K3 tensor-core path: the PPO minibatch loop (a2c/algo/ppo.py:62-107) on tcgen05 (UMMA kind::f16, FP32 accumulate
 // in TMEM). Included by k3_ppo.cu (shares K3Args, k3_pack_kernel, fast_tanh, the DSMEM helpers).
 //
-// One cluster of two CTAs per task: rank 0 = actor, rank 1 = critic (they share only the global gradient norm).
+// One cluster of 2 * RS CTAs per task: ranks [0, RS) = actor, [RS, 2 RS) = critic (the halves share only the global
+// gradient norm); with RS = 2 the row tiles of every minibatch alternate between the two CTAs of a half (small
+// populations: twice the SMs per task), which then add their gradients through DSMEM and run Adam redundantly.
 // A CTA keeps its half's weights resident in shared memory as UMMA B operands and runs TWO independent 128-thread
 // pipelines ("groups"); group g owns the 128-row tiles t = g, g+2, ... of every minibatch, thread = row = TMEM lane.
 // While one group waits for its MMAs the other runs its epilogue, which hides the issue->complete latency of the
@@ -81,10 +83,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const int warp = tc::uniform_warp_idx();         // warp-uniform by construction: MMA operands stay in uniform registers
     const int g = warp >> 2, r = tid & 127;          // group, row inside the tile (= TMEM lane)
     const int q = warp & 3, hcol = warp >> 2;        // lane quadrant, column half used in the step tail
-    const int task = blockIdx.x >> 1;
+    const int RS = a.rs;                             // CTAs per network half (row split): 1 or 2
+    const int task = blockIdx.x / (2 * RS);
     const unsigned rank = group_rank<2>();
-    const bool actor = rank == 0;
-    const int half = (int)rank;
+    const int half = (int)rank / RS, rs = (int)rank % RS;
+    const bool actor = half == 0;
     const int KH = actor ? A : M;
     const NetLayout &L = a.L;
     const TcSmem sl = tc_smem_layout();
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         put_param(e, p);
     }
     // Adam moments: reference order -> half-local order in the workspace
-    float *wM = a.mv + ((size_t)(task * 2 + half) * 2) * TC_NHP, *wV = wM + TC_NHP;
+    float *wM = a.mv + ((size_t)((task * 2 + half) * RS + rs) * 2) * TC_NHP, *wV = wM + TC_NHP;   // one copy per CTA
     if (!a.grad_only)
         for (int e = tid; e < 4 * n4; e += TC_THREADS) {
             const bool in = e < nH;
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
 
     const int32_t *perm = a.perm + ((a.perm_shared || a.grad_only) ? 0 : (size_t)task * a.E * a.S);
     const float *recg = a.rec + (size_t)task * a.S * RSG;
-    const int ntiles = (a.mb + 127) >> 7;
+    const int ntiles_all = (a.mb + 127) >> 7;
+    const int ntiles = rs < ntiles_all ? (ntiles_all - rs + RS - 1) / RS : 0;    // my tiles: global tile = local * RS + rs
     uint32_t phA[2] = {0u, 0u}, phB[2] = {0u, 0u};    // mbarrier phase parities (per tile of the pair)
     bool pendB[2] = {false, false};
 
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int k = 0; k < NIT; ++k) {
-                const int f = tid + TC_THREADS * k, rowi = (tt + i) * 128 + f / NP;
+                const int f = tid + TC_THREADS * k, rowi = ((tt + i) * RS + rs) * 128 + f / NP;
                 const bool ok = sv && tt + i < ntiles && f < 128 * NP && rowi < a.mb;
                 ridx[i][k] = ld_nc_s32(pb + (ok ? rowi : 0));
                 vm_idx |= (ok ? 1u : 0u) << (i * NIT + k);
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         float gbh[8], gls[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { gbh[i] = 0.f; gls[i] = 0.f; }
-        if (actor && tid == 0) {   // entropy with the parameters this step starts from
+        if (actor && rs == 0 && tid == 0) {   // entropy with the parameters this step starts from
             float ent = 0.f;
             for (int d = 0; d < A; ++d) ent += 0.5f + 0.91893853320467274178f + lss[d];
             loss_ent += ent;
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                     sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
                     sc[8] = s2.x; sc[9] = s2.y; sc[10] = s2.z; sc[11] = s2.w;
                 }
-                const bool row_valid = (tp + g) * 128 + r < a.mb;
+                const bool row_valid = ((tp + g) * RS + rs) * 128 + r < a.mb;
                 tc::tmem_ld_wait();
                 if (actor) {
                     float lp = 0.f, diffv[8], ivv[8];
@@ -624,14 +628,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
 #pragma unroll
             for (int w = 0; w < 8; ++w) { sb += part[w * 16 + tid]; sl_ += part[w * 16 + 8 + tid]; }
             if (tid < KH) GR[obh + tid] = sb;
-            if (actor && tid < A) GR[ols + tid] = sl_ - ecoef;          // d(-ecoef * entropy) / d logstd = -ecoef
+            if (actor && tid < A) GR[ols + tid] = sl_ - (rs == 0 ? ecoef : 0.f);   // d(-ecoef * entropy) / d logstd = -ecoef, once
         }
         if (tid < 4 && nH + tid < 4 * n4) GR[nH + tid] = 0.f;            // padding of the last float4
         __syncthreads();
         TCT(34)
 
+        // row split: the other CTA of my half holds the gradient of the other tiles in ITS GR (same offset)
+        uint32_t peerGR = 0;
+        if (RS > 1) {
+            sync_group<2>();                                   // both GRs complete
+            peerGR = mapa_u32(smem_u32(GR), (uint32_t)(half * RS + (rs ^ 1)));
+        }
         if (a.grad_only) {
-            for (int e = tid; e < nH; e += TC_THREADS) a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = GR[e];
+            if (rs == 0)
+                for (int e = tid; e < nH; e += TC_THREADS) {
+                    float gsum = GR[e];
+                    if (RS > 1) { float pv; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pv) : "r"(peerGR + 4u * (uint32_t)e) : "memory"); gsum += pv; }
+                    a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gsum;
+                }
+            if (RS > 1) sync_group<2>();                       // the peer's GR stays valid until it has been read
             break;
         }
 
@@ -644,6 +660,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             const int i4 = tid + u * TC_THREADS;
             if (i4 < n4) {
                 g4[u] = reinterpret_cast<const float4 *>(GR)[i4];
+                if (RS > 1) {                                  // fixed order (rs 0 + rs 1): both CTAs get identical sums
+                    const float4 pg = ld_dsmem4(peerGR + 16u * (uint32_t)i4);
+                    const float4 lo4 = rs == 0 ? g4[u] : pg, hi4 = rs == 0 ? pg : g4[u];
+                    g4[u] = make_float4(lo4.x + hi4.x, lo4.y + hi4.y, lo4.z + hi4.z, lo4.w + hi4.w);
+                }
                 m4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wM) + i4);
                 v4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wV) + i4);
                 sq = fmaf(g4[u].x, g4[u].x, sq); sq = fmaf(g4[u].y, g4[u].y, sq);
@@ -654,9 +675,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         // only synchronisation, every thread then adds the 16 partials in one fixed order
         sq = warp_sum(sq);
         float *ssq2 = ssqS + 16 * (s & 1);    // slots alternate by step parity: the peer may still be reading the last ones
-        if (lane == 0) {
-            ssq2[rank * 8 + warp] = sq;
-            st_dsmem1(mapa_u32(smem_u32(ssq2 + rank * 8 + warp), rank ^ 1u), sq);
+        if (lane == 0) {                      // my half's partials -> me and the CTA of the other half with my row-split index
+            ssq2[half * 8 + warp] = sq;
+            st_dsmem1(mapa_u32(smem_u32(ssq2 + half * 8 + warp), (uint32_t)((1 - half) * RS + rs)), sq);
         }
         TCT(35)
         sync_group<2>();
@@ -710,7 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     }   // steps
 
     // ---------------- write back ----------------
-    if (!a.grad_only) {
+    if (!a.grad_only && rs == 0) {
         for (int e = tid; e < nH; e += TC_THREADS) {
             const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
             a.params[gi] = PM[e];
@@ -719,19 +740,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     }
     {   // losses: the critic CTA reports the value loss, the actor CTA the action loss and the entropy
         const float la = block_sum(loss_act, red), lv = block_sum(loss_val, red), le = block_sum(loss_ent, red);
-        if (tid == 0) {
-            const float ns = (float)a.nsteps;
-            if (actor) {
-                a.losses[task * 3 + 1] = la * inv_mb / ns;
-                a.losses[task * 3 + 2] = le / ns;
-                if (!a.grad_only) a.adam_step[task] = step0 + a.nsteps;
-            } else {
-                a.losses[task * 3 + 0] = lv * 0.5f / ((float)a.mb * M) / ns;
-            }
+        if (tid == 0) {                   // per-CTA sums (each CTA saw its own rows) -> combined by the rs == 0 CTA of the half
+            a.lpart[(task * 16 + rank) * 4 + 0] = lv;
+            a.lpart[(task * 16 + rank) * 4 + 1] = la;
+            a.lpart[(task * 16 + rank) * 4 + 2] = le;
+            __threadfence();
         }
     }
     tc::tc_fence_before();
-    sync_group<2>();                 // no DSMEM traffic may target an exited CTA
+    sync_group<2>();                 // no DSMEM traffic may target an exited CTA; loss partials are published
+    if (tid == 0 && rs == 0) {
+        float lv = 0.f, la = 0.f, le = 0.f;
+        for (int k = 0; k < RS; ++k) {
+            lv += __ldcg(a.lpart + (task * 16 + half * RS + k) * 4 + 0);
+            la += __ldcg(a.lpart + (task * 16 + half * RS + k) * 4 + 1);
+            le += __ldcg(a.lpart + (task * 16 + half * RS + k) * 4 + 2);
+        }
+        const float ns = (float)a.nsteps;
+        if (actor) {
+            a.losses[task * 3 + 1] = la * inv_mb / ns;
+            a.losses[task * 3 + 2] = le / ns;
+            if (!a.grad_only) a.adam_step[task] = step0 + a.nsteps;
+        } else {
+            a.losses[task * 3 + 0] = lv * 0.5f / ((float)a.mb * M) / ns;
+        }
+    }
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 

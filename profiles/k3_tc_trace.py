@@ -31,7 +31,7 @@ for _ in range(3):
     pop.step()
 torch.cuda.synchronize()
 r256 = lambda b: (b + 255) // 256 * 256
-off_tr = r256(P * S * 32 * 4) + r256(P * 2 * 64 * 4) + r256(P * 16 * 4) + r256(P * 64 * 4) + r256(P * 2 * 2 * 6144 * 4)
+off_tr = r256(P * S * 32 * 4) + r256(P * 2 * 64 * 4) + r256(P * 16 * 4) + r256(P * 64 * 4) + r256(P * 2 * 2 * 2 * 6144 * 4)
 off = (-pop.workspace.data_ptr()) % 256
 n = P * 2 * 2 * 2 * 2 * 48
 raw = pop.workspace[off + off_tr: off + off_tr + n * 8].cpu().numpy().view(np.int64)
