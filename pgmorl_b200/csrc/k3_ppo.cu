@@ -687,8 +687,10 @@ static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
 
 static int k3_launch(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
     if (pl.tc) {
-        if (a.L.O == 17) return k3_launch_k(k3_tc_kernel<17, 6, 2>, pl.C, a, pl, P, st);
-        return k3_launch_k(k3_tc_kernel<11, 3, 3>, pl.C, a, pl, P, st);
+        if (a.L.O == 17) return pl.rs == 2 ? k3_launch_k(k3_tc_kernel<17, 6, 2, 2>, pl.C, a, pl, P, st)
+                                           : k3_launch_k(k3_tc_kernel<17, 6, 2, 1>, pl.C, a, pl, P, st);
+        return pl.rs == 2 ? k3_launch_k(k3_tc_kernel<11, 3, 3, 2>, pl.C, a, pl, P, st)
+                          : k3_launch_k(k3_tc_kernel<11, 3, 3, 1>, pl.C, a, pl, P, st);
     }
     switch (pl.C) {
         case 1: return k3_launch_c<1>(a, pl, P, st);

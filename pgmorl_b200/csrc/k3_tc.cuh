@@ -68,7 +68,7 @@ constexpr uint32_t TC_D1 = 0, TC_D2 = 64, TC_ACC = 128, TC_GSTRIDE = 192, TC_GW2
 #define TCT(i)
 #endif
 
-template <int O, int A, int M>
+template <int O, int A, int M, int RS>      // RS = CTAs per network half (row split): 1 or 2
 __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     constexpr int OP = (O + 3) / 4 * 4;
     constexpr int NK1 = (O + 1 + 15) / 16;           // K steps of layer 1: x, ones column at index O, zero padding
@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     const int warp = tc::uniform_warp_idx();         // warp-uniform by construction: MMA operands stay in uniform registers
     const int g = warp >> 2, r = tid & 127;          // group, row inside the tile (= TMEM lane)
     const int q = warp & 3, hcol = warp >> 2;        // lane quadrant, column half used in the step tail
-    const int RS = a.rs;                             // CTAs per network half (row split): 1 or 2
     const int task = blockIdx.x / (2 * RS);
     const unsigned rank = group_rank<2>();
     const int half = (int)rank / RS, rs = (int)rank % RS;
@@ -104,7 +103,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     __half *WhA1 = (__half *)(smem_raw + sl.WhA1), *WhA2 = (__half *)(smem_raw + sl.WhA2);
     float *PM = (float *)(smem_raw + sl.PM);
     float *SC = (float *)(smem_raw + sl.SC);                            // [2 tiles][128 rows][12]
-    float *GR = (float *)(smem_raw + sl.grp[0]);                         // gradient staging (step tail only)
+    float *GR = (float *)(smem_raw + sl.grp[0]);                         // gradient staging (step tail only), parameter order
+    float *GRW2 = GR + TC_NHP;                                           // ... except dW2: rows padded to 68 floats, so that the
+    constexpr int GW2LD = 68;                                            // 16 row-owner lanes of a warp store conflict free
     float *misc = (float *)(smem_raw + sl.misc);
     float *red = misc + TCM_RED, *part = misc + TCM_PART, *ssqS = misc + TCM_SSQ;
     double *sh_d = (double *)(smem_raw + sl.misc + 1024);
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
             tc::tmem_st32(tq + TC_GW2 + 32 * hcol, z);
             if (hcol == 0) tc::tmem_st8(tq + TC_GWH, z);
             if (lane < 16) {                               // dW2 rows: (dz2 2^12)^T (h1 2^8)
-                float *dst = GR + oW2 + (16 * q + lane) * H + 32 * hcol;
+                float *dst = GRW2 + (16 * q + lane) * GW2LD + 32 * hcol;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                     *reinterpret_cast<float4 *>(dst + i) = make_float4(gw[i] * (1.f / (TC_SD * TC_SH)), gw[i + 1] * (1.f / (TC_SD * TC_SH)),
@@ -643,8 +644,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         if (a.grad_only) {
             if (rs == 0)
                 for (int e = tid; e < nH; e += TC_THREADS) {
-                    float gsum = GR[e];
-                    if (RS > 1) { float pv; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pv) : "r"(peerGR + 4u * (uint32_t)e) : "memory"); gsum += pv; }
+                    const int ge = (e >= oW2 && e < ob2) ? TC_NHP + ((e - oW2) >> 6) * GW2LD + ((e - oW2) & 63) : e;   // staging slot
+                    float gsum = GR[ge];
+                    if (RS > 1) { float pv; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pv) : "r"(peerGR + 4u * (uint32_t)ge) : "memory"); gsum += pv; }
                     a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gsum;
                 }
             if (RS > 1) sync_group<2>();                       // the peer's GR stays valid until it has been read
@@ -655,20 +657,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         constexpr int NS = (TC_NHP / 4 + TC_THREADS - 1) / TC_THREADS;      // 6
         float4 g4[NS], m4[NS], v4[NS];
         float sq = 0.f;
+        {
+            float4 pg[NS];
 #pragma unroll
-        for (int u = 0; u < NS; ++u) {
-            const int i4 = tid + u * TC_THREADS;
-            if (i4 < n4) {
-                g4[u] = reinterpret_cast<const float4 *>(GR)[i4];
-                if (RS > 1) {                                  // fixed order (rs 0 + rs 1): both CTAs get identical sums
-                    const float4 pg = ld_dsmem4(peerGR + 16u * (uint32_t)i4);
-                    const float4 lo4 = rs == 0 ? g4[u] : pg, hi4 = rs == 0 ? pg : g4[u];
-                    g4[u] = make_float4(lo4.x + hi4.x, lo4.y + hi4.y, lo4.z + hi4.z, lo4.w + hi4.w);
+            for (int u = 0; u < NS; ++u) {                     // all loads first (shared memory, peer DSMEM, L2), then the sums
+                const int i4 = tid + u * TC_THREADS;
+                if (i4 < n4) {
+                    const int e0 = 4 * i4;
+                    const int gi4 = (e0 >= oW2 && e0 < ob2) ? (TC_NHP + ((e0 - oW2) >> 6) * GW2LD + ((e0 - oW2) & 63)) >> 2 : i4;   // staging slot
+                    g4[u] = reinterpret_cast<const float4 *>(GR)[gi4];
+                    if (RS > 1) pg[u] = ld_dsmem4(peerGR + 16u * (uint32_t)gi4);
+                    m4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wM) + i4);
+                    v4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wV) + i4);
                 }
-                m4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wM) + i4);
-                v4[u] = ld_cg_f4(reinterpret_cast<const float4 *>(wV) + i4);
-                sq = fmaf(g4[u].x, g4[u].x, sq); sq = fmaf(g4[u].y, g4[u].y, sq);
-                sq = fmaf(g4[u].z, g4[u].z, sq); sq = fmaf(g4[u].w, g4[u].w, sq);
+            }
+#pragma unroll
+            for (int u = 0; u < NS; ++u) {
+                const int i4 = tid + u * TC_THREADS;
+                if (i4 < n4) {
+                    if (RS > 1) {                              // fixed order (rs 0 + rs 1): both CTAs get identical sums
+                        const float4 lo4 = rs == 0 ? g4[u] : pg[u], hi4 = rs == 0 ? pg[u] : g4[u];
+                        g4[u] = make_float4(lo4.x + hi4.x, lo4.y + hi4.y, lo4.z + hi4.z, lo4.w + hi4.w);
+                    }
+                    sq = fmaf(g4[u].x, g4[u].x, sq); sq = fmaf(g4[u].y, g4[u].y, sq);
+                    sq = fmaf(g4[u].z, g4[u].z, sq); sq = fmaf(g4[u].w, g4[u].w, sq);
+                }
             }
         }
         // squared norm: per-warp partials go to my own slots and straight to the peer CTA; the cluster barrier is the

@@ -18,10 +18,11 @@ from pgmorl_b200.layout import ENV_SHAPES  # noqa: E402
 from pgmorl_b200.population_state import PopulationMOPG  # noqa: E402
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+CL = int(sys.argv[2]) if len(sys.argv) > 2 else 32      # 32: 2 CTAs per task, 64: 4 CTAs per task
 d = ENV_SHAPES["halfcheetah"]
 T, N, E, B = 2048, 4, 10, 32
 S = T * N
-pop = PopulationMOPG(d, P, T, N, cluster=32)
+pop = PopulationMOPG(d, P, T, N, cluster=CL)
 traj, eps, perm, w, ov, flats = synthetic_inputs(d, P, T, N, E, 1)
 for p in range(P):
     pop.load_task(p, flats[p], weights=w[p], obj_var=ov[p])
@@ -33,9 +34,10 @@ torch.cuda.synchronize()
 r256 = lambda b: (b + 255) // 256 * 256
 off_tr = r256(P * S * 32 * 4) + r256(P * 2 * 64 * 4) + r256(P * 16 * 4) + r256(P * 64 * 4) + r256(P * 2 * 2 * 2 * 6144 * 4)
 off = (-pop.workspace.data_ptr()) % 256
-n = P * 2 * 2 * 2 * 2 * 48
+NC = CL // 16          # CTAs per task
+n = P * NC * 2 * 2 * 2 * 48
 raw = pop.workspace[off + off_tr: off + off_tr + n * 8].cpu().numpy().view(np.int64)
-tr = raw.reshape(P * 2, 2, 2, 2, 48)      # cta, group, who, step, mark
+tr = raw.reshape(P * NC, 2, 2, 2, 48)      # cta, group, who, step, mark
 names = {1: "waitB+X", 2: "sync+issueG1", 3: "waitG1(0)", 4: "E1(0)", 5: "sync+issueG2(0)", 6: "waitG1(1)", 7: "E1(1)",
          8: "sync+issueG2(1)", 9: "waitG2(0)", 10: "E2(0)", 11: "sync+issueG3(0)", 12: "waitG2(1)", 13: "E2(1)",
          14: "sync+issueG3(1)", 15: "waitG3", 16: "E3", 17: "sync+issueG4,GWh", 18: "waitG4(0)", 19: "E4(0)",
@@ -43,12 +45,12 @@ names = {1: "waitB+X", 2: "sync+issueG1", 3: "waitG1(0)", 4: "E1(0)", 5: "sync+i
          26: "waitGW2(0)", 27: "E5b+sync+issueG1X(0)", 28: "waitG5(1)", 29: "E5a(1)", 30: "waitGW2(1)",
          31: "E5b+sync+issueG1X(1)", 32: "waitG1X(0)", 33: "drain dW2,dWh + waitG1X(1)", 34: "drain G1X + sums", 35: "ssq+ldmv", 36: "clusterbar", 37: "adam",
          38: "sync"}
-for cta in (0, 1):
+for cta in range(NC):
     for g in (0, 1):
         for who in (0, 1):
             c = tr[cta, g, who, 1, :39].astype(np.int64)
             dur = np.diff(c)
-            print(f"cta {cta} ({'actor' if cta == 0 else 'critic'}) group {g} thread r={'0 (issuer)' if who == 0 else '64'}:"
+            print(f"cta {cta} ({'actor' if cta < NC // 2 else 'critic'}) group {g} thread r={'0 (issuer)' if who == 0 else '64'}:"
                   f" step = {int(tr[cta, g, who, 1, 38] - tr[cta, g, who, 0, 38])} cycles")
             print("   ", " ".join(f"{names[i + 1]}={int(x)}" for i, x in enumerate(dur)))
             x = tr[cta, g, who, 1]
