@@ -268,12 +268,17 @@ def main():
     def run(steps, e2e):
         """-> (device ms per step, list of per-stage ms or None)"""
         marks = []
+        if e2e:
+            pop.upload_staged_async()                  # inputs of the first iteration
         for i in range(steps):
             flush.fill_(i & 0xFF)                      # evict L2 between timed iterations (not timed)
             s, e = ev(), ev()
             if e2e:
+                # every timed iteration: wait for ITS inputs' H2D copy, start the next iteration's copy on the copy stream
+                # (it runs under this iteration's kernels), compute, read the losses back to the host
                 s.record()
-                pop.upload_staged()
+                pop.swap_inputs()
+                pop.upload_staged_async()
                 pop.step()
                 pop._h_losses.copy_(pop.losses, non_blocking=True)
                 exchange(i)
@@ -345,7 +350,13 @@ def main():
         # which K3 kernel ran: the tensor-core path (tcgen05 on FP16 operand pairs) is chosen explicitly (cluster 32) or by
         # the library from 8 tasks on for the shapes it is built for; otherwise the FP32 FFMA cluster kernels
         tc = args.cluster == 32 or (args.cluster == 0 and P >= 8 and (d.obs, d.act, d.obj) in ((17, 6, 2), (11, 3, 3)))
-        common = {"unit": "TFLOP/s", "achieved": k3_tflops, "traffic": None, "algorithmic_flops_per_launch": P * S * upd,
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures (profiles/): only the
+        # two configurations that were captured, null otherwise
+        traffic = {("c2", False): 7.5e6, ("walker64", True): 81.4e6}.get((args.config, tc))
+        common = {"unit": "TFLOP/s", "achieved": k3_tflops, "traffic": traffic,
+                  "traffic_source": ("profiles/README_r01.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+                                     if traffic else None),
+                  "algorithmic_bytes_per_launch": P * S * k3b / E, "algorithmic_flops_per_launch": P * S * upd,
                   "launch_ms": k3_ms, "hbm_achieved_gbs": P * S * k3b / (k3_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                   "hbm_peak_source": "measured" if peaks else "fallback",
                   "fp32_ffma_peak_tflops": ffma_peak, "frac_of_fp32_ffma_peak": k3_tflops / ffma_peak}

@@ -150,6 +150,27 @@ class PopulationMOPG:
         for k, h in self._h.items():
             getattr(self, k).copy_(h, non_blocking=True)
 
+    # ---- pipelined uploads: the next iteration's inputs travel host -> HBM on a copy stream while this one computes ----
+    def upload_staged_async(self):
+        """H2D of the pinned staging buffers into the ALTERNATE set of input buffers, on a separate stream.
+        The caller must have finished (synchronised) the iteration that last read the alternate set."""
+        if not hasattr(self, "_alt"):
+            self._alt = {k: torch.empty_like(getattr(self, k)) for k in self._h}
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copy_done = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            for k, h in self._h.items():
+                self._alt[k].copy_(h, non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+
+    def swap_inputs(self):
+        """Make the set filled by the last upload_staged_async() current (the compute stream waits for that copy)."""
+        torch.cuda.current_stream().wait_event(self._copy_done)
+        for k in self._h:
+            cur = getattr(self, k)
+            setattr(self, k, self._alt[k])
+            self._alt[k] = cur
+
     def step_from_host(self, obs, rewards, masks, bad_masks, eps, perm):
         """End-to-end call: host buffers in, host losses out (H2D + K1..K3 + D2H)."""
         self.upload(obs, rewards, masks, bad_masks, eps, perm)

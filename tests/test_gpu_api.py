@@ -122,3 +122,34 @@ def test_sample_task_lifecycle_and_state_dict_roundtrip():
     v2, logp2, ent, _ = s.actor_critic.evaluate_actions(x, None, None, action)
     assert torch.allclose(value, v2) and torch.allclose(logp, logp2, atol=1e-5) and value.shape == (4, d.obj)
     assert torch.allclose(s.actor_critic.get_value(x, None, None), value)
+
+
+def test_pipelined_uploads_match_blocking_path():
+    """upload_staged_async + swap_inputs (next iteration's H2D under this one's kernels) gives the same iteration as upload()."""
+    from pgmorl_b200 import synthetic
+    from pgmorl_b200.layout import NetDims
+    from pgmorl_b200.population_state import PopulationMOPG
+    d = NetDims(17, 6, 2)
+    P, T, N, E, B = 2, 64, 4, 2, 4
+    outs = []
+    for pipelined in (False, True):
+        pop = PopulationMOPG(d, P, T, N, ppo_epoch=E, num_mini_batch=B)
+        for p in range(P):
+            pop.load_task(p, synthetic.init_policy_flat(d, seed=7 + p).numpy(), weights=[0.4, 0.6], obj_var=[1.0, 2.0])
+        pop.set_lr(3e-4)
+        for j in range(3):
+            traj = synthetic.make_trajectories(P, T, N, d, seed=100 + j)
+            eps, perm = synthetic.host_rng_streams(j, T, N, d.act, E)
+            src = dict(obs=traj["obs"], rewards=traj["rewards"], masks=traj["masks"], bad_masks=traj["bad_masks"],
+                       eps=eps.to(torch.float32), perm=perm.to(torch.int32))
+            if pipelined:
+                for k, t in src.items():
+                    pop._h[k].copy_(torch.as_tensor(t).reshape(pop._h[k].shape))
+                pop.upload_staged_async()
+                pop.swap_inputs()
+            else:
+                pop.upload(**src)
+            pop.step()
+            torch.cuda.synchronize()
+        outs.append(pop.params.clone())
+    assert torch.equal(outs[0], outs[1])

@@ -256,3 +256,26 @@ def test_population_iterations_match_reference_goldens(name):
             assert rel_err(flat, z[pre + "params"]) < 1e-4
             assert rel_err(m, z[pre + "adam_m"]) < 1e-3 and rel_err(v, z[pre + "adam_v"]) < 1e-3
             assert rel_err(losses[p], z[pre + "losses"]) < 1e-3
+
+
+@pytest.mark.parametrize("cluster", [8, 32, 64])
+def test_k3_per_task_permutations_equal_shared(cluster):
+    """perm given per task ([P,E,S]) with identical rows must reproduce the shared-permutation ([1,E,S]) result bit for bit
+    (the reference seeds every worker alike, mopg.py:96, but the C ABI accepts per-task streams)."""
+    from pgmorl_b200 import kernels as K
+    d = DIMS["walker"]
+    P, T, N, B = 3, 96, 4, 2                       # mb = 192: two row tiles on the tensor-core path, the second one ragged
+    cur, pk, perm = _ppo_inputs(d, P, T, N, seed=17)
+    res = []
+    for shared in (True, False):
+        gp, gm, gv = dev(cur), torch.zeros(P, d.n_par, device="cuda"), torch.zeros(P, d.n_par, device="cuda")
+        gstep = torch.zeros(P, dtype=torch.int32, device="cuda")
+        pm = dev(perm[None], torch.int32)
+        if not shared:
+            pm = pm.expand(P, -1, -1).contiguous()
+        K.ppo_update(gp, gm, gv, gstep, dev(np.full(P, 3e-4), torch.float64), dev(pk["obs"]), dev(pk["action"]),
+                     dev(pk["logp"]), dev(pk["value"]), dev(pk["returns"]), dev(pk["adv"]), pm, B, d, cluster=cluster)
+        torch.cuda.synchronize()
+        res.append((gp.clone(), gm.clone(), gv.clone()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
