@@ -124,9 +124,11 @@ class Population:
         """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_3d.py:239-333)."""
         N = args.num_tasks
         samples, tests = [], []
+        # the reference rebuilds this simplex grid for every sample (population_3d.py:262-263); it is a pure function of the
+        # arguments (no RNG), so it is enumerated once
+        grid = []
+        generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
         for sample in self.sample_batch:
-            grid = []
-            generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
             tw = self._test_weights(args, opt_graph, sample, grid)
             if len(tw) > 0:
                 samples.append(sample); tests.append(tw)
