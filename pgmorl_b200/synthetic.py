@@ -229,11 +229,53 @@ class ReplayVecEnv:
         pass
 
 
+class SeededReplayVecEnv:
+    """Replay environment for whole runs (driver-loop tests): the trajectory of MOPG iteration j is
+    make_trajectories(seed = base_seed + j), where j is read from torch's global seed -- both the reference's worker
+    (mopg.py:96) and the batched update call torch.manual_seed(j) before stepping iteration j. reset() returns a fixed
+    observation because it is called before the first manual_seed."""
+
+    def __init__(self, dims, T, N, obj_var, base_seed=0):
+        self.dims, self.T, self.N, self.base_seed = dims, T, N, base_seed
+        self.observation_space, self.action_space = _Box(dims.obs), _Box(dims.act)
+        self.ob_rms = _Rms(np.zeros(dims.obs), np.ones(dims.obs))
+        self.ret_rms = None
+        self.obj_rms = _Rms(np.zeros(dims.obj), obj_var)
+        self.venv = self
+        self.j, self.t, self.traj = None, 0, None
+
+    def reset(self):
+        self.j, self.t = None, 0
+        return torch.full((self.N, self.dims.obs), 0.25, dtype=torch.float32)
+
+    def step(self, action):
+        j = int(torch.initial_seed())
+        if j != self.j:
+            self.j, self.t = j, 0
+            self.traj = {k: v[0].numpy() for k, v in make_trajectories(1, self.T, self.N, self.dims, seed=self.base_seed + j).items()}
+        t = self.t
+        self.t += 1
+        obs = torch.as_tensor(self.traj["obs"][t + 1])
+        done = np.asarray(self.traj["masks"][t + 1]) == 0
+        infos = []
+        for n in range(len(done)):
+            info = {"obj": np.asarray(self.traj["rewards"][t, n], dtype=np.float64),
+                    "obj_raw": np.asarray(self.traj["rewards"][t, n], dtype=np.float64)}
+            if self.traj["bad_masks"][t + 1, n] == 0:
+                info["bad_transition"] = True
+            infos.append(info)
+        return obs, None, done, infos
+
+    def close(self):
+        pass
+
+
 class ToyEvalEnv:
     """Deterministic gym-like evaluation env: objective = smooth function of the policy's mean action."""
 
     def __init__(self, dims, horizon=5):
         self.dims, self.horizon = dims, horizon
+        self.observation_space, self.action_space = _Box(dims.obs), _Box(dims.act)
 
     def seed(self, s):
         self.rng = np.random.RandomState(s)
@@ -250,3 +292,17 @@ class ToyEvalEnv:
 
     def close(self):
         pass
+
+
+def run_args_2d(save_dir, T=64, N=4):
+    """Namespace of a short 2-objective PG-MORL run at Walker2d dims (driver-loop golden): 6 warm-up tasks
+    (delta_weight 0.2), warm-up of 2 iterations, 2 generations of 2 iterations, prediction-guided selection."""
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        env_name="replay", seed=0, obj_num=2, num_steps=T, num_processes=N, num_env_steps=6 * T * N,
+        warmup_iter=2, update_iter=2, selection_method="prediction-guided", min_weight=0.0, max_weight=1.0,
+        delta_weight=0.2, save_dir=save_dir, layernorm=False, algo="ppo", clip_param=0.2, ppo_epoch=2, num_mini_batch=4,
+        value_loss_coef=0.5, entropy_coef=0.0, lr=3e-4, max_grad_norm=0.5, gamma=0.995, obj_rms=True, ob_rms=True,
+        eval_num=1, raw=True, use_linear_lr_decay=True, lr_decay_ratio=1.0, use_gae=True, gae_lambda=0.95,
+        use_proper_time_limits=True, rl_log_interval=0, pbuffer_num=100, pbuffer_size=2, num_tasks=6,
+        num_weight_candidates=7, sparsity=1.0)

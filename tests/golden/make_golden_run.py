@@ -1,0 +1,59 @@
+"""Golden output of a WHOLE short PG-MORL run of the unmodified reference (`morl.run`, morl/morl.py:28-239: warm-up +
+evolutionary generations with prediction-guided selection, forked MOPG workers) on replay environments, for the driver
+loop of pgmorl_b200/morl.py. The reference's own result files (objs / optgraph / elites / weights / predictions /
+offsprings per generation) are copied to tests/golden/run_2d/.
+
+    python tests/golden/make_golden_run.py          (build container only: needs /root/reference)
+"""
+import os
+import shutil
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_import  # noqa: E402
+
+ref_import.install()
+sys.modules.setdefault("environments", types.ModuleType("environments"))     # morl.py:3 only registers gym envs
+
+from pgmorl_b200 import synthetic  # noqa: E402
+from pgmorl_b200.layout import NetDims  # noqa: E402
+
+
+def run_args(save_dir):
+    """The configuration of the golden run; tests/test_gpu_run.py builds the same namespace."""
+    return synthetic.run_args_2d(save_dir)
+
+
+def main():
+    import a2c_ppo_acktr.envs as envs_mod
+    import gym
+    d = NetDims(17, 6, 2)
+    save_dir = tempfile.mkdtemp()
+    args = run_args(save_dir)
+    envs_mod.make_vec_envs = lambda **kw: synthetic.SeededReplayVecEnv(d, args.num_steps, args.num_processes, [1.3, 0.7], base_seed=500)
+    gym.make = lambda name: synthetic.ToyEvalEnv(d)
+    import morl  # the reference's driver
+    t0 = time.time()
+    morl.run(args)
+    print("reference run: %.1f s" % (time.time() - t0))
+    out = os.path.join(ROOT, "tests", "golden", "run_2d")
+    shutil.rmtree(out, ignore_errors=True)
+    for gen in sorted(os.listdir(save_dir)):
+        if gen == "final":
+            os.makedirs(os.path.join(out, gen), exist_ok=True)
+            shutil.copy(os.path.join(save_dir, gen, "objs.txt"), os.path.join(out, gen, "objs.txt"))
+            continue
+        for sub in ("ep", "population", "elites"):
+            os.makedirs(os.path.join(out, gen, sub), exist_ok=True)
+            for f in os.listdir(os.path.join(save_dir, gen, sub)):
+                shutil.copy(os.path.join(save_dir, gen, sub, f), os.path.join(out, gen, sub, f))
+    print("golden written to", out, sorted(os.listdir(out)))
+
+
+if __name__ == "__main__":
+    main()
