@@ -182,6 +182,30 @@ int pgm_select_greedy_f64(const double *ep, int E, const double *cand, int C, in
                           void *stream);
 
 /* ---------------------------------------------------------------------------
+ * K6  running normalisation of raw simulator output, all P x N environments of the shard in one launch per
+ * environment step. Replaces, per task, VecNormalize.step_wait / reset
+ * (externals/baselines/baselines/common/vec_env/vec_normalize.py:29-66), the a2c override of _obfilt
+ * (a2c/envs.py:197-211) and RunningMeanStd.update (baselines/common/running_mean_std.py:10-31), so that the host
+ * environment workers exchange only raw observations / actions with the GPU.
+ *   raw_obs [P,N,O], raw_rew [P,N] (scalar reward; may be NULL), raw_obj [P,N,M] (may be NULL), done [P,N] (1 = episode ended)
+ *   running moments, FP64, updated in place, bit-identical to numpy's:
+ *     ob_mean/ob_var [P,O], ob_count [P]       (all NULL: observations pass through unnormalised)
+ *     ret_acc [P,N] discounted return, ret_stat [P,3] = mean, var, count    (NULL: not tracked)
+ *     obj_acc [P,N,M] discounted objective sums, obj_started [P] (0 until the first step),
+ *     obj_mean/obj_var [P,M], obj_count [P]    (moments NULL: objectives pass through unnormalised)
+ *   outputs, FP32: obs_out = clip((obs - mean) / sqrt(var + epsilon), +-clipob) for task p at obs_out + p * obs_task_stride
+ *     ([N,O] rows, i.e. the slot of the rollout buffer K1 reads next); obj_out = clip(obj / sqrt(obj_var + epsilon), +-cliprew)
+ *     at obj_out + p * obj_task_stride ([N,M]); mask_out [N] at mask_out + p * mask_task_stride = 1 - done.
+ *   update = 0 freezes the observation moments (VecNormalize.eval()); reset = 1 is VecNormalize.reset(): only the
+ *   observations are processed and ret_acc restarts at 0. N <= 128. */
+int pgm_vecnorm_step_f64(const double *raw_obs, const double *raw_rew, const double *raw_obj, const uint8_t *done,
+                         double *ob_mean, double *ob_var, double *ob_count, double *ret_acc, double *ret_stat,
+                         double *obj_acc, int32_t *obj_started, double *obj_mean, double *obj_var, double *obj_count,
+                         float *obs_out, size_t obs_task_stride, float *obj_out, size_t obj_task_stride,
+                         float *mask_out, size_t mask_task_stride, double gamma, double clipob, double cliprew,
+                         double epsilon, int update, int reset, int P, int N, int O, int M, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Self-test of the tcgen05 (5th-generation tensor core) building blocks of the K3 tensor-core path
  * (csrc/tc.cuh): TF32 UMMA through every shared-memory operand view K3 uses, TMEM load/store, the 3-way
  * TF32 split. No reference counterpart (the reference runs torch-CPU GEMMs, algo/ppo.py:62-107).

@@ -46,6 +46,7 @@ SIGNATURES = {
     "pgm_front_metrics_f64": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
     "pgm_select_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "pgm_select_greedy_f64": (_I, [_P, _I, _P, _I, _I, C.c_double, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "pgm_vecnorm_step_f64": (_I, [_P] * 14 + [_P, _Z, _P, _Z, _P, _Z] + [C.c_double] * 4 + [_I] * 6 + [_P]),
     "pgm_tc_selftest": (_I, [_P, _I, _P]),
     "pgm_tc_mma_bench": (_I, [_P] + [_I] * 8 + [_P]),
     "pgm_tc_layout_probe": (_I, [_P] + [_I] * 19 + [_P]),

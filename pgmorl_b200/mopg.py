@@ -23,15 +23,21 @@ from .a2c_ppo_acktr.storage import RolloutStorage
 from .population_state import PopulationMOPG
 from .sample import Sample
 
-_HOOKS = {"make_vec_envs": None, "gym_make": None}
+_HOOKS = {"make_vec_envs": None, "gym_make": None, "make_raw_vec_envs": None}
 
 
-def set_env_hooks(make_vec_envs=None, gym_make=None):
-    """Install the environment factories (signature of a2c_ppo_acktr.envs.make_vec_envs / gym.make)."""
+def set_env_hooks(make_vec_envs=None, gym_make=None, make_raw_vec_envs=None):
+    """Install the environment factories (signature of a2c_ppo_acktr.envs.make_vec_envs / gym.make).
+    `make_raw_vec_envs(**same kwargs)` returns vectorised environments WITHOUT the VecNormalize wrapper:
+    `reset() -> raw obs [N,O]`, `step(actions) -> (raw obs [N,O] f64, raw scalar rewards [N], done [N], infos with the raw
+    'obj' vector and optionally 'bad_transition')`. When it is installed, `mopg_population_update` keeps the running
+    normalisation on the device (K6, vec_normalize.DeviceVecNormalize); pass `False` to uninstall."""
     if make_vec_envs is not None:
         _HOOKS["make_vec_envs"] = make_vec_envs
     if gym_make is not None:
         _HOOKS["gym_make"] = gym_make
+    if make_raw_vec_envs is not None:
+        _HOOKS["make_raw_vec_envs"] = make_raw_vec_envs or None
 
 
 def _make_vec_envs(**kw):
@@ -140,6 +146,66 @@ def MOPG_worker(args, task_id, task, device, iteration, num_updates, start_time,
     done_event.wait()
 
 
+def _population_update_raw(args, task_batch, pop, device, start_iter, final_iter, total_num_updates):
+    """The rollout loop of `mopg_population_update` with the normalisation on the device: the host only steps the raw
+    simulators; K6 turns their output into the normalised observation / reward / mask slots of the rollout buffers and
+    K1 reads the observation from there."""
+    from .vec_normalize import DeviceVecNormalize
+    P, T, N, M = len(task_batch), args.num_steps, args.num_processes, args.obj_num
+    dims = pop.dims
+    kw = dict(env_name=args.env_name, seed=args.seed, num_processes=N, gamma=args.gamma, log_dir=None, device=device,
+              allow_early_resets=False, obj_rms=args.obj_rms, ob_rms=args.ob_rms)
+    envs_all = [_HOOKS["make_raw_vec_envs"](**kw) for _ in task_batch]
+    # a2c/envs.py:86-91: VecNormalize(ret=False) without a discount, else VecNormalize(gamma=...); ob / obj moments optional
+    vn = DeviceVecNormalize(P, N, dims.obs, M, ob=args.ob_rms, ret=args.gamma is not None, obj_rms=args.obj_rms,
+                            gamma=args.gamma if args.gamma is not None else 0.99, device=pop.device)
+    for p, task in enumerate(task_batch):
+        vn.load_task(p, task.sample.env_params)
+    vn.reset(np.stack([np.asarray(e.reset(), dtype=np.float64) for e in envs_all]), pop.obs[:, 0:N])
+    offspring = [[] for _ in range(P)]
+    bad = torch.empty(P, N, pin_memory=True)
+    for j in range(start_iter, final_iter):
+        torch.manual_seed(j)
+        lr = args.lr - (args.lr * ((j * args.lr_decay_ratio) / float(total_num_updates))) if args.use_linear_lr_decay else args.lr
+        pop.set_lr(lr)
+        pop.masks[:, 0] = 1.0 if j == start_iter else pop.masks[:, T]
+        pop.bad_masks[:, 0] = 1.0 if j == start_iter else pop.bad_masks[:, T]
+        if j > start_iter:
+            pop.obs[:, 0:N].copy_(pop.obs[:, T * N:])                                               # after_update (storage.py:71-75)
+        for step in range(T):
+            eps_t = torch.empty(N, dims.act, dtype=torch.float64).normal_(0, 1)
+            act_host = pop.act_step_resident(step, eps_t).cpu()
+            raw = [envs.step(act_host[p]) for p, envs in enumerate(envs_all)]
+            for p, (_, _, _, infos) in enumerate(raw):
+                for n, info in enumerate(infos):
+                    bad[p, n] = 0.0 if 'bad_transition' in info.keys() else 1.0
+            vn.step(np.stack([np.asarray(r[0], dtype=np.float64) for r in raw]),
+                    np.stack([np.asarray(r[1], dtype=np.float64).reshape(N) for r in raw]),
+                    np.stack([np.stack([np.asarray(i['obj'], dtype=np.float64) for i in r[3]]) for r in raw]),
+                    np.stack([np.asarray(r[2], dtype=bool) for r in raw]),
+                    pop.obs[:, (step + 1) * N:(step + 2) * N], pop.rewards[:, step], pop.masks[:, step + 1])
+            pop.bad_masks[:, step + 1].copy_(bad)
+        pop.finish_rollout_resident()
+        if vn.has_obj:
+            pop.obj_var.copy_(vn.obj_var.to(torch.float32))
+        else:
+            pop.obj_var.fill_(1.0 - 1e-8)
+        pop.perm.copy_(torch.stack([torch.randperm(T * N) for _ in range(args.ppo_epoch)]).to(torch.int32)[None])
+        pop.update_only()
+        for p, task in enumerate(task_batch):
+            ac, agent = deepcopy(task.sample.actor_critic), deepcopy(task.sample.agent)
+            ac.flat = pop.params[p].clone()
+            agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
+            agent.optimizer.step_count = int(pop.adam_step[p])
+            agent.optimizer.param_groups[0]['lr'] = lr
+            sample = Sample(vn.snapshot(p), ac, agent)
+            sample.objs = evaluation(args, sample)
+            offspring[p].append(sample)
+    for envs in envs_all:
+        envs.close()
+    return offspring
+
+
 def mopg_population_update(args, task_batch, device, iteration, num_updates, start_time=None, cluster=0):
     """All tasks of this shard advance together; returns offspring[task_id] = list of Samples (one per iteration),
     the content the reference's workers put on the queue (morl/morl.py:93-99)."""
@@ -155,16 +221,22 @@ def mopg_population_update(args, task_batch, device, iteration, num_updates, sta
                          num_mini_batch=args.num_mini_batch, gamma=args.gamma, gae_lambda=args.gae_lambda,
                          hyper=hyper, device=dev, cluster=cluster)
     envs_all = []
+    raw_mode = _HOOKS["make_raw_vec_envs"] is not None
     for p, task in enumerate(task_batch):
         ac, opt = task.sample.actor_critic, task.sample.agent.optimizer
         pop.params[p].copy_(ac.flat); pop.adam_m[p].copy_(opt.exp_avg); pop.adam_v[p].copy_(opt.exp_avg_sq)
         pop.adam_step[p] = opt.step_count
         pop.weights[p].copy_(torch.as_tensor(np.asarray(task.scalarization.weights, dtype=np.float64), dtype=torch.float32))
+        if raw_mode:
+            continue
         envs = _make_vec_envs(env_name=args.env_name, seed=args.seed, num_processes=args.num_processes, gamma=args.gamma,
                               log_dir=None, device=device, allow_early_resets=False, obj_rms=args.obj_rms, ob_rms=args.ob_rms)
         _restore_rms(envs, task.sample.env_params)
         envs_all.append(envs)
     T, N, M = args.num_steps, args.num_processes, args.obj_num
+    if raw_mode:
+        return _population_update_raw(args, task_batch, pop, device, iteration, min(iteration + num_updates, total_num_updates),
+                                      total_num_updates)
     obs_now = torch.stack([torch.as_tensor(e.reset()).to(torch.float32) for e in envs_all])       # [P,N,O] host
     offspring = [[] for _ in range(P)]
     start_iter, final_iter = iteration, min(iteration + num_updates, total_num_updates)

@@ -47,7 +47,7 @@ def select_tasks(args, population, ep, opt_graph, template, iteration, rl_num_up
     if method == 'moead':        # for each grid weight, the population member with the best scalarised value
         scals, elites = _grid_scalarizations(args, template), []
         for s in scals:
-            values = [float(s.evaluate(torch.Tensor(sample.objs))) for sample in population.sample_batch]
+            values = [float(s.evaluate(torch.as_tensor(np.asarray(sample.objs, dtype=np.float64)))) for sample in population.sample_batch]
             best, best_value = None, -np.inf
             for sample, value in zip(population.sample_batch, values):      # strict '>' : first maximum wins
                 if value > best_value:

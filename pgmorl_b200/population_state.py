@@ -112,6 +112,28 @@ class PopulationMOPG:
         self.value[:, rows].copy_(value); self.action[:, rows].copy_(action); self.logp[:, rows].copy_(logp)
         return action
 
+    def act_step_resident(self, t, eps_t):
+        """K1 in per-step mode on the observation ALREADY in the rollout buffer (written there by K6,
+        vec_normalize.DeviceVecNormalize): nothing but the noise travels host -> device. Returns actions [P,N,A]."""
+        P, N, d = self.P, self.N, self.dims
+        if not hasattr(self, "_step_obs"):
+            self._step_obs = torch.empty(P, N, d.obs, device=self.device)
+            self._step_out = (torch.empty(P, N, d.obj, device=self.device), torch.empty(P, N, d.act, device=self.device),
+                              torch.empty(P, N, device=self.device))
+        rows = slice(t * N, (t + 1) * N)
+        self._step_obs.copy_(self.obs[:, rows])
+        eps = eps_t.to(self.device, torch.float32)[None].contiguous()
+        value, action, logp = K.policy_forward(self.params, self._step_obs, d, eps=eps, out=self._step_out)
+        self.value[:, rows].copy_(value); self.action[:, rows].copy_(action); self.logp[:, rows].copy_(logp)
+        return action
+
+    def finish_rollout_resident(self):
+        """Bootstrap value of the observation K6 left in the last slot (mopg.py:132-135)."""
+        T, N, d = self.T, self.N, self.dims
+        self._step_obs.copy_(self.obs[:, T * N:])
+        value, _, _ = K.policy_forward(self.params, self._step_obs, d, rows_a=0, mode=K.ACT_DETERMINISTIC)
+        self.value[:, T * N:].copy_(value)
+
     def store_transition(self, p, t, objs, masks, bad_masks):
         """Reward vector / termination flags task p observed after step t (host values)."""
         self.rewards[p, t].copy_(torch.as_tensor(objs, dtype=torch.float32))

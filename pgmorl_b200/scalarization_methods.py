@@ -1,15 +1,24 @@
-"""Scalarisation functions (mirror of morl/scalarization_methods.py:5-29)."""
+"""Scalarisation functions (mirror of morl/scalarization_methods.py:5-29). Weights are float64 tensors: the
+reference runs under torch.set_default_dtype(torch.float64) (morl/morl.py:33), this package does not touch the
+process-wide default."""
+import numpy as np
 import torch
+
+
+def _f64(weights):
+    if isinstance(weights, torch.Tensor):
+        return weights.detach().to(torch.float64).clone()
+    return torch.as_tensor(np.asarray(weights, dtype=np.float64))
 
 
 class ScalarizationFunction:
     def __init__(self, num_objs, weights=None):
         self.num_objs = num_objs
-        self.weights = None if weights is None else torch.Tensor(weights)
+        self.weights = None if weights is None else _f64(weights)
 
     def update_weights(self, weights):
         if weights is not None:
-            self.weights = torch.Tensor(weights)
+            self.weights = _f64(weights)
 
     def evaluate(self, objs):
         raise NotImplementedError

@@ -24,24 +24,33 @@ from pgmorl_b200 import synthetic  # noqa: E402
 from pgmorl_b200.layout import NetDims  # noqa: E402
 
 
-def run_args(save_dir):
+METHODS = ("prediction-guided", "moead", "ra", "pfa", "random")     # morl/morl.py:128-169
+
+
+def run_args(save_dir, method="prediction-guided"):
     """The configuration of the golden run; tests/test_gpu_run.py builds the same namespace."""
-    return synthetic.run_args_2d(save_dir)
+    args = synthetic.run_args_2d(save_dir)
+    args.selection_method = method
+    return args
 
 
-def main():
+def out_dir(method):
+    return os.path.join(ROOT, "tests", "golden", "run_2d" if method == "prediction-guided" else "run_2d_" + method)
+
+
+def one_run(method):
     import a2c_ppo_acktr.envs as envs_mod
     import gym
     d = NetDims(17, 6, 2)
     save_dir = tempfile.mkdtemp()
-    args = run_args(save_dir)
+    args = run_args(save_dir, method)
     envs_mod.make_vec_envs = lambda **kw: synthetic.SeededReplayVecEnv(d, args.num_steps, args.num_processes, [1.3, 0.7], base_seed=500)
     gym.make = lambda name: synthetic.ToyEvalEnv(d)
     import morl  # the reference's driver
     t0 = time.time()
     morl.run(args)
     print("reference run: %.1f s" % (time.time() - t0))
-    out = os.path.join(ROOT, "tests", "golden", "run_2d")
+    out = out_dir(method)
     shutil.rmtree(out, ignore_errors=True)
     for gen in sorted(os.listdir(save_dir)):
         if gen == "final":
@@ -53,6 +62,11 @@ def main():
             for f in os.listdir(os.path.join(save_dir, gen, sub)):
                 shutil.copy(os.path.join(save_dir, gen, sub, f), os.path.join(out, gen, sub, f))
     print("golden written to", out, sorted(os.listdir(out)))
+
+
+def main():
+    for method in (sys.argv[1:] or METHODS):
+        one_run(method)
 
 
 if __name__ == "__main__":
