@@ -349,7 +349,9 @@ def main():
         k3_tflops = P * S * upd / (k3_ms * 1e-3) / 1e12
         # which K3 kernel ran: the tensor-core path (tcgen05 on FP16 operand pairs) is chosen explicitly (cluster 32) or by
         # the library from 8 tasks on for the shapes it is built for; otherwise the FP32 FFMA cluster kernels
-        tc = args.cluster == 32 or (args.cluster == 0 and P >= 8 and (d.obs, d.act, d.obj) in ((17, 6, 2), (11, 3, 3)))
+        wide = (d.obs, d.act, d.obj) == (376, 17, 2)          # Humanoid: the streamed tensor-core kernel (csrc/k3_tcw.cuh)
+        tc = (args.cluster in (32, 64) or (wide and args.cluster in (0, 128)) or
+              (args.cluster == 0 and P >= 8 and (d.obs, d.act, d.obj) in ((17, 6, 2), (11, 3, 3))))
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures (profiles/): only the
         # two configurations that were captured, null otherwise
         traffic = {("c2", False): 7.5e6, ("walker64", True): 81.4e6}.get((args.config, tc))
@@ -362,7 +364,7 @@ def main():
                   "fp32_ffma_peak_tflops": ffma_peak, "frac_of_fp32_ffma_peak": k3_tflops / ffma_peak}
         if tc:
             tpeak = peaks.get("bf16_tflops_sustained", 1400.0)    # FP16 and BF16 UMMA run at the same rate
-            roofline = dict(common, kernel="k3_tc_kernel", bound="tensor", peak=tpeak, frac=k3_tflops / tpeak,
+            roofline = dict(common, kernel="k3_tcw_kernel" if wide else "k3_tc_kernel", bound="tensor", peak=tpeak, frac=k3_tflops / tpeak,
                             peak_source=("measured" if peaks else "fallback") + " dense 16-bit tensor peak (sustained)",
                             note="algorithmic FLOPs; the kernel executes 3 MMAs per product (FP16 operand pairs, FP32-level "
                                  "accuracy) on 128xNx16 tiles with N <= 64, which are shared-memory-operand bound (113 B/clk "

@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_kernel(const K3Args a) {
 }  // namespace pgm
 #include "k3_fast.cuh"
 #include "k3_tc.cuh"
+#include "k3_tcw.cuh"
 namespace pgm {
 
 // ------------------------------------------------------------------------------------------
@@ -548,11 +549,12 @@ namespace pgm {
 // ------------------------------------------------------------------------------------------
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
-    bool DB, fast, tc;
+    bool DB, fast, tc, tcw;
     int rs;
     int stage_floats;
     size_t smem;
     size_t off_rec, off_gpart, off_ssq, off_lpart, off_trace, off_mv, total;
+    size_t off_xp, off_scr, off_w1img, off_pmv;      // wide tensor-core path (k3_tcw.cuh)
 };
 
 static size_t k3_smem_bytes(const NetLayout &L, int C, int TM, bool DB, int RSS) {
@@ -571,10 +573,44 @@ static bool k3_tc_dims(int O, int A, int M) { return (O == 17 && A == 6 && M == 
 static size_t k3_tc_mv_bytes(int P) { return (size_t)P * 2 * 2 * 2 * TC_NHP * sizeof(float); }   // [P][half][rs <= 2][m|v]
 constexpr int K3_CLUSTER_TC = 32;   // `cluster` values that select the tensor-core path explicitly: 32 = 2 CTAs per task,
 constexpr int K3_CLUSTER_TC2 = 64;  // 64 = 4 CTAs per task (row tiles split over two CTAs per network half)
+constexpr int K3_CLUSTER_TC4 = 128; // 128 = 8 CTAs per task (wide-observation kernel only)
+// shape the wide-observation tensor-core kernel (k3_tcw.cuh) is instantiated for: Humanoid
+static bool k3_tcw_dims(int O, int A, int M) { return O == 376 && A == 17 && M == 2; }
+static size_t k3_tcw_bytes(int P, int S, int O, int A, size_t *oxp, size_t *oscr, size_t *ow1, size_t *opmv) {
+    size_t off = 0;
+    auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t a0 = seg((size_t)P * S * TW_XROW_HW * sizeof(__half));
+    const size_t a1 = seg((size_t)P * S * TW_SCF * sizeof(float));
+    const size_t a2 = seg((size_t)P * 2 * TW_NB * 8192 * sizeof(__half));
+    const size_t a3 = seg((size_t)P * 2 * 3 * tw_nhp(O, A) * sizeof(float));
+    if (oxp) { *oxp = a0; *oscr = a1; *ow1 = a2; *opmv = a3; }
+    return off;
+}
 
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
-    pl.tc = false; pl.off_mv = 0;
+    pl.tc = false; pl.tcw = false; pl.off_mv = 0;
+    // wide observations (Humanoid): the streamed tensor-core kernel; row split over as many CTAs per half as fill the SMs
+    if (k3_tcw_dims(O, A, M) && (cluster == 0 || cluster == K3_CLUSTER_TC || cluster == K3_CLUSTER_TC2 || cluster == K3_CLUSTER_TC4)) {
+        const int tiles = (mb + 127) / 128;
+        if (cluster == 0) pl.rs = (tiles >= 4 && 8 * P <= sms) ? 4 : ((tiles >= 2 && 4 * P <= sms) ? 2 : 1);
+        else pl.rs = cluster == K3_CLUSTER_TC4 ? 4 : (cluster == K3_CLUSTER_TC2 ? 2 : 1);
+        pl.tc = true; pl.tcw = true; pl.C = 2 * pl.rs; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
+        pl.RSG = 0; pl.RSS = 0; pl.NHP = 64; pl.DB = false; pl.fast = false; pl.stage_floats = 0;
+        pl.smem = tw_smem_layout().total;
+        size_t off = 0;
+        auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        pl.off_rec = 0;
+        pl.off_gpart = seg((size_t)P * 2 * pl.G * pl.NHP * sizeof(float));
+        pl.off_ssq = seg((size_t)P * 16 * sizeof(float));
+        pl.off_lpart = seg((size_t)P * 16 * 4 * sizeof(float));
+        pl.off_trace = 0;
+        const size_t base = off;
+        off += k3_tcw_bytes(P, S, O, A, &pl.off_xp, &pl.off_scr, &pl.off_w1img, &pl.off_pmv);
+        pl.off_xp += base; pl.off_scr += base; pl.off_w1img += base; pl.off_pmv += base;
+        pl.total = off;
+        return PGM_OK;
+    }
     // auto: the tensor-core path wins as soon as the FFMA path can no longer give every task a 16-CTA cluster (measured on
     // a B200, profiles/k3_sweep.py: 1.2x at P = 8, 2.4x at 16, 3.3x from 37 tasks on; below 8 tasks FFMA is 6 % faster)
     if (cluster == 0 && k3_tc_dims(O, A, M) && P >= 8) {
@@ -607,7 +643,7 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     PGM_REQUIRE(O >= 1 && O <= 384 && A >= 1 && A <= 32 && M >= 1 && M <= 16,
                 "ppo: unsupported dims O=%d A=%d M=%d (O<=384, A<=32, M<=16)", O, A, M);
     PGM_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16,
-                "ppo: cluster must be 0 (auto), 1, 2, 4, 8, 16 (FP32 FFMA paths), 32 or 64 (tensor-core path) (got %d)", cluster);
+                "ppo: cluster must be 0 (auto), 1, 2, 4, 8, 16 (FP32 FFMA paths), 32, 64 (tensor-core paths) or 128 (wide tensor-core path) (got %d)", cluster);
     int C = cluster;
     if (C == 0) {   // fill the SMs: double the cluster while every task still gets its CTAs resident at once
         C = 2;      // one CTA per network half is the throughput configuration (large populations)
@@ -685,6 +721,19 @@ static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
     }
 }
 
+template <typename Kern>
+static int k3_launch_w(Kern kern, const K3Args &a, const TwExtra &x, const K3Plan &pl, int P, cudaStream_t st) {
+    PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P * pl.C); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    PGM_CUDA(cudaLaunchKernelEx(&cfg, kern, a, x));
+    return PGM_OK;
+}
+
 static int k3_launch(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
     if (pl.tc) {
         if (a.L.O == 17) return pl.rs == 2 ? k3_launch_k(k3_tc_kernel<17, 6, 2, 2>, pl.C, a, pl, P, st)
@@ -727,6 +776,7 @@ extern "C" size_t pgm_ppo_workspace_bytes(int P, int S, int O, int A, int M, int
     seg((size_t)P * 16 * sizeof(float));
     seg((size_t)P * 64 * sizeof(float));
     if (k3_tc_dims(O, A, M)) seg(k3_tc_mv_bytes(P));
+    if (k3_tcw_dims(O, A, M)) seg(k3_tcw_bytes(P, S, O, A, nullptr, nullptr, nullptr, nullptr) + 1024);
 #ifdef PGM_K3_TRACE
     seg((size_t)P * 16 * 4 * 16 * 2 * sizeof(long long));
 #endif
@@ -765,6 +815,22 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
     a.grad_out = grad_out; a.perm_shared = perm_shared; a.E = E; a.B = B; a.mb = mb; a.S = S;
     a.grad_only = grad_out != nullptr; a.nsteps = a.grad_only ? 1 : E * B;
     a.Rg = pl.Rg; a.RSG = pl.RSG; a.RSS = pl.RSS; a.NHP = pl.NHP; a.stage_floats = pl.stage_floats; a.rs = pl.rs; a.hy = *hy; a.L = NetLayout(O, A, M);
+    if (pl.tcw) {
+        TwExtra x;
+        x.xp = (const __half *)(ws + pl.off_xp); x.scr = (const float *)(ws + pl.off_scr);
+        x.w1img = (__half *)(ws + pl.off_w1img); x.pmv = (float *)(ws + pl.off_pmv);
+        const size_t total = (size_t)P * S * (TW_NB * 64 + TW_SCF);
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > sms * 16) blocks = sms * 16;
+        k3w_pack_kernel<376, 17, 2><<<blocks, 256, 0, st>>>(obs, obs_ts, action, logp_old, value_old, v_ts, returns, adv,
+                                                            (__half *)(ws + pl.off_xp), (float *)(ws + pl.off_scr), P, S);
+        PGM_CUDA(cudaGetLastError());
+        // features O+1 .. 383 of the last W1 block image are never written by the kernel: they must be zero, not stale bytes
+        PGM_CUDA(cudaMemsetAsync(ws + pl.off_w1img, 0, (size_t)P * 2 * TW_NB * 8192 * sizeof(__half), st));
+        if (pl.rs == 4) return k3_launch_w(k3_tcw_kernel<376, 17, 2, 4>, a, x, pl, P, st);
+        if (pl.rs == 2) return k3_launch_w(k3_tcw_kernel<376, 17, 2, 2>, a, x, pl, P, st);
+        return k3_launch_w(k3_tcw_kernel<376, 17, 2, 1>, a, x, pl, P, st);
+    }
     {
         const size_t total = (size_t)P * S * pl.RSG;
         int blocks = (int)((total + 255) / 256);

@@ -134,16 +134,19 @@ def _ppo_inputs(d, P, T, N, seed):
     return cur, pack, perm
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 32, 64])      # 32 / 64 = tensor-core path (tcgen05, csrc/k3_tc.cuh), 2 / 4 CTAs per task
+# 32 / 64 / 128 = tensor-core paths (tcgen05): 2 / 4 / 8 CTAs per task; csrc/k3_tc.cuh (Walker2d, Hopper-v3 shapes),
+# csrc/k3_tcw.cuh (Humanoid: layer 1 streamed in 64-feature blocks)
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 32, 64, 128])
 @pytest.mark.parametrize("name,P,T,N,mb", [("walker", 2, 64, 4, 256), ("walker", 1, 30, 4, 100),
-                                            ("hopper3", 2, 48, 2, 64), ("humanoid", 1, 32, 8, 96)])
+                                            ("hopper3", 2, 48, 2, 64), ("humanoid", 1, 32, 8, 96),
+                                            ("humanoid", 2, 64, 8, 512), ("humanoid", 1, 40, 8, 300)])
 def test_k3_gradient_matches_oracle(name, P, T, N, mb, cluster):
     from pgmorl_b200 import kernels as K
     d = DIMS[name]
     if name == "humanoid" and cluster == 1:
         pytest.skip("wide networks need cluster >= 2 (both halves do not fit one CTA's shared memory)")
-    if name == "humanoid" and cluster >= 32:
-        pytest.skip("the tensor-core path is built for the Walker2d/HalfCheetah and Hopper-v3 shapes")
+    if name != "humanoid" and cluster == 128:
+        pytest.skip("8 CTAs per task exist on the wide-observation tensor-core path only")
     cur, pk, perm = _ppo_inputs(d, P, T, N, seed=11)
     S = T * N
     idx = np.random.RandomState(0).permutation(S)[:mb]
@@ -193,6 +196,35 @@ def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
         assert rel_err(gp[p].cpu().numpy(), flat) < 1e-5       # parameters (gate 1e-4)
         assert rel_err(gm[p].cpu().numpy(), m) < 1e-4          # Adam first moment
         assert rel_err(gv[p].cpu().numpy(), v) < 1e-4          # Adam second moment
+        assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 1e-4
+
+
+@pytest.mark.parametrize("cluster", [0, 8, 32, 64, 128])
+@pytest.mark.parametrize("T,N,B", [(48, 8, 1), (48, 8, 3), (64, 8, 1)])       # minibatches of 384 (3 row tiles), 128, 512 rows
+def test_k3_update_matches_oracle_humanoid(T, N, B, cluster):
+    """the update on Humanoid dims: generic FFMA path (cluster 8) and the wide tensor-core kernel with 1 / 2 / 4 CTAs
+    per network half (32 / 64 / 128; 0 = auto), same tolerances as the other shapes"""
+    from pgmorl_b200 import kernels as K
+    d, P = DIMS["humanoid"], 2
+    cur, pk, perm = _ppo_inputs(d, P, T, N, seed=19)
+    rng = np.random.RandomState(3)
+    m0, v0 = rng.randn(P, d.n_par) * 1e-3, rng.rand(P, d.n_par) * 1e-5
+    step0, lr = np.array([0, 7], dtype=np.int32), np.array([3e-4, 2.5e-4])
+    gp, gm, gv, gstep = dev(cur), dev(m0), dev(v0), dev(step0, torch.int32)
+    losses = K.ppo_update(gp, gm, gv, gstep, dev(lr, torch.float64), dev(pk["obs"]), dev(pk["action"]),
+                          dev(pk["logp"]), dev(pk["value"]), dev(pk["returns"]), dev(pk["adv"]),
+                          dev(perm[None], torch.int32), B, d, cluster=cluster)
+    torch.cuda.synchronize()
+    for p in range(P):
+        flat, m, v = (dev(t[p]).cpu().numpy().astype(np.float64) for t in (cur, m0, v0))
+        step, lref = orc.ppo_update(flat, m, v, int(step0[p]), lr[p], (d.obs, d.act, d.obj),
+                                    pk["obs"][p].reshape(T + 1, N, d.obs).astype(np.float64),
+                                    pk["action"][p].reshape(T, N, -1), pk["logp"][p].reshape(T, N),
+                                    pk["value"][p].reshape(T + 1, N, -1), pk["returns"][p].reshape(T, N, -1),
+                                    pk["adv"][p].reshape(T, N), perm, B)
+        assert int(gstep[p]) == step
+        assert rel_err(gp[p].cpu().numpy(), flat) < 1e-5
+        assert rel_err(gm[p].cpu().numpy(), m) < 1e-4 and rel_err(gv[p].cpu().numpy(), v) < 1e-4
         assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 1e-4
 
 
