@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) k1_forward_kernel(con
 
 }  // namespace pgm
 #include "k1_tc.cuh"
+#include "k1_tcw.cuh"
 
 using namespace pgm;
 
@@ -152,6 +153,24 @@ static int k1_tc_launch(Kern kern, K1Args &a, int P, int O, cudaStream_t st) {
     return PGM_OK;
 }
 
+// wide observations (Humanoid): one tile at a time, CTAs per (task, half) sized to fill the SMs once
+static int k1_tcw_launch(K1Args &a, int P, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    PGM_CUDA(cudaGetDevice(&dev));
+    PGM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = (a.rows_v + 127) / 128;
+    int nblk = sms / (2 * P);
+    if (nblk > ntiles) nblk = ntiles;
+    if (nblk < 1) nblk = 1;
+    a.chunks_per_cta = (ntiles + nblk - 1) / nblk;
+    nblk = (ntiles + a.chunks_per_cta - 1) / a.chunks_per_cta;
+    const size_t smem = k1w_smem_layout().total;
+    PGM_CUDA(cudaFuncSetAttribute(k1_tcw_kernel<376, 17, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_tcw_kernel<376, 17, 2><<<dim3(nblk, 2, P), K1T_THREADS, smem, st>>>(a);
+    PGM_CUDA(cudaGetLastError());
+    return PGM_OK;
+}
+
 extern "C" int pgm_policy_forward_f32(const float *params, const float *obs, const float *eps, int eps_shared,
                                       float *action, float *value, float *logp, int mode, int P, int rows_v,
                                       int rows_a, int O, int A, int M, void *stream) {
@@ -171,6 +190,7 @@ extern "C" int pgm_policy_forward_f32(const float *params, const float *obs, con
         if (O == 17) return k1_tc_launch(k1_tc_kernel<17, 6, 2>, a, P, O, (cudaStream_t)stream);
         return k1_tc_launch(k1_tc_kernel<11, 3, 3>, a, P, O, (cudaStream_t)stream);
     }
+    if (O == 376 && A == 17 && M == 2 && rows_v >= 1024) return k1_tcw_launch(a, P, (cudaStream_t)stream);
     const bool split = k1_smem_bytes(a.L, 4, false) > 110 * 1024;       // keep two CTAs per SM for small networks
     const int TM = split ? 2 : 4, RC = 16 * TM;
     const size_t smem = k1_smem_bytes(a.L, TM, split);

@@ -604,7 +604,11 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
         pl.off_gpart = seg((size_t)P * 2 * pl.G * pl.NHP * sizeof(float));
         pl.off_ssq = seg((size_t)P * 16 * sizeof(float));
         pl.off_lpart = seg((size_t)P * 16 * 4 * sizeof(float));
+#ifdef PGM_K3_TRACE
+        pl.off_trace = seg((size_t)P * 8 * 2 * 48 * sizeof(long long));
+#else
         pl.off_trace = 0;
+#endif
         const size_t base = off;
         off += k3_tcw_bytes(P, S, O, A, &pl.off_xp, &pl.off_scr, &pl.off_w1img, &pl.off_pmv);
         pl.off_xp += base; pl.off_scr += base; pl.off_w1img += base; pl.off_pmv += base;

@@ -51,7 +51,7 @@ __host__ __device__ inline TwSmem tw_smem_layout() {
     return s;
 }
 // misc (floats): red[40] | part[8 warps][48] | ssq[2 parities][8 ranks][8 warps]; at byte 2304: double sh_d[4], 8 mbarriers, tmem ptr
-constexpr int TWM_RED = 0, TWM_PART = 40, TWM_SSQ = 424;
+constexpr int TWM_RED = 0, TWM_PART = 40, TWM_SSQ = 424, TWM_IV = 552;   // iv[24] = exp(-2 logstd)
 // TMEM columns
 constexpr uint32_t TW_ACC = 0, TW_D1 = 64, TW_D2 = 128, TW_GW2 = 192, TW_GWH = 256, TW_GW1 = 288;   // GW1: 3 x 64
 
@@ -95,6 +95,14 @@ __global__ void k3w_pack_kernel(const float *__restrict__ obs, size_t obs_ts, co
     }
 }
 
+// PGM_K3_TRACE builds: clock64 marks of thread 0 (the MMA issuer), optimiser steps 8 and 9 (profiles/k3_tcw_trace.py):
+// trace[(cta * 2 + step - 8) * 48 + mark]
+#ifdef PGM_K3_TRACE
+#define TWT(i) if (trace_on) a.trace[trace_base + (i)] = clock64();
+#else
+#define TWT(i)
+#endif
+
 struct TwExtra {          // wide-path buffers inside the workspace
     const __half *xp;     // [P][S][TW_XROW_HW]
     const float *scr;     // [P][S][TW_SCF]
@@ -126,8 +134,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     const int obh = oWh + KH * H, ols = obh + KH;
     const int nH = ols + (actor ? A : 0);
     const int n4 = (nH + 3) >> 2;
-    const int n4s = (n4 + RS - 1) / RS;                  // my slice of the half: float4 indices [i4lo, i4hi)
-    const int i4lo = rs * n4s, i4hi = min(n4, i4lo + n4s);
+    // my slice of the half: chunks of 256 float4 go round-robin to the RS CTAs (every CTA gets the same share of each
+    // tensor: the W2 / head publishes through DSMEM are the expensive ones); thread tid owns float4 (u RS + rs) 256 + tid
+    constexpr int NU = ((NHP / 4 + TC_THREADS - 1) / TC_THREADS + RS - 1) / RS;
+    auto slice_i4 = [&](int u) { return (u * RS + rs) * TC_THREADS + tid; };
 
     unsigned char *S_h1 = smem_raw + sl.H1, *S_h2 = smem_raw + sl.H2, *S_do = smem_raw + sl.DO;
     __half *W2a = (__half *)(smem_raw + sl.W2a), *W2b = (__half *)(smem_raw + sl.W2b);
@@ -140,9 +150,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     constexpr int GW2LD = 68;
     static_assert((NHP + H * GW2LD) * 4 <= 65536 + 2 * (int)TW_STAGE, "gradient staging does not fit");
     float *misc = (float *)(smem_raw + sl.misc);
-    float *red = misc + TWM_RED, *part = misc + TWM_PART, *ssqS = misc + TWM_SSQ;
+    float *red = misc + TWM_RED, *part = misc + TWM_PART, *ssqS = misc + TWM_SSQ, *ivS = misc + TWM_IV;
     double *sh_d = (double *)(smem_raw + sl.misc + 2304);
-    uint64_t *mbars = (uint64_t *)(smem_raw + sl.misc + 2304 + 32);     // 0 chain, 1-2 forward stages, 3 weight grads, 4-5 G1X pairs, 6 tile done
+    uint64_t *mbars = (uint64_t *)(smem_raw + sl.misc + 2304 + 32);     // 0 chain, 1-3 forward stages, 4 weight grads, 5-6 G1X pairs, 7 tile done
     uint32_t *tmem_ptr_s = (uint32_t *)(smem_raw + sl.misc + 2304 + 96);
     const float *b2s = FP, *bhs = FP + 64, *lss = FP + 96;
 
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     __syncthreads();
     if (warp == 0) tc::tmem_alloc(tmem_ptr_s, 512);
     if (tid == 0) {
-        for (int i = 0; i < 7; ++i) tc::mbar_init(mbars + i, 1);
+        for (int i = 0; i < 8; ++i) tc::mbar_init(mbars + i, 1);
         tc::fence_mbar_init();
     }
     // publish one parameter / four consecutive parameters (half-local index) to wherever the kernels read them:
@@ -214,7 +224,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     sync_group<2>();                                     // every CTA of the cluster zeroed its shared memory
     {   // my slice: reference order -> half-local master / moments in the workspace, operand images
         const float *gpar = a.params + (size_t)task * L.n_par;
-        for (int i4 = i4lo + tid; i4 < i4hi; i4 += TC_THREADS) {
+        for (int u = 0; u < NU; ++u) {
+            const int i4 = slice_i4(u);
+            if (i4 >= n4) break;
             float pv[4], mv[4], vv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     const float *scg = x.scr + (size_t)task * a.S * TW_SCF;
     const int ntiles_all = (a.mb + 127) >> 7;
     const int ntiles = rs < ntiles_all ? (ntiles_all - rs + RS - 1) / RS : 0;
-    uint32_t ph[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};      // mbarrier phase parities
+    uint32_t ph[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // mbarrier phase parities
     auto mwait = [&](int b) { tc::mbar_wait(mbars + b, ph[b]); ph[b] ^= 1u; };
 
     // ---- descriptors (images are [rows][64 halfwords], SWIZZLE_128B; see k3_tc.cuh for the two views) ----
@@ -286,8 +298,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     const uint64_t dH1a_mn = dMN(aH1, 32768), dH1b_mn = dMN(aH1 + 16384, 32768);
     const uint64_t dH2a_mn = dMN(aH2, 32768), dH2b_mn = dMN(aH2 + 16384, 32768);
     const uint64_t dDOa_mn = dMN(aDO, 16384), dDOb_mn = dMN(aDO + 64, 16384);    // N = 32 head columns: a1 | a2
-    // forward stage s: x block a1 at aST + s * TW_STAGE, a2 + 16384, W1 block a1 + 32768, a2 + 40960
-    const uint64_t dSXa_k = dK(aST), dSXb_k = dK(aST + 16384), dSWa_k = dK(aST + 32768), dSWb_k = dK(aST + 40960);
     // backward x slots: slot 0 = H2, slots 1..3 = ST; a pair of slots (2p, 2p + 1) is one M = 128 MN-major operand
     const uint64_t dX0a_mn = dMN(aH2, 32768), dX0b_mn = dMN(aH2 + 16384, 32768);             // slots (0, 1)
     const uint64_t dX2a_mn = dMN(aST + 32768, 32768), dX2b_mn = dMN(aST + 49152, 32768);     // slots (2, 3)
@@ -321,6 +331,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     };
 
     for (int s = 0; s < a.nsteps; ++s) {
+#ifdef PGM_K3_TRACE
+        const bool trace_on = a.trace && (s == 8 || s == 9) && tid == 0;
+        const size_t trace_base = ((size_t)blockIdx.x * 2 + (s - 8)) * 48;
+#endif
         if (actor && rs == 0 && tid == 0) {   // entropy with the parameters this step starts from
             float ent = 0.f;
             for (int d = 0; d < A; ++d) ent += 0.5f + 0.91893853320467274178f + lss[d];
@@ -328,6 +342,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
         }
         for (int i = tid; i < 8 * 48; i += TC_THREADS) part[i] = 0.f;
         DB2[tid] = 0.f;
+        if (actor && tid < A) ivS[tid] = expf(-2.f * lss[tid]);
         const int ep = s / a.B, bb = s - ep * a.B;
         const int32_t *pb = perm + (size_t)ep * a.S + (size_t)bb * a.mb;
 
@@ -342,45 +357,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                 ridx[k] = ld_nc_s32(pb + (ok ? rowi : 0));
                 rvalid |= (ok ? 1u : 0u) << k;
             }
+            TWT(0)
             __syncthreads();                                   // everyone is done with the previous tile / step tail (SC, DO, ST)
+            if ((tid & 15) < 6) {                              // per-row scalars: pieces 0..5 of the 8 rows this thread gathers
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int f = tid + TC_THREADS * k, row = f / 6, pc = f - row * 6;
-                const int rowi = row0 + row;
-                const bool ok = rowi < a.mb;
-                const int idx = ld_nc_s32(pb + (ok ? rowi : 0));
-                cp_async16_z(tc::smem_addr(SC) + (uint32_t)f * 16u, scg + (size_t)idx * TW_SCF + pc * 4, ok);
+                for (int k = 0; k < 8; ++k) {
+                    const int row = (tid >> 4) + 16 * k, pc = tid & 15;
+                    cp_async16_z(tc::smem_addr(SC) + (uint32_t)(row * 6 + pc) * 16u, scg + (size_t)ridx[k] * TW_SCF + pc * 4, (rvalid >> k) & 1u);
+                }
             }
-            load_xblock(0, aST); load_w1block(0, aST + 32768);
-            cp_async_commit();
-            load_xblock(1, aST + TW_STAGE); load_w1block(1, aST + TW_STAGE + 32768);
-            cp_async_commit();
+            // three forward stages (x block 32 KB + W1 block 16 KB): the two in ST, and H2 + DO, both idle until E2 / E3
+            const uint32_t stX[3] = {aST, aST + TW_STAGE, aH2}, stW[3] = {aST + 32768, aST + TW_STAGE + 32768, aDO};
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { load_xblock(b, stX[b]); load_w1block(b, stW[b]); cp_async_commit(); }
+            TWT(1)
             // ---------------- G1: Z1 = [x | 1] W1^T over six streamed blocks ----------------
-#pragma unroll 1
+#pragma unroll
             for (int b = 0; b < TW_NB; ++b) {
-                if (b < TW_NB - 1) cp_async_wait<1>(); else cp_async_wait<0>();
+                if (b < TW_NB - 2) cp_async_wait<2>(); else if (b == TW_NB - 2) cp_async_wait<1>(); else cp_async_wait<0>();
                 tc::fence_async_smem();
                 __syncthreads();
-                const uint32_t so = (uint32_t)(b & 1) * TW_STAGE;
+                const int st = b % 3;
                 if (warp == 0 && tc::elect_one()) {
                     tc::tc_fence_after();
+                    const uint64_t xa = dK(stX[st]), xb = dK(stX[st] + 16384), wa = dK(stW[st]), wb = dK(stW[st] + 8192);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        mma3(tmem + TW_ACC, tc::desc_advance(dSXa_k, so + 32 * ks), tc::desc_advance(dSXb_k, so + 32 * ks),
-                             tc::desc_advance(dSWa_k, so + 32 * ks), tc::desc_advance(dSWb_k, so + 32 * ks), ID_KK, (b > 0 || ks > 0) ? 1u : 0u);
+                        mma3(tmem + TW_ACC, tc::desc_advance(xa, 32 * ks), tc::desc_advance(xb, 32 * ks),
+                             tc::desc_advance(wa, 32 * ks), tc::desc_advance(wb, 32 * ks), ID_KK, (b > 0 || ks > 0) ? 1u : 0u);
                     if (b == TW_NB - 1) tc::mma_commit(mbars + 0);                  // covers every MMA of G1
-                    else if (b + 2 < TW_NB) tc::mma_commit(mbars + 1 + (b & 1));    // stage b & 1 is refilled below
+                    else if (b + 3 < TW_NB) tc::mma_commit(mbars + 1 + st);         // stage st is refilled below
                 }
-                if (b + 2 < TW_NB) {
-                    mwait(1 + (b & 1));                        // the MMAs of block b released their stage
-                    load_xblock(b + 2, aST + so); load_w1block(b + 2, aST + so + 32768);
+                if (b + 3 < TW_NB) {
+                    mwait(1 + st);                             // the MMAs of block b released their stage
+                    load_xblock(b + 3, stX[st]); load_w1block(b + 3, stW[st]);
                     cp_async_commit();
                 }
+                TWT(2 + b)
             }
             // ---------------- E1: h1 = tanh(Z1) -> H1 pair, 1 - h1^2 -> TMEM ----------------
             {
                 unsigned char *rowh1 = S_h1 + r * 128;
                 mwait(0); tc::tc_fence_after();
+                TWT(8)
                 // the stages are free: prefetch x blocks 1..3 of the backward pass into slots 1..3
                 load_xblock(1, aST); load_xblock(2, aST + 32768); load_xblock(3, aST + 65536);
                 cp_async_commit();
@@ -392,6 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                 tc::tmem_st32(tq + TW_D1 + 32 * hcol, dd);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_pair8(rowh1, (uint32_t)(4 * hcol + c), rowh1 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
+                TWT(9)
                 sync_all();
                 if (warp == 0 && tc::elect_one()) {
                     tc::tc_fence_after();
@@ -401,11 +421,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                              tc::desc_advance(dW2a_k, 32 * ks), tc::desc_advance(dW2b_k, 32 * ks), ID_KK, ks > 0);
                     tc::mma_commit(mbars + 0);
                 }
+                TWT(10)
             }
             // ---------------- E2: h2 = tanh(Z2 + b2) -> H2 pair, 1 - h2^2 -> TMEM ----------------
             {
                 unsigned char *rowh2 = S_h2 + r * 128;
                 mwait(0); tc::tc_fence_after();
+                TWT(11)
                 float z[32], dd[32];
                 tc::tmem_ld32(tq + TW_ACC + 32 * hcol, z);
                 tc::tmem_ld_wait();
@@ -416,6 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                 tc::tmem_st32(tq + TW_D2 + 32 * hcol, dd);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_pair8(rowh2, (uint32_t)(4 * hcol + c), rowh2 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
+                TWT(12)
                 sync_all();
                 if (warp == 0 && tc::elect_one()) {
                     tc::tc_fence_after();
@@ -425,18 +448,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                              tc::desc_advance(dWh1_k, 32 * ks), tc::desc_advance(dWh2_k, 32 * ks), ID_HEAD, ks > 0);
                     tc::mma_commit(mbars + 0);
                 }
+                TWT(13)
             }
             // ---------------- E3: per-row loss and d loss / d head (warps 0..3: thread = row) ----------------
             mwait(0); tc::tc_fence_after();
+            TWT(14)
             if (hcol == 0) {
-                float ho[32], dq[KHP];
+                float ho[32], dq[32];
                 tc::tmem_ld32(tq + TW_ACC, ho);
                 const float *sc = SC + r * TW_SCF;
                 const bool row_valid = row0 + r < a.mb;
                 tc::tmem_ld_wait();
                 float gb[KHP], gl[KHP];
 #pragma unroll
-                for (int d = 0; d < KHP; ++d) { gb[d] = 0.f; gl[d] = 0.f; dq[d] = 0.f; }
+                for (int d = 0; d < KHP; ++d) { gb[d] = 0.f; gl[d] = 0.f; }
+#pragma unroll
+                for (int d = 0; d < 32; ++d) dq[d] = 0.f;
                 if (actor) {
                     float lp = 0.f, diffv[KHP], ivv[KHP];
 #pragma unroll
@@ -444,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                         diffv[d] = 0.f; ivv[d] = 0.f;
                         if (d < A) {
                             const float ls = lss[d];
-                            const float iv = expf(-2.f * ls);
+                            const float iv = ivS[d];
                             const float diff = sc[d] - fmaf(ho[d], 1.f / (TC_SH * TC_SW), bhs[d]);
                             lp += -0.5f * (diff * diff * iv) - ls - 0.91893853320467274178f;
                             diffv[d] = diff; ivv[d] = iv;
@@ -487,17 +514,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                 }
                 unsigned char *rowd = S_do + r * 128;
 #pragma unroll
-                for (int c = 0; c < KHP / 8; ++c) store_pair8(rowd, (uint32_t)c, rowd, (uint32_t)(4 + c), swz, dq + 8 * c);
-                // head bias / logstd gradients: warp sums -> this warp's partial slots
+                for (int c = 0; c < 4; ++c) store_pair8(rowd, (uint32_t)c, rowd, (uint32_t)(4 + c), swz, dq + 8 * c);
+                // head bias / logstd gradients: sums over the warp's 32 rows -> this warp's partial slots
+                if (actor) {                                   // 2 A <= 32 + 2 values: halving butterfly on 32, plain sums for the rest
+                    float v[32];
 #pragma unroll
-                for (int d = 0; d < KHP; ++d) {
-                    if (d < (actor ? A : M)) {
+                    for (int d = 0; d < 32; ++d) v[d] = d < A ? gb[d < A ? d : 0] : ((d - A < A) ? gl[(d - A < A) ? d - A : 0] : 0.f);
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float keep = up ? v[i + off] : v[i], send = up ? v[i] : v[i + off];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    part[warp * 48 + (lane < A ? lane : 24 + lane - A)] += v[0];        // lane l holds value l
+#pragma unroll
+                    for (int d = 32 - A; d < A; ++d) {                                    // logstd entries that did not fit
+                        const float sg = warp_sum(gl[d]);
+                        if (lane == 0) part[warp * 48 + 24 + d] += sg;
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < M; ++d) {
                         const float sb = warp_sum(gb[d]);
-                        const float sg = actor ? warp_sum(gl[d]) : 0.f;
-                        if (lane == 0) { part[warp * 48 + d] += sb; part[warp * 48 + 24 + d] += sg; }
+                        if (lane == 0) part[warp * 48 + d] += sb;
                     }
                 }
             }
+            TWT(15)
             sync_all();
             if (warp == 0 && tc::elect_one()) {
                 tc::tc_fence_after();
@@ -511,10 +557,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                          tc::desc_advance(dDOa_mn, 2048 * ks), tc::desc_advance(dDOb_mn, 2048 * ks), ID_GWH, 1);
                 tc::mma_commit(mbars + 0);
             }
+            TWT(16)
             // ---------------- E4: dz2 = dz2pre (1 - h2^2) -> H2 pair (in place); db2 += column sums ----------------
             {
                 unsigned char *rowh2 = S_h2 + r * 128;
                 mwait(0); tc::tc_fence_after();
+                TWT(17)
                 float z[32], dd[32];
                 tc::tmem_ld32(tq + TW_ACC + 32 * hcol, z);
                 tc::tmem_ld32(tq + TW_D2 + 32 * hcol, dd);
@@ -534,6 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                     }
                 }
                 DB2[warp * 32 + lane] += z[0];
+                TWT(18)
                 sync_all();
                 if (warp == 0 && tc::elect_one()) {
                     tc::tc_fence_after();
@@ -546,26 +595,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                     for (int ks = 0; ks < 8; ++ks)                                                 // dW2 += dz2^T h1
                         mma3(tmem + TW_GW2, tc::desc_advance(dH2a_mn, 2048 * ks), tc::desc_advance(dH2b_mn, 2048 * ks),
                              tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks), ID_GW2, 1);
-                    tc::mma_commit(mbars + 3);
+                    tc::mma_commit(mbars + 4);
                 }
+                TWT(19)
             }
             // ---------------- E5: dz1 = dz1pre (1 - h1^2) -> H1 pair (in place) ----------------
             {
                 unsigned char *rowh1 = S_h1 + r * 128;
                 mwait(0); tc::tc_fence_after();
+                TWT(20)
                 float z[32], dd[32];
                 tc::tmem_ld32(tq + TW_ACC + 32 * hcol, z);
                 tc::tmem_ld32(tq + TW_D1 + 32 * hcol, dd);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) z[k] = z[k] * (1.f / TC_SW) * dd[k];
-                mwait(3);                                      // dW2 MMAs are done reading h1 and dz2: H2 becomes x slot 0
+                mwait(4);                                      // dW2 MMAs are done reading h1 and dz2: H2 becomes x slot 0
+                TWT(21)
                 load_xblock(0, aH2);
                 cp_async_commit();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_pair8(rowh1, (uint32_t)(4 * hcol + c), rowh1 + 16384, (uint32_t)(4 * hcol + c), swz, z + 8 * c);
                 cp_async_wait<0>();
                 sync_all();
+                TWT(22)
             }
             // ---------------- G1X: dW1^T[feature][j] += x^T dz1, two blocks (M = 128 features) per accumulator ----------------
             if (warp == 0 && tc::elect_one()) {
@@ -574,35 +627,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                 for (int ks = 0; ks < 8; ++ks)
                     mma3(tmem + TW_GW1, tc::desc_advance(dX0a_mn, 2048 * ks), tc::desc_advance(dX0b_mn, 2048 * ks),
                          tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks), ID_GW1, 1);
-                tc::mma_commit(mbars + 4);
+                tc::mma_commit(mbars + 5);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                     mma3(tmem + TW_GW1 + 64, tc::desc_advance(dX2a_mn, 2048 * ks), tc::desc_advance(dX2b_mn, 2048 * ks),
                          tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks), ID_GW1, 1);
-                tc::mma_commit(mbars + 5);
+                tc::mma_commit(mbars + 6);
             }
-            mwait(4);                                          // slots 0, 1 are free: blocks 4, 5
+            TWT(23)
+            mwait(5);                                          // slots 0, 1 are free: blocks 4, 5
+            TWT(24)
             load_xblock(4, aH2); load_xblock(5, aST);
             cp_async_commit();
             cp_async_wait<0>();
             tc::fence_async_smem();
             __syncthreads();
+            TWT(25)
             if (warp == 0 && tc::elect_one()) {
                 tc::tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                     mma3(tmem + TW_GW1 + 128, tc::desc_advance(dX0a_mn, 2048 * ks), tc::desc_advance(dX0b_mn, 2048 * ks),
                          tc::desc_advance(dH1a_mn, 2048 * ks), tc::desc_advance(dH1b_mn, 2048 * ks), ID_GW1, 1);
-                tc::mma_commit(mbars + 6);
+                tc::mma_commit(mbars + 7);
             }
-            mwait(5);
-            mwait(6);                                          // every MMA of this tile is complete: H1, H2, ST, DO are free
+            TWT(26)
+            mwait(6);
+            mwait(7);                                          // every MMA of this tile is complete: H1, H2, ST, DO are free
             tc::tc_fence_after();
+            TWT(27)
         }   // tiles
 
         // ================= step tail =================
         // gradients: TMEM -> GR (parameter order; aliases the tile buffers), accumulators handed back zeroed
         __syncthreads();
+        TWT(28)
         {
             float gw[32], z[32];
 #pragma unroll
@@ -660,8 +719,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();
+        TWT(29)
         sync_group<2>();                                   // every GR of the cluster is complete
         tc::tc_fence_after();
+        TWT(30)
 
         // my slice: sum over the row-split CTAs of my half in fixed order, keep the sum in my own GR
         uint32_t peerGR[RS];
@@ -672,23 +733,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
             return (e0 >= oW2 && e0 < ob2) ? (NHP + ((e0 - oW2) >> 6) * GW2LD + ((e0 - oW2) & 63)) >> 2 : i4;
         };
         float sq = 0.f;
-        for (int i4 = i4lo + tid; i4 < i4hi; i4 += TC_THREADS) {
-            const int gs = gslot(i4);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int UB = 4;                               // slice items per batch: all loads of a batch are in flight together
+#pragma unroll 1
+        for (int u0 = 0; u0 < NU; u0 += UB) {
+            float4 part4[UB][RS];
 #pragma unroll
-            for (int k = 0; k < RS; ++k) {
-                const float4 v = (k == rs) ? reinterpret_cast<const float4 *>(GR)[gs] : ld_dsmem4(peerGR[k] + 16u * (uint32_t)gs);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            if (a.grad_only) {
-                const float gv[4] = {acc.x, acc.y, acc.z, acc.w};
+            for (int uu = 0; uu < UB; ++uu) {
+                const int i4 = slice_i4(u0 + uu);
+                const int gs = gslot(i4 < n4 ? i4 : 0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (4 * i4 + u < nH) a.grad_out[(size_t)task * L.n_par + L.to_global(half, 4 * i4 + u)] = gv[u];
+                for (int k = 0; k < RS; ++k)
+                    part4[uu][k] = (k == rs) ? reinterpret_cast<const float4 *>(GR)[gs] : ld_dsmem4(peerGR[k] + 16u * (uint32_t)gs);
             }
-            sq = fmaf(acc.x, acc.x, sq); sq = fmaf(acc.y, acc.y, sq); sq = fmaf(acc.z, acc.z, sq); sq = fmaf(acc.w, acc.w, sq);
-            // the sum replaces my own partial: a slot nobody else reads (peers read only THEIR slices of my GR)
-            reinterpret_cast<float4 *>(GR)[gs] = acc;
+#pragma unroll
+            for (int uu = 0; uu < UB; ++uu) {
+                const int i4 = slice_i4(u0 + uu);
+                if (u0 + uu < NU && i4 < n4) {
+                    float4 acc = part4[uu][0];
+#pragma unroll
+                    for (int k = 1; k < RS; ++k) { acc.x += part4[uu][k].x; acc.y += part4[uu][k].y; acc.z += part4[uu][k].z; acc.w += part4[uu][k].w; }
+                    if (a.grad_only) {
+                        const float gv[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * i4 + e < nH) a.grad_out[(size_t)task * L.n_par + L.to_global(half, 4 * i4 + e)] = gv[e];
+                    }
+                    sq = fmaf(acc.x, acc.x, sq); sq = fmaf(acc.y, acc.y, sq); sq = fmaf(acc.z, acc.z, sq); sq = fmaf(acc.w, acc.w, sq);
+                    // the sum replaces my own partial: a slot nobody else reads (peers read only THEIR slices of my GR)
+                    reinterpret_cast<float4 *>(GR)[gslot(i4)] = acc;
+                }
+            }
         }
         if (a.grad_only) { sync_group<2>(); break; }        // peers' GRs stay valid until they have been read
 
@@ -700,44 +774,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
             for (int k = 0; k < C; ++k)
                 st_dsmem1(mapa_u32(smem_u32(ssq2 + (int)rank * 8 + warp), (uint32_t)k), sq);
         }
+        TWT(31)
         sync_group<2>();
+        TWT(32)
         float tot = 0.f;
 #pragma unroll
         for (int i = 0; i < 8 * C; ++i) tot += ssq2[i];
         const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
         const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
-        for (int i4 = i4lo + tid; i4 < i4hi; i4 += TC_THREADS) {
-            const float4 g4 = reinterpret_cast<const float4 *>(GR)[gslot(i4)];
-            float4 p4 = ld_cg_f4(reinterpret_cast<const float4 *>(PMg) + i4);
-            float4 m4 = ld_cg_f4(reinterpret_cast<const float4 *>(Mg) + i4), v4 = ld_cg_f4(reinterpret_cast<const float4 *>(Vg) + i4);
-#define TW_ADAM(cc)                                                                 \
-            {                                                                       \
-                const float gq = g4.cc * coef;                                      \
-                m4.cc = fmaf(gq - m4.cc, omb1, m4.cc);                              \
-                v4.cc = fmaf(omb2 * gq, gq, v4.cc * b2f);                           \
-                const float denom = fmaf(fast_sqrt(v4.cc), ibc2, aeps);             \
-                p4.cc -= step_size * __fdividef(m4.cc, denom);                      \
+#pragma unroll 1
+        for (int u0 = 0; u0 < NU; u0 += UB) {
+            float4 p4[UB], m4[UB], v4[UB];
+#pragma unroll
+            for (int uu = 0; uu < UB; ++uu) {               // loads first (L2 latency), then the arithmetic
+                const int i4 = slice_i4(u0 + uu);
+                const int ic = i4 < n4 ? i4 : 0;
+                p4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(PMg) + ic);
+                m4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(Mg) + ic);
+                v4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(Vg) + ic);
             }
-            TW_ADAM(x) TW_ADAM(y) TW_ADAM(z) TW_ADAM(w)
+#pragma unroll
+            for (int uu = 0; uu < UB; ++uu) {
+                const int i4 = slice_i4(u0 + uu);
+                if (u0 + uu < NU && i4 < n4) {
+                    const float4 g4 = reinterpret_cast<const float4 *>(GR)[gslot(i4)];
+#define TW_ADAM(cc)                                                                         \
+                    {                                                                       \
+                        const float gq = g4.cc * coef;                                      \
+                        m4[uu].cc = fmaf(gq - m4[uu].cc, omb1, m4[uu].cc);                  \
+                        v4[uu].cc = fmaf(omb2 * gq, gq, v4[uu].cc * b2f);                   \
+                        const float denom = fmaf(fast_sqrt(v4[uu].cc), ibc2, aeps);         \
+                        p4[uu].cc -= step_size * __fdividef(m4[uu].cc, denom);              \
+                    }
+                    TW_ADAM(x) TW_ADAM(y) TW_ADAM(z) TW_ADAM(w)
 #undef TW_ADAM
-            __stcg(reinterpret_cast<float4 *>(PMg) + i4, p4);
-            __stcg(reinterpret_cast<float4 *>(Mg) + i4, m4);
-            __stcg(reinterpret_cast<float4 *>(Vg) + i4, v4);
-            put4(4 * i4, p4);
+                    __stcg(reinterpret_cast<float4 *>(PMg) + i4, p4[uu]);
+                    __stcg(reinterpret_cast<float4 *>(Mg) + i4, m4[uu]);
+                    __stcg(reinterpret_cast<float4 *>(Vg) + i4, v4[uu]);
+                    put4(4 * i4, p4[uu]);
+                }
+            }
         }
         __threadfence();
         tc::fence_async_smem();
         tc::tc_fence_before();
+        TWT(33)
         sync_group<2>();                                    // new weights are visible everywhere; my GR may be overwritten
         tc::tc_fence_after();
+        TWT(34)
     }   // steps
 
     // ---------------- write back ----------------
     if (!a.grad_only) {
-        for (int i4 = i4lo + tid; i4 < i4hi; i4 += TC_THREADS)
+        for (int uq = 0; uq < NU; ++uq)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int e = 4 * i4 + u;
+                const int e = 4 * slice_i4(uq) + u;
                 if (e < nH) {
                     const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
                     a.params[gi] = __ldcg(PMg + e); a.adam_m[gi] = __ldcg(Mg + e); a.adam_v[gi] = __ldcg(Vg + e);

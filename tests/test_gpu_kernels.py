@@ -47,7 +47,9 @@ def make_case(d, P, T, N, seed):
 @pytest.mark.parametrize("name,P,T,N", [("walker", 3, 50, 4), ("hopper3", 2, 33, 2), ("walker", 1, 1, 4),
                                          ("humanoid", 2, 21, 8),
                                          # >= 1024 rows: the tensor-core forward (csrc/k1_tc.cuh), ragged last tile
-                                         ("walker", 2, 301, 4), ("hopper3", 3, 613, 2)])
+                                         ("walker", 2, 301, 4), ("hopper3", 3, 613, 2),
+                                         # Humanoid, >= 1024 rows: the wide tensor-core forward (csrc/k1_tcw.cuh)
+                                         ("humanoid", 2, 150, 8), ("humanoid", 20, 140, 8)])
 @pytest.mark.parametrize("shared_eps", [True, False])
 def test_k1_rollout_matches_oracle(name, P, T, N, shared_eps):
     from pgmorl_b200 import kernels as K
@@ -66,10 +68,10 @@ def test_k1_rollout_matches_oracle(name, P, T, N, shared_eps):
         assert rel_err(logp[p].cpu().numpy().reshape(T, N), ref[p]["logp"]) < 2e-5
 
 
-@pytest.mark.parametrize("T", [40, 300])          # 300 x 4 rows: tensor-core forward
-def test_k1_modes(T):
+@pytest.mark.parametrize("name,T", [("walker", 40), ("walker", 300), ("humanoid", 300)])    # 300 x 4 rows: tensor-core forwards
+def test_k1_modes(name, T):
     from pgmorl_b200 import kernels as K
-    d = DIMS["walker"]
+    d = DIMS[name]
     P, N = 2, 4
     params, traj, eps, _, _, _, ref = make_case(d, P, T, N, seed=5)
     obs = dev(traj["obs"]).reshape(P, (T + 1) * N, d.obs)
