@@ -815,10 +815,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                 }
             }
         }
+        TWT(33)
         __threadfence();
         tc::fence_async_smem();
         tc::tc_fence_before();
-        TWT(33)
+        TWT(35)
         sync_group<2>();                                    // new weights are visible everywhere; my GR may be overwritten
         tc::tc_fence_after();
         TWT(34)

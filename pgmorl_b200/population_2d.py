@@ -10,6 +10,7 @@ import numpy as np
 
 from . import kernels as K
 from .prediction import predict_population
+from .utils import norm2
 
 
 class Population:
@@ -92,7 +93,7 @@ class Population:
             angle = lo + (hi - lo) / (num_weights - 1) * i
             weight = np.array([np.cos(angle), np.sin(angle)])
             if weight[0] >= -1e-7 and weight[1] >= -1e-7:
-                if not any(np.linalg.norm(w - weight) < 1e-3 for w in succ_w):
+                if not any(norm2(w - weight) < 1e-3 for w in succ_w):
                     out.append(weight)
         return out
 

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import kernels as K
 from .prediction import predict_population
-from .utils import generate_weights_batch_dfs
+from .utils import generate_weights_batch_dfs, norm2
 
 
 class Population:
@@ -103,19 +103,21 @@ class Population:
         for s in opt_graph.succ[sample.optgraph_id]:
             w = deepcopy(opt_graph.weights[s])
             succ_w.append(w / np.sum(w))
-        used = lambda weight: any(np.linalg.norm(w - weight) < 1e-3 for w in succ_w)
+        used = lambda weight: any(norm2(w - weight) < 1e-3 for w in succ_w)
         out = []
         if not used(center):
             out.append(center)
         order = np.array([i for i in range(len(grid))])
         np.random.shuffle(order)
+        norm_center = norm2(center)
         for i in range(len(order)):
             if len(out) >= num_weights:
                 break
             weight = grid[order[i]]
-            if np.linalg.norm(weight - center) < 1e-3:
+            if norm2(weight - center) < 1e-3:
                 continue
-            angle = np.arccos(np.clip(np.dot(center, weight) / np.linalg.norm(center) / np.linalg.norm(weight), -1.0, 1.0))
+            cosine = np.dot(center, weight) / norm_center / norm2(weight)
+            angle = np.arccos(min(max(cosine, -1.0), 1.0))
             if angle < np.pi / 4.0 and not used(weight):
                 out.append(weight)
         return out

@@ -8,6 +8,7 @@ launch of K4 (csrc/k4_fit.cu). Predictions are then objs + f(test weight)."""
 import numpy as np
 
 from . import kernels as K
+from .utils import norm2
 
 
 class GraphView:
@@ -39,7 +40,7 @@ def _enough_distinct(weights):
     for i in range(len(weights)):
         distinct = True
         for j in range(i):
-            if np.linalg.norm(weights[i] - weights[j]) < 1e-5:
+            if norm2(weights[i] - weights[j]) < 1e-5:
                 distinct = False
                 break
         if distinct:
@@ -66,7 +67,7 @@ def fit_inputs(view, k, obj_num, cap_threshold):
     coef = np.empty(len(e))
     for r in range(len(e)):                                   # same scalar expressions as population_2d.py:92-95
         diff = np.abs(src[r] - ok)
-        dist = np.linalg.norm(diff / np.abs(ok))
+        dist = norm2(diff / np.abs(ok))
         coef[r] = np.exp(-((dist / sigma) ** 2) / 2.0)
     out = []
     for dim in range(obj_num):

@@ -3,6 +3,8 @@ The arithmetic-heavy ones run in the float64 CUDA kernels of K5 (bit-exact with 
 there is no CPU implementation behind them."""
 from copy import deepcopy
 
+import math
+
 import numpy as np
 
 from . import kernels as K
@@ -79,3 +81,10 @@ def update_ep_and_compute_hypervolume_sparsity(task_id, ep_objs_batch, new_objs,
     """Process entry point of the reference's 3-objective scorer (utils.py:102-106); kept for API parity."""
     new_ep = update_ep(ep_objs_batch, new_objs)
     queue.put([task_id, compute_hypervolume(new_ep), compute_sparsity(new_ep)])
+
+
+def norm2(v):
+    """np.linalg.norm of a real 1-D vector without its Python overhead: the same two operations numpy performs
+    (sqnorm = v.dot(v); sqrt(sqnorm)), hence the same bits -- the selection compares these against thresholds."""
+    v = np.asarray(v)
+    return math.sqrt(v.dot(v))

@@ -39,15 +39,16 @@ tr = pop.workspace[off + off_tr: off + off_tr + n * 8].cpu().numpy().view(np.int
 names = ["idx", "sync+issue loads 0,1"] + [f"G1 block {b}" for b in range(6)] + [
     "wait G1", "E1", "sync+issue G2", "wait G2", "E2", "sync+issue G3", "wait G3", "E3", "sync+issue G4,GWh", "wait G4", "E4+db2",
     "sync+issue G5,GW2", "wait G5", "wait GW2", "E5+x0 load+sync", "issue G1X 0,1", "wait G1X 0", "load x4,x5+sync", "issue G1X 2",
-    "wait G1X", "tail sync", "TMEM->GR", "cluster bar 1", "slice reduce+ssq", "cluster bar 2", "Adam+publish", "cluster bar 3"]
+    "wait G1X", "tail sync", "TMEM->GR", "cluster bar 1", "slice reduce+ssq", "cluster bar 2", "Adam+publish", "cluster bar 3", "release fence"]
 for cta in range(NC):
     c = tr[cta, 1, :35].astype(np.int64)
     ntile_marks = c[0] != 0
     print(f"cta {cta} ({'actor' if cta < NC // 2 else 'critic'}): step = {int(tr[cta, 1, 34] - tr[cta, 0, 34])} cycles"
           + ("" if ntile_marks else " (no tile)"))
     prev = tr[cta, 0, 34]
-    for i in range(35):
-        if c[i] == 0:
+    for i in list(range(34)) + [35, 34]:          # mark 35 (after the release fence) sits between 33 and 34
+        v = tr[cta, 1, i]
+        if v == 0:
             continue
-        print(f"    {names[i]:>24s} {int(c[i] - prev):7d}")
-        prev = c[i]
+        print(f"    {names[i]:>24s} {int(v - prev):7d}")
+        prev = v
