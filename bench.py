@@ -208,6 +208,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: NCCL's version banner / debug output (printed to stdout when the box sets
+    # NCCL_DEBUG) goes to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     S = T * N
     metric = "MOPG env-steps/sec (rollout infer + GAE + PPO update)"
     workload = {"workload": f"{env}-shape population MOPG update: {P} tasks/GPU x {N} envs x {T} steps, "

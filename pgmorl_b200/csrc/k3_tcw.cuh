@@ -734,6 +734,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
         };
         float sq = 0.f;
         constexpr int UB = 4;                               // slice items per batch: all loads of a batch are in flight together
+        constexpr int NBATCH = (NU + UB - 1) / UB;
+        // master / moment loads are software-pipelined one batch ahead; the first batch is issued here, before the gradient
+        // reduction and the norm barrier, so its L2 round trip is hidden completely
+        float4 pA[UB], mA[UB], vA[UB], pB[UB], mB[UB], vB[UB];
+        auto ld_batch = [&](int u0, float4 *p4, float4 *m4, float4 *v4) {
+#pragma unroll
+            for (int uu = 0; uu < UB; ++uu) {
+                const int i4 = slice_i4(u0 + uu);
+                const int ic = (u0 + uu < NU && i4 < n4) ? i4 : 0;
+                p4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(PMg) + ic);
+                m4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(Mg) + ic);
+                v4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(Vg) + ic);
+            }
+        };
+        if (!a.grad_only) ld_batch(0, pA, mA, vA);
 #pragma unroll 1
         for (int u0 = 0; u0 < NU; u0 += UB) {
             float4 part4[UB][RS];
@@ -782,17 +797,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
         for (int i = 0; i < 8 * C; ++i) tot += ssq2[i];
         const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
         const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
-#pragma unroll 1
-        for (int u0 = 0; u0 < NU; u0 += UB) {
-            float4 p4[UB], m4[UB], v4[UB];
-#pragma unroll
-            for (int uu = 0; uu < UB; ++uu) {               // loads first (L2 latency), then the arithmetic
-                const int i4 = slice_i4(u0 + uu);
-                const int ic = i4 < n4 ? i4 : 0;
-                p4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(PMg) + ic);
-                m4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(Mg) + ic);
-                v4[uu] = ld_cg_f4(reinterpret_cast<const float4 *>(Vg) + ic);
-            }
+        auto adam_batch = [&](int u0, float4 *p4, float4 *m4, float4 *v4) {
 #pragma unroll
             for (int uu = 0; uu < UB; ++uu) {
                 const int i4 = slice_i4(u0 + uu);
@@ -814,6 +819,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
                     put4(4 * i4, p4[uu]);
                 }
             }
+        };
+#pragma unroll 1
+        for (int b = 0; b < NBATCH; b += 2) {               // two batches per trip: buffers A and B alternate statically
+            if (b + 1 < NBATCH) ld_batch((b + 1) * UB, pB, mB, vB);
+            adam_batch(b * UB, pA, mA, vA);
+            if (b + 2 < NBATCH) ld_batch((b + 2) * UB, pA, mA, vA);
+            if (b + 1 < NBATCH) adam_batch((b + 1) * UB, pB, mB, vB);
         }
         TWT(33)
         __threadfence();
