@@ -36,6 +36,7 @@ CONFIGS = {
     "walker1024": ("walker2d", 1024, 2048, 4, 10, 32, 0.995),
     "hopper3": ("hopper3", 15, 2048, 4, 10, 32, 0.995),
     "humanoid8": ("humanoid", 8, 2048, 8, 10, 32, 0.99),     # BASELINE.json configs[3] shape: 64 tasks over 8 GPUs
+    "humanoid16": ("humanoid", 16, 2048, 8, 10, 32, 0.99),   # ... over 4 GPUs
     "humanoid32": ("humanoid", 32, 2048, 8, 10, 32, 0.99),   # ... over 2 GPUs
 }
 GEN_ITERS = 20           # update_iter of the reference's launch scripts (scripts/walker2d-v2.py:40)

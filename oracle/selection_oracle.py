@@ -528,3 +528,47 @@ def jacobi_svd(A, sweeps=60):
     s = s[order]; A = A[:, order]; V = V[:, order]
     U = np.where(s > 0, A / np.where(s > 0, s, 1.0), 0.0)
     return U, s, V.T
+
+
+def qr_jacobi_svd(A, sweeps=60):
+    """The SVD of the CUDA port (csrc/k4_fit.cu::qr_jacobi_svd): Householder QR of the tall augmented Jacobian,
+    then a one-sided Jacobi SVD of the 4 x 4 triangular factor with round-robin pair order
+    (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2). Returns (U, s, Vt), s sorted in descending order like LAPACK.
+    Same role as LAPACK's gesdd inside scipy's trf (trf.py:312-318); not bit-identical to it."""
+    A = np.array(A, dtype=np.float64)
+    m, n = A.shape
+    assert n == 4
+    Q = np.eye(m)
+    for j in range(n):
+        x = A[j:, j]
+        nx = np.sqrt(x @ x)
+        if nx == 0.0:
+            continue
+        v = x.copy()
+        v[0] -= -np.copysign(nx, x[0])
+        beta = 1.0 / (nx * (nx + abs(x[0])))
+        A[j:, j:] -= np.outer(v, beta * (v @ A[j:, j:]))
+        Q[:, j:] -= np.outer(Q[:, j:] @ v, beta * v)
+    B = np.triu(A[:n, :n])
+    V = np.eye(n)
+    for _ in range(sweeps):
+        rotated = False
+        for p, q in ((0, 1), (2, 3), (0, 2), (1, 3), (0, 3), (1, 2)):
+            al, be, ga = B[:, p] @ B[:, p], B[:, q] @ B[:, q], B[:, p] @ B[:, q]
+            if ga == 0.0 or abs(ga) <= 1e-16 * np.sqrt(al * be):
+                continue
+            rotated = True
+            d, h = be - al, 2.0 * ga
+            t = np.copysign(1.0, d) * h / (abs(d) + np.sqrt(d * d + h * h))
+            c = 1.0 / np.sqrt(1.0 + t * t); sn = c * t
+            bp, bq = B[:, p].copy(), B[:, q].copy()
+            B[:, p], B[:, q] = c * bp - sn * bq, sn * bp + c * bq
+            vp, vq = V[:, p].copy(), V[:, q].copy()
+            V[:, p], V[:, q] = c * vp - sn * vq, sn * vp + c * vq
+        if not rotated:
+            break
+    s = np.sqrt((B * B).sum(0))
+    order = np.argsort(-s, kind="stable")
+    s = s[order]; B = B[:, order]; V = V[:, order]
+    UR = np.where(s > 0, B / np.where(s > 0, s, 1.0), 0.0)
+    return Q[:, :n] @ UR, s, V.T

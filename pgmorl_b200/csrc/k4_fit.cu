@@ -7,7 +7,8 @@
 // (scipy/optimize/_lsq/least_squares.py:900-1030, trf.py:129-412, common.py). The port follows the
 // numpy restatement in oracle/selection_oracle.py::trf_fit (which reproduces scipy bit for bit with
 // LAPACK's SVD) line by line; the one substitution is the SVD of the (K+4) x 4 augmented Jacobian:
-// a one-sided Jacobi (Hestenes) SVD, accurate to ~1e-16 relative but not bit-identical to gesdd.
+// Householder QR, then a one-sided Jacobi (Hestenes) SVD of the 4 x 4 triangular factor in registers
+// (oracle/selection_oracle.py::qr_jacobi_svd), accurate to ~1e-16 relative but not bit-identical to gesdd.
 //
 //   model     f(x) = A (e^{a(x-b)} - 1) / (e^{a(x-b)} + 1) + c,   residual_i = (f(x_i) - y_i) w_i
 //   per fit   K weighted points (x, y, w), upper bounds ub[4]; start ones(4); max_nfev = 400
@@ -31,7 +32,7 @@ __device__ __forceinline__ bool wall(bool p) { return __all_sync(0xffffffffu, p)
 
 struct Fit {
     const double *x, *y, *w;   // global [K]
-    double *f, *J, *A, *fn;    // shared: f[K], J[K][4], A[K+4][4], fn[K]
+    double *f, *J, *A, *fn;    // shared: f[K], J[K][4], A[K+4][4], fn[K+4]
     int K, lane;
     double lb[4], ub[4];
 };
@@ -177,9 +178,87 @@ __device__ inline void min_quad1d(double a, double b, double lo, double hi, doub
     t_out = tb; y_out = yb;
 }
 
-// One-sided Jacobi SVD of A [(K+4) x 4] in smem: on exit columns of A are u_i * s_i; V accumulates rotations.
-__device__ inline void jacobi_svd(const Fit &q, double V[4][4], double s[4]) {
+// all-reduce of four values at once (the butterflies interleave, one latency instead of four)
+__device__ __forceinline__ void wsum4(double &a, double &b, double &c, double &d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+        const double tc = __shfl_xor_sync(0xffffffffu, c, o), td = __shfl_xor_sync(0xffffffffu, d, o);
+        a += ta; b += tb; c += tc; d += td;
+    }
+}
+
+// Jacobi rotation that orthogonalises two columns with squared norms al, be and inner product ga
+// (identity when they already are orthogonal to 1e-16); returns whether it rotated.
+__device__ __forceinline__ bool jacobi_angle(double al, double be, double ga, double &cs, double &sn) {
+    cs = 1.0; sn = 0.0;
+    if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) return false;
+    // tan of the rotation angle, t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (be - al) / (2 ga),
+    // written with one square root and one division: t = sign(d) h / (|d| + sqrt(d^2 + h^2)), d = be - al, h = 2 ga
+    const double d = be - al, h = 2.0 * ga;
+    const double t = copysign(1.0, d) * h / (fabs(d) + sqrt(d * d + h * h));
+    cs = rsqrt(1.0 + t * t);
+    sn = cs * t;
+    return true;
+}
+
+// SVD of the augmented Jacobian A [(K+4) x 4] (rows across lanes, in smem) and uf = U^T f_aug, the two things
+// trf.py:312-318 takes from numpy's svd. Like LAPACK's driver for tall matrices it first reduces A to its 4 x 4
+// triangular factor: Householder QR with f_aug (q.fn, overwritten) carried as a fifth column, R and (Q^T f)[:4]
+// replicated in every lane; then a one-sided Jacobi SVD of R entirely in registers (no shuffles), the two
+// independent rotations of each round-robin round side by side. Singular values are left unsorted.
+__device__ inline void qr_jacobi_svd(const Fit &q, double V[4][4], double s[4], double uf[4]) {
     const int rows = q.K + 4;
+    double B[4][4], qtf[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double n2 = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
+        for (int r = q.lane; r < rows; r += 32)
+            if (r >= j) { const double a = q.A[4 * r + j]; n2 += a * a; }
+        n2 = wsum(n2);
+        const double x0 = q.A[4 * j + j];
+        double rowj[4], fj = q.fn[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rowj[c] = q.A[4 * j + c];
+        __syncwarp();
+        const double nx = sqrt(n2);
+        if (nx == 0.0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) B[j][c] = (c < j) ? 0.0 : rowj[c];
+            qtf[j] = fj;
+            continue;
+        }
+        const double alpha = -copysign(nx, x0), v0 = x0 - alpha;
+        const double beta = 1.0 / (nx * (nx + fabs(x0)));          // 2 / (v.v)
+        // w_c = beta * v . A[:, c] for the columns right of j and for f
+        double df = 0.0;
+        for (int r = q.lane; r < rows; r += 32)
+            if (r >= j) {
+                const double vr = (r == j) ? v0 : q.A[4 * r + j];
+                if (j < 3) e0 += vr * q.A[4 * r + (j + 1 < 4 ? j + 1 : 3)];
+                if (j < 2) e1 += vr * q.A[4 * r + (j + 2 < 4 ? j + 2 : 3)];
+                if (j < 1) e2 += vr * q.A[4 * r + 3];
+                df += vr * q.fn[r];
+            }
+        wsum4(e0, e1, e2, df);
+        e0 *= beta; e1 *= beta; e2 *= beta; df *= beta;
+        for (int r = q.lane; r < rows; r += 32)
+            if (r > j) {
+                const double vr = q.A[4 * r + j];
+                if (j < 3) q.A[4 * r + (j + 1 < 4 ? j + 1 : 3)] -= vr * e0;
+                if (j < 2) q.A[4 * r + (j + 2 < 4 ? j + 2 : 3)] -= vr * e1;
+                if (j < 1) q.A[4 * r + 3] -= vr * e2;
+                q.fn[r] -= vr * df;
+            }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) B[j][c] = (c < j) ? 0.0 : rowj[c];
+        B[j][j] = alpha;
+        if (j < 3) B[j][j + 1 < 4 ? j + 1 : 3] = rowj[j + 1 < 4 ? j + 1 : 3] - v0 * e0;
+        if (j < 2) B[j][j + 2 < 4 ? j + 2 : 3] = rowj[j + 2 < 4 ? j + 2 : 3] - v0 * e1;
+        if (j < 1) B[j][3] = rowj[3] - v0 * e2;
+        qtf[j] = fj - v0 * df;
+        __syncwarp();
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -187,40 +266,43 @@ __device__ inline void jacobi_svd(const Fit &q, double V[4][4], double s[4]) {
     for (int sweep = 0; sweep < 60; ++sweep) {
         bool rotated = false;
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
+        for (int rnd = 0; rnd < 3; ++rnd) {
+            // round-robin pairs: (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2)
+            const int p0 = 0, c0 = rnd + 1;
+            const int p1 = (rnd == 0) ? 2 : 1, c1 = (rnd == 2) ? 2 : 3;
+            double al0 = 0.0, be0 = 0.0, ga0 = 0.0, al1 = 0.0, be1 = 0.0, ga1 = 0.0;
 #pragma unroll
-            for (int c = p + 1; c < 4; ++c) {
-                double al = 0.0, be = 0.0, ga = 0.0;
-                for (int r = q.lane; r < rows; r += 32) {
-                    const double ap = q.A[4 * r + p], aq = q.A[4 * r + c];
-                    al += ap * ap; be += aq * aq; ga += ap * aq;
-                }
-                al = wsum(al); be = wsum(be); ga = wsum(ga);
-                if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
-                rotated = true;
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                for (int r = q.lane; r < rows; r += 32) {
-                    const double ap = q.A[4 * r + p], aq = q.A[4 * r + c];
-                    q.A[4 * r + p] = cs * ap - sn * aq;
-                    q.A[4 * r + c] = sn * ap + cs * aq;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double vp = V[i][p], vq = V[i][c];
-                    V[i][p] = cs * vp - sn * vq;
-                    V[i][c] = sn * vp + cs * vq;
-                }
-                __syncwarp();
+            for (int i = 0; i < 4; ++i) {
+                al0 += B[i][p0] * B[i][p0]; be0 += B[i][c0] * B[i][c0]; ga0 += B[i][p0] * B[i][c0];
+                al1 += B[i][p1] * B[i][p1]; be1 += B[i][c1] * B[i][c1]; ga1 += B[i][p1] * B[i][c1];
             }
+            double cs0, sn0, cs1, sn1;
+            const bool r0 = jacobi_angle(al0, be0, ga0, cs0, sn0);
+            const bool r1 = jacobi_angle(al1, be1, ga1, cs1, sn1);
+            rotated = rotated || r0 || r1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (r0) {
+                    const double bp = B[i][p0], bq = B[i][c0], vp = V[i][p0], vq = V[i][c0];
+                    B[i][p0] = cs0 * bp - sn0 * bq; B[i][c0] = sn0 * bp + cs0 * bq;
+                    V[i][p0] = cs0 * vp - sn0 * vq; V[i][c0] = sn0 * vp + cs0 * vq;
+                }
+                if (r1) {
+                    const double bp = B[i][p1], bq = B[i][c1], vp = V[i][p1], vq = V[i][c1];
+                    B[i][p1] = cs1 * bp - sn1 * bq; B[i][c1] = sn1 * bp + cs1 * bq;
+                    V[i][p1] = cs1 * vp - sn1 * vq; V[i][c1] = sn1 * vp + cs1 * vq;
+                }
+            }
+        }
         if (!rotated) break;
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        double a = 0.0;
-        for (int r = q.lane; r < rows; r += 32) a += q.A[4 * r + c] * q.A[4 * r + c];
-        s[c] = sqrt(wsum(a));
+        double n2 = 0.0, a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { n2 += B[i][c] * B[i][c]; a += B[i][c] * qtf[i]; }
+        s[c] = sqrt(n2);
+        uf[c] = s[c] > 0.0 ? a / s[c] : 0.0;
     }
 }
 
@@ -371,7 +453,7 @@ __global__ void __launch_bounds__(32 * K4_WARPS) k4_fit_kernel(const double *__r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fit = blockIdx.x * K4_WARPS + warp;
     if (fit >= F) return;
-    const int per = 10 * Kmax + 16;
+    const int per = 10 * Kmax + 20;
     Fit q;
     q.lane = lane; q.K = klen[fit];
     q.x = gx + (size_t)fit * Kmax; q.y = gy + (size_t)fit * Kmax; q.w = gw + (size_t)fit * Kmax;
@@ -424,15 +506,10 @@ __global__ void __launch_bounds__(32 * K4_WARPS) k4_fit_kernel(const double *__r
             for (int c = 0; c < 4; ++c) q.A[4 * (m + lane) + c] = (c == lane) ? sqrt(diag[lane]) : 0.0;
         }
         __syncwarp();
+        for (int r = lane; r < m + 4; r += 32) q.fn[r] = (r < m) ? q.f[r] : 0.0;     // f_augmented
+        __syncwarp();
         double V[4][4], s[4], uf[4];
-        jacobi_svd(q, V, s);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            double a = 0.0;
-            for (int r = lane; r < m; r += 32) a += q.A[4 * r + c] * q.f[r];     // f_augmented tail is zero
-            a = wsum(a);
-            uf[c] = s[c] > 0.0 ? a / s[c] : 0.0;
-        }
+        qr_jacobi_svd(q, V, s, uf);
         const double theta_sb = fmax(0.995, 1.0 - g_norm);
         double actual = -1.0, cost_new = cost, xn[4];
         while (actual <= 0.0 && nfev < max_nfev) {
@@ -495,7 +572,7 @@ extern "C" int pgm_fit_hyperbolic_f64(const double *x, const double *y, const do
     PGM_REQUIRE(x && y && w && k_len && ub && theta && status && nfev && cost, "pgm_fit_hyperbolic_f64: null pointer");
     PGM_REQUIRE(F >= 0 && Kmax >= 1, "pgm_fit_hyperbolic_f64: bad sizes F=%d Kmax=%d", F, Kmax);
     if (F == 0) return PGM_OK;
-    const size_t smem = (size_t)K4_WARPS * (10 * (size_t)Kmax + 16) * sizeof(double);
+    const size_t smem = (size_t)K4_WARPS * (10 * (size_t)Kmax + 20) * sizeof(double);
     PGM_REQUIRE(smem <= 200 * 1024, "pgm_fit_hyperbolic_f64: Kmax=%d exceeds the shared-memory budget (max 620 points per fit)", Kmax);
     PGM_CUDA(cudaFuncSetAttribute(k4_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k4_fit_kernel<<<(F + K4_WARPS - 1) / K4_WARPS, 32 * K4_WARPS, smem, (cudaStream_t)stream>>>(
