@@ -209,9 +209,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly ONE JSON line: NCCL's version banner / debug output (printed to stdout when the box sets
-    # NCCL_DEBUG) goes to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line: whatever native libraries write to file descriptor 1 (NCCL prints its version
+    # banner / debug output there) is sent to stderr, and the JSON line goes to a private duplicate of the real stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     S = T * N
     metric = "MOPG env-steps/sec (rollout infer + GAE + PPO update)"
     workload = {"workload": f"{env}-shape population MOPG update: {P} tasks/GPU x {N} envs x {T} steps, "
@@ -234,7 +236,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
                 "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return 0
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -409,7 +412,8 @@ def main():
                 line["cpu_baseline"]["ms_per_step"] = ref["ms_per_step"]
             except Exception as ex:   # keep the GPU numbers even if the CPU leg fails
                 line["cpu_baseline"] = {"error": repr(ex)[:200]}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -199,13 +199,13 @@ def select_greedy(ep, cand, alpha, num_tasks):
 # ---------------------------------------------------------------------------------------------
 # K4: batched hyperbolic-model fits (float64)
 # ---------------------------------------------------------------------------------------------
-def fit_hyperbolic(xs, ys, ws, ubs):
-    """Fit F models at once. xs/ys/ws: lists of 1-D arrays (ragged, K_f points each); ubs [F,4].
-    Returns (theta [F,4], status [F], nfev [F], cost [F]) as numpy arrays."""
+def fit_hyperbolic_launch(xs, ys, ws, ubs):
+    """Upload F ragged fit problems and launch K4 on the current stream WITHOUT waiting for it; the returned
+    handle goes to `fit_hyperbolic_collect`. Host work that does not need the fits can run in between."""
     import numpy as np
     F = len(xs)
     if F == 0:
-        return np.zeros((0, 4)), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+        return None
     klen = np.array([len(v) for v in xs], dtype=np.int32)
     Kmax = max(int(klen.max()), 1)
     pack = np.zeros((3, F, Kmax), dtype=np.float64)
@@ -222,4 +222,19 @@ def fit_hyperbolic(xs, ys, ws, ubs):
     cost = torch.empty(F, dtype=torch.float64, device=dev)
     check(lib().pgm_fit_hyperbolic_f64(ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(kl), ptr(ub), ptr(theta), ptr(status),
                                        ptr(nfev), ptr(cost), F, Kmax, _stream()))
-    return theta.cpu().numpy(), status.cpu().numpy().astype(np.int64), nfev.cpu().numpy().astype(np.int64), cost.cpu().numpy()
+    return dict(inputs=(d, kl, ub), theta=theta, status=status, nfev=nfev, cost=cost)     # inputs kept alive until collect
+
+
+def fit_hyperbolic_collect(handle):
+    """Wait for a `fit_hyperbolic_launch` and return (theta [F,4], status [F], nfev [F], cost [F]) as numpy arrays."""
+    import numpy as np
+    if handle is None:
+        return np.zeros((0, 4)), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+    return (handle["theta"].cpu().numpy(), handle["status"].cpu().numpy().astype(np.int64),
+            handle["nfev"].cpu().numpy().astype(np.int64), handle["cost"].cpu().numpy())
+
+
+def fit_hyperbolic(xs, ys, ws, ubs):
+    """Fit F models at once. xs/ys/ws: lists of 1-D arrays (ragged, K_f points each); ubs [F,4].
+    Returns (theta [F,4], status [F], nfev [F], cost [F]) as numpy arrays."""
+    return fit_hyperbolic_collect(fit_hyperbolic_launch(xs, ys, ws, ubs))

@@ -9,7 +9,7 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import predict_population
+from .prediction import finish_predictions, launch_fits
 from .utils import norm2
 
 
@@ -101,13 +101,12 @@ class Population:
         """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_2d.py:229-304)."""
         N = args.num_tasks
         # ---- prediction: candidates = (sample, weight) pairs with their predicted objectives
-        samples, tests = [], []
-        for sample in self.sample_batch:
-            tw = self._test_weights(opt_graph, sample, args.num_weight_candidates)
-            if len(tw) > 0:
-                samples.append(sample); tests.append(tw)
-        preds, self.last_fits = predict_population(opt_graph, [s.optgraph_id for s in samples], tests, args.obj_num,
-                                                   cap_threshold=False)
+        # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
+        pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=False)
+        all_tests = [self._test_weights(opt_graph, sample, args.num_weight_candidates) for sample in self.sample_batch]
+        samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
+        tests = [tw for tw in all_tests if len(tw) > 0]
+        preds, self.last_fits = finish_predictions(pending, all_tests)
         candidates = []
         for sample, tw, pr in zip(samples, tests, preds):
             for w, p in zip(tw, pr):

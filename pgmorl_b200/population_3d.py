@@ -9,7 +9,7 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import predict_population
+from .prediction import finish_predictions, launch_fits
 from .utils import generate_weights_batch_dfs, norm2
 
 
@@ -125,17 +125,16 @@ class Population:
     def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
         """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_3d.py:239-333)."""
         N = args.num_tasks
-        samples, tests = [], []
         # the reference rebuilds this simplex grid for every sample (population_3d.py:262-263); it is a pure function of the
         # arguments (no RNG), so it is enumerated once
         grid = []
         generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
-        for sample in self.sample_batch:
-            tw = self._test_weights(args, opt_graph, sample, grid)
-            if len(tw) > 0:
-                samples.append(sample); tests.append(tw)
-        preds, self.last_fits = predict_population(opt_graph, [s.optgraph_id for s in samples], tests, args.obj_num,
-                                                   cap_threshold=True)
+        # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
+        pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=True)
+        all_tests = [self._test_weights(args, opt_graph, sample, grid) for sample in self.sample_batch]
+        samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
+        tests = [tw for tw in all_tests if len(tw) > 0]
+        preds, self.last_fits = finish_predictions(pending, all_tests)
         candidates = []
         for sample, tw, pr in zip(samples, tests, preds):
             for w, p in zip(tw, pr):

@@ -55,20 +55,29 @@ def fit_inputs(view, k, obj_num, cap_threshold):
     3-objective variant's stop at threshold >= 1 (population_3d.py:46); the 2-objective one widens until
     more than 3 distinct weights are found (population_2d.py:50)."""
     threshold, sigma = 0.1, 0.03
+    ok = view.objs[k]
+    aok = np.abs(ok)
+    rel = np.abs(ok - view.objs)                              # |objs_k - objs_i| for every node i, reused by each widening
     while True:
-        e = view.nearest_edges(k, threshold)
+        near = np.all(rel < aok * threshold, axis=1)
+        e = np.nonzero(near[view.parent])[0] if len(view.parent) else np.zeros(0, dtype=np.int64)
         wd = view.edge_w[e]
         if _enough_distinct(wd) or (cap_threshold and threshold >= 1.0):
             break
+        if not np.isfinite(threshold):          # the reference would widen forever here (fewer than 4 distinct weights
+            break                               # in the whole graph); fits are launched for every sample, so stop instead
         threshold *= 2.0
         sigma *= 2.0
-    ok = view.objs[k]
-    src = view.objs[view.parent[e]]
+    q = rel / aok                                             # same element-wise operations as population_2d.py:92-93
     coef = np.empty(len(e))
-    for r in range(len(e)):                                   # same scalar expressions as population_2d.py:92-95
-        diff = np.abs(src[r] - ok)
-        dist = norm2(diff / np.abs(ok))
-        coef[r] = np.exp(-((dist / sigma) ** 2) / 2.0)
+    node_coef = {}
+    for r in range(len(e)):                                   # one Gaussian weight per source node, shared by its edges
+        i = view.parent[e[r]]
+        c = node_coef.get(i)
+        if c is None:
+            dist = norm2(q[i])
+            c = node_coef[i] = np.exp(-((dist / sigma) ** 2) / 2.0)
+        coef[r] = c
     out = []
     for dim in range(obj_num):
         x = wd[:, dim].copy()
@@ -82,21 +91,40 @@ def model(x, A, a, b, c):
     return A * (np.exp(a * (x - b)) - 1) / (np.exp(a * (x - b)) + 1) + c
 
 
-def predict_population(opt_graph, node_ids, test_weights_per_node, obj_num, cap_threshold):
-    """For every node: predicted objectives objs + delta(test weight) for each of its test weights.
-    test_weights_per_node[i] is an array [n_i, M] (any positive scaling; normalised to sum 1 here, as
-    population_2d.py:28-32). Returns (list of [n_i, M] prediction arrays, fit record dict)."""
+def launch_fits(opt_graph, node_ids, obj_num, cap_threshold):
+    """Build the training data of every node's model and launch all n x M fits (K4) without waiting for them.
+    Returns a handle for `finish_predictions`; the caller may do host work that does not need the fits meanwhile."""
     view = GraphView(opt_graph)
     xs, ys, ws, ubs = [], [], [], []
     for k in node_ids:
         for x, y, w, ub in fit_inputs(view, k, obj_num, cap_threshold):
             xs.append(x); ys.append(y); ws.append(w); ubs.append(ub)
-    theta, status, nfev, cost = K.fit_hyperbolic(xs, ys, ws, ubs)        # all n_pop * M fits in one launch
-    preds = []
-    for i, k in enumerate(node_ids):
+    return dict(view=view, node_ids=list(node_ids), obj_num=obj_num, x=xs, y=ys, w=ws, ub=ubs,
+                fits=K.fit_hyperbolic_launch(xs, ys, ws, ubs))                    # all fits in one launch
+
+
+def finish_predictions(handle, test_weights_per_node):
+    """Second half of `predict_population`. test_weights_per_node[i] is an array [n_i, M] for node_ids[i] (any
+    positive scaling; normalised to sum 1 here, as population_2d.py:28-32) or None / empty: that node then
+    contributes neither predictions nor fit records (the reference never fits a sample without test weights)."""
+    theta, status, nfev, cost = K.fit_hyperbolic_collect(handle["fits"])
+    view, M = handle["view"], handle["obj_num"]
+    preds, keep = [], []
+    for i, k in enumerate(handle["node_ids"]):
+        if test_weights_per_node[i] is None or len(test_weights_per_node[i]) == 0:
+            continue
+        keep.extend(range(i * M, (i + 1) * M))
         tw = np.array(test_weights_per_node[i], dtype=np.float64)
         for row in tw:
             row /= np.sum(row)
-        delta = np.transpose(np.array([model(tw.T[dim], *theta[i * obj_num + dim]) for dim in range(obj_num)]))
+        delta = np.transpose(np.array([model(tw.T[dim], *theta[i * M + dim]) for dim in range(M)]))
         preds.append(np.array([view.objs[k] + delta[j] for j in range(len(tw))]))
-    return preds, dict(x=xs, y=ys, w=ws, ub=ubs, theta=theta, status=status, nfev=nfev, cost=cost)
+    pick = lambda seq: [seq[j] for j in keep]
+    return preds, dict(x=pick(handle["x"]), y=pick(handle["y"]), w=pick(handle["w"]), ub=pick(handle["ub"]),
+                       theta=theta[keep], status=status[keep], nfev=nfev[keep], cost=cost[keep])
+
+
+def predict_population(opt_graph, node_ids, test_weights_per_node, obj_num, cap_threshold):
+    """For every node: predicted objectives objs + delta(test weight) for each of its test weights.
+    Returns (list of [n_i, M] prediction arrays, fit record dict)."""
+    return finish_predictions(launch_fits(opt_graph, node_ids, obj_num, cap_threshold), test_weights_per_node)
