@@ -180,6 +180,39 @@ def selection_leg(cpu=True):
                 out[key]["cpu_ms_per_generation"] = 1e3 * (t_fit + t_sel)
                 out[key]["cpu_sample"] = ("scipy least_squares on every fit + python scoring, 1 core"
                                           + ("" if M == 2 else "; scoring timed on 1 of 15 greedy rounds and scaled"))
+        # full performance buffers (n_pop 200 / 1 400 candidates / archive 300 and
+        # n_pop 420 / 2 940 candidates / archive 500), built directly by synthetic.make_selection_state
+        from pgmorl_b200.synthetic import make_selection_state
+        for M, n_pop, n_ep in ((2, 200, 300), (3, 420, 500)):
+            times = []
+            for rep in range(3):
+                args_s, graph, pop, ep = make_selection_state(M, n_pop, n_ep, seed=3)
+                np.random.seed(7)
+                template = WeightedSumScalarization(num_objs=M, weights=np.ones(M) / M)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                pop.prediction_guided_selection(args_s, 0, ep, graph, template)
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            key = f"{M}d_full"
+            out[key] = {"ms_per_generation": 1e3 * min(times[1:]), "n_pop": n_pop, "candidates": len(pop.last_candidates),
+                        "fits": len(pop.last_fits["x"]), "archive": n_ep, "tasks": args_s.num_tasks}
+            if cpu:
+                from oracle import selection_oracle as so
+                f = pop.last_fits
+                sub = range(0, len(f["x"]), 8)                       # every 8th fit, scaled
+                t0 = time.perf_counter()
+                for i in sub:
+                    so.fit_scipy(f["x"][i], f["y"][i], f["w"][i], f["ub"][i])
+                t_fit = (time.perf_counter() - t0) * len(f["x"]) / len(sub)
+                cand = np.array([c["prediction"] for c in pop.last_candidates])
+                csub = cand[:: max(1, len(cand) // 40)]              # ~40 candidates of one greedy round, scaled
+                t0 = time.perf_counter()
+                (so.greedy_select_2d if M == 2 else so.greedy_select_3d)(ep.obj_batch, csub, args_s.sparsity, 1)
+                t_sel = (time.perf_counter() - t0) * len(cand) / len(csub) * args_s.num_tasks
+                out[key]["cpu_ms_per_generation"] = 1e3 * (t_fit + t_sel)
+                out[key]["cpu_sample"] = ("scipy least_squares on every 8th fit and python scoring of ~40 candidates of one "
+                                          "greedy round, both scaled to the full counts, 1 core")
     finally:
         torch.set_default_dtype(torch.float32)
     return out

@@ -19,7 +19,7 @@
 
 namespace pgm {
 
-constexpr int K4_WARPS = 4;
+constexpr int K4_WARPS = 1;          // one fit per CTA: a slow fit (400 evaluations) does not pin the warp slots of finished neighbours
 constexpr double K4_EPS = 2.220446049250313e-16;
 constexpr double K4_FSCALE = 20.0;
 

@@ -92,10 +92,13 @@ class Population:
         return self.evaluate_hypervolume_sparsity(candidates, mask, virtual_ep_objs_batch)[1]
 
     # ------------------------------------------------------------------ selection
-    def _test_weights(self, args, opt_graph, sample, grid):
+    def _test_weights(self, args, opt_graph, sample, grid, grid_arr=None, grid_norm=None):
         """Centre weight + randomly ordered simplex-grid weights within 45 degrees of it, up to
         num_weight_candidates, skipping weights an existing successor already used (population_3d.py:248-284).
-        Consumes numpy's global RNG exactly like the reference (np.random.shuffle)."""
+        Consumes numpy's global RNG exactly like the reference (np.random.shuffle).
+        `grid_arr` / `grid_norm` (the grid as one array and its row norms) only save work: a weight whose largest
+        coordinate difference from a vector exceeds 1e-3 cannot be within 1e-3 of it in L2 norm, so the exact test
+        (same expression as the reference) runs only for the others; decisions are unchanged."""
         num_weights = args.num_weight_candidates
         center = opt_graph.weights[sample.optgraph_id]
         center = center / np.sum(center)
@@ -103,22 +106,30 @@ class Population:
         for s in opt_graph.succ[sample.optgraph_id]:
             w = deepcopy(opt_graph.weights[s])
             succ_w.append(w / np.sum(w))
-        used = lambda weight: any(norm2(w - weight) < 1e-3 for w in succ_w)
+        if grid_arr is None:
+            grid_arr = np.array(grid, dtype=np.float64)
+            grid_norm = [norm2(w) for w in grid]
+        close_to_center = (np.abs(grid_arr - center).max(axis=1) <= 1.0e-3).tolist()
+        close_to_succ = [(np.abs(grid_arr - w).max(axis=1) <= 1.0e-3).tolist() for w in succ_w]
+        used_exact = lambda weight: any(norm2(w - weight) < 1e-3 for w in succ_w)
         out = []
-        if not used(center):
+        if not used_exact(center):
             out.append(center)
-        order = np.array([i for i in range(len(grid))])
+        order = np.arange(len(grid))                  # same dtype and length as the reference's list-built array
         np.random.shuffle(order)
         norm_center = norm2(center)
-        for i in range(len(order)):
+        quarter = np.pi / 4.0
+        for i in order.tolist():
             if len(out) >= num_weights:
                 break
-            weight = grid[order[i]]
-            if norm2(weight - center) < 1e-3:
+            weight = grid[i]
+            if close_to_center[i] and norm2(weight - center) < 1e-3:
                 continue
-            cosine = np.dot(center, weight) / norm_center / norm2(weight)
+            cosine = np.dot(center, weight) / norm_center / grid_norm[i]
             angle = np.arccos(min(max(cosine, -1.0), 1.0))
-            if angle < np.pi / 4.0 and not used(weight):
+            if angle < quarter:
+                if any(c[i] and norm2(w - weight) < 1e-3 for c, w in zip(close_to_succ, succ_w)):
+                    continue
                 out.append(weight)
         return out
 
@@ -131,7 +142,9 @@ class Population:
         generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
         pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=True)
-        all_tests = [self._test_weights(args, opt_graph, sample, grid) for sample in self.sample_batch]
+        grid_arr = np.array(grid, dtype=np.float64)
+        grid_norm = [norm2(w) for w in grid]
+        all_tests = [self._test_weights(args, opt_graph, sample, grid, grid_arr, grid_norm) for sample in self.sample_batch]
         samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
         tests = [tw for tw in all_tests if len(tw) > 0]
         preds, self.last_fits = finish_predictions(pending, all_tests)

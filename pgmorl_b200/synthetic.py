@@ -178,6 +178,46 @@ def run_selection_history(classes, args, generations, seed, update_iter=3, warmu
     return ep, population, graph
 
 
+def make_selection_state(obj_num, n_pop, n_ep, seed=0, siblings=6, **arg_overrides):
+    """A full-size selection problem built directly (2 objectives at n_pop 200 / 1 400
+    candidates / archive 300; 3 objectives at n_pop 420 / 2 940 candidates / archive 500), without running the
+    hundreds of generations a real history would need to fill every performance buffer.
+
+    Opt-graph: families of one root and `siblings` children trained with distinct simplex-grid weights (so every
+    neighbourhood holds more than 3 distinct weights, population_2d.py:39-50); the population is made of children,
+    `n_pop` of them. Archive: `n_ep` mutually non-dominated points on a sphere that cuts through the population's
+    objective range, so some candidates extend the front and others are dominated.
+    Returns (args, opt_graph, population, ep) of the product's classes."""
+    from . import population_2d, population_3d
+    from .ep import EP
+    from .opt_graph import OptGraph
+    rng = np.random.RandomState(seed)
+    M = obj_num
+    args = SelectionArgs(M, **arg_overrides)
+    grid = [w for w in simplex_weights(M, 0.125 if M == 3 else 0.1) if np.min(w) > 0]
+    graph = OptGraph()
+    members = []
+    while len(members) < n_pop:
+        direction = rng.dirichlet(np.ones(M) * 4.0)
+        root_objs = direction / np.linalg.norm(direction) * rng.uniform(60.0, 100.0)
+        root = graph.insert(np.ones(M) / M, root_objs.copy(), -1)
+        for j in rng.choice(len(grid), size=siblings, replace=False):
+            w = np.asarray(grid[j], dtype=np.float64)
+            child_objs = root_objs + _response(rng, root_objs, w)
+            members.append(ObjSample(child_objs.copy(), graph.insert(w.copy(), child_objs.copy(), root)))
+    members = members[:n_pop]
+    pop = (population_2d if M == 2 else population_3d).Population(args)
+    pop.sample_batch = members
+    # points of equal norm in the positive orthant are mutually non-dominated (a >= b with a != b implies |a| > |b|)
+    v = np.abs(rng.normal(size=(n_ep, M))) + 0.05
+    shell = v / np.linalg.norm(v, axis=1, keepdims=True) * 80.0
+    shell = shell[np.argsort(shell[:, 0], kind="stable")]                 # the archive is kept in objective-0 order
+    ep = EP()
+    ep.obj_batch = np.array(shell)
+    ep.sample_batch = np.array([ObjSample(o.copy()) for o in ep.obj_batch], dtype=object)
+    return args, graph, pop, ep
+
+
 # ---------------------------------------------------------------------------------------------
 # Replay environments: the VecEnv / gym surface MOPG_worker touches, fed from synthetic trajectories
 # ---------------------------------------------------------------------------------------------

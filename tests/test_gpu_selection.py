@@ -198,3 +198,46 @@ def _run_generations(z, gens, M, name):
               f"{int(fits_ok.sum())}/{len(fits_ok)}")
     print(f"{name}: {exact}/{gens} generations bit-exact, {explained} explained by chaotic fits")
     assert exact >= gens - 2
+
+
+@pytest.mark.parametrize("M,n_pop,n_ep", [(2, 200, 300), (3, 420, 500)])
+def test_selection_at_full_population_size(M, n_pop, n_ep):
+    """SURVEY.md section 8(d) sizes: every performance buffer full (2 objectives: 200 samples, ~1 400 candidates,
+    archive of 300; 3 objectives: 420 samples, ~2 900 candidates, archive of 500). The product's whole selection runs;
+    its scoring is then checked bit for bit against the oracle on the product's own predictions: all rounds and all
+    picks with 2 objectives, the first round on a random subset of candidates with 3 (the Python oracle needs ~20 ms per
+    candidate there). A sample of the fits is compared with scipy."""
+    import torch
+    from pgmorl_b200.scalarization_methods import WeightedSumScalarization
+    from pgmorl_b200.synthetic import make_selection_state
+    torch.set_default_dtype(torch.float64)
+    try:
+        args, graph, pop, ep = make_selection_state(M, n_pop, n_ep, seed=3)
+        np.random.seed(7)
+        template = WeightedSumScalarization(num_objs=M, weights=np.ones(M) / M)
+        elites, scals, predicted = pop.prediction_guided_selection(args, 0, ep, graph, template)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    cand = np.array([c["prediction"] for c in pop.last_candidates])
+    assert len(pop.sample_batch) == n_pop and len(cand) >= 4 * n_pop and len(elites) == args.num_tasks
+    assert np.isfinite(cand).all()
+    hv, sp = np.asarray(pop.last_hv), np.asarray(pop.last_sparsity)
+    if M == 2:
+        best, ohv, osp = so.greedy_select_2d(ep.obj_batch, cand, args.sparsity, args.num_tasks)
+        for r in range(args.num_tasks):
+            assert np.array_equal(hv[r], ohv[r]) and np.array_equal(sp[r], osp[r]), r
+            assert np.array_equal(predicted[r], cand[best[r]]), r
+    else:
+        idx = np.random.RandomState(1).choice(len(cand), 150, replace=False)
+        best, ohv, osp = so.greedy_select_3d(ep.obj_batch, cand[idx], args.sparsity, 1)
+        assert np.array_equal(hv[0][idx], ohv[0]) and np.array_equal(sp[0][idx], osp[0])
+        # the product's first pick is the arg-max of its own first-round scores (first index on ties)
+        score = hv[0] - args.sparsity * sp[0]
+        assert np.array_equal(predicted[0], cand[int(np.argmax(score))])
+    f = pop.last_fits
+    assert len(f["x"]) == n_pop * M
+    sel = np.random.RandomState(2).choice(len(f["x"]), 60, replace=False)
+    ok = sum(bool(np.isclose(f["theta"][i], so.fit_scipy(f["x"][i], f["y"][i], f["w"][i], f["ub"][i]).x,
+                             rtol=1e-6, atol=1e-9).all()) for i in sel)
+    print(f"M={M}: {len(cand)} candidates, archive {n_ep}; {ok}/60 sampled fits within 1e-6 of scipy")
+    assert ok >= 54
