@@ -573,7 +573,7 @@ extern "C" int pgm_fit_hyperbolic_f64(const double *x, const double *y, const do
     PGM_REQUIRE(F >= 0 && Kmax >= 1, "pgm_fit_hyperbolic_f64: bad sizes F=%d Kmax=%d", F, Kmax);
     if (F == 0) return PGM_OK;
     const size_t smem = (size_t)K4_WARPS * (10 * (size_t)Kmax + 20) * sizeof(double);
-    PGM_REQUIRE(smem <= 200 * 1024, "pgm_fit_hyperbolic_f64: Kmax=%d exceeds the shared-memory budget (max 620 points per fit)", Kmax);
+    PGM_REQUIRE(smem <= 200 * 1024, "pgm_fit_hyperbolic_f64: Kmax=%d exceeds the shared-memory budget (max 2558 points per fit)", Kmax);
     PGM_CUDA(cudaFuncSetAttribute(k4_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k4_fit_kernel<<<(F + K4_WARPS - 1) / K4_WARPS, 32 * K4_WARPS, smem, (cudaStream_t)stream>>>(
         x, y, w, k_len, ub, theta, status, nfev, cost, F, Kmax, 400);

@@ -123,13 +123,13 @@ def test_k4_fits_match_scipy(name):
 
 def test_k4_ragged_fits_up_to_the_size_limit_match_scipy():
     """The recorded histories only hold small neighbourhoods (4-16 points, one row per lane). Well-conditioned
-    synthetic fits with 5 ... 620 points (up to 20 rows per lane, ragged batch, all in one launch) must follow
+    synthetic fits with 4 ... 2 500 points (up to 79 rows per lane, ragged batch, all in one launch) must follow
     scipy step for step: same status, same number of function evaluations, theta within 1e-9 relative.
     Also: an empty batch returns empty arrays, and a fit beyond the shared-memory limit raises."""
     from pgmorl_b200 import kernels as K
     r = np.random.RandomState(7)
     xs, ys, ws, ubs, ref = [], [], [], [], []
-    for k in (5, 33, 64, 200, 620, 17, 100, 32, 31, 97, 4, 333):
+    for k in (5, 33, 64, 200, 620, 17, 100, 32, 31, 97, 4, 333, 2500):
         for rep in range(2):
             x = np.sort(r.uniform(0, 1, k))
             A, a, b, c = r.uniform(5, 60), r.uniform(1, 8), r.uniform(.2, .8), r.uniform(-20, 20)
@@ -149,7 +149,7 @@ def test_k4_ragged_fits_up_to_the_size_limit_match_scipy():
     e = K.fit_hyperbolic([], [], [], [])
     assert e[0].shape == (0, 4) and len(e[1]) == 0
     with pytest.raises(Exception):
-        K.fit_hyperbolic([np.linspace(0, 1, 700)], [np.zeros(700)], [np.ones(700)], [so.upper_bounds(np.zeros(700))])
+        K.fit_hyperbolic([np.linspace(0, 1, 2600)], [np.zeros(2600)], [np.ones(2600)], [so.upper_bounds(np.zeros(2600))])
 
 
 @pytest.mark.parametrize("name,M", [("selection_2d.npz", 2), ("selection_3d.npz", 3)])
