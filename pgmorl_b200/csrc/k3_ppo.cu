@@ -587,13 +587,42 @@ static size_t k3_tcw_bytes(int P, int S, int O, int A, size_t *oxp, size_t *oscr
     return off;
 }
 
+// Clusters of 2*rs CTAs of the wide kernel that the device keeps resident at once (a cluster has to fit one GPC, so this
+// is less than SMs / cluster size); -1 when it cannot be queried (no device: workspace sizing on a build machine).
+static int k3_tcw_resident_clusters(int rs) {
+    static int cache[5] = {-2, -2, -2, -2, -2};
+    if (cache[rs] != -2) return cache[rs];
+    const void *kern = rs == 4 ? (const void *)k3_tcw_kernel<376, 17, 2, 4>
+                               : (rs == 2 ? (const void *)k3_tcw_kernel<376, 17, 2, 2> : (const void *)k3_tcw_kernel<376, 17, 2, 1>);
+    const size_t smem = tw_smem_layout().total;
+    int n = -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * rs * 64); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2 * rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = -1;
+    }
+    if (n < 0) (void)cudaGetLastError();
+    return cache[rs] = n;
+}
+
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
     pl.tc = false; pl.tcw = false; pl.off_mv = 0;
     // wide observations (Humanoid): the streamed tensor-core kernel; row split over as many CTAs per half as fill the SMs
     if (k3_tcw_dims(O, A, M) && (cluster == 0 || cluster == K3_CLUSTER_TC || cluster == K3_CLUSTER_TC2 || cluster == K3_CLUSTER_TC4)) {
         const int tiles = (mb + 127) / 128;
-        if (cluster == 0) pl.rs = (tiles >= 4 && 8 * P <= sms) ? 4 : ((tiles >= 2 && 4 * P <= sms) ? 2 : 1);
+        if (cluster == 0) {
+            // most CTAs per task whose clusters are all resident at once (a second wave of clusters doubles the step)
+            auto fits = [&](int rs) {
+                const int res = k3_tcw_resident_clusters(rs);
+                return tiles >= rs && 2 * rs * P <= sms && (res < 0 || P <= res);
+            };
+            pl.rs = fits(4) ? 4 : (fits(2) ? 2 : 1);
+        }
         else pl.rs = cluster == K3_CLUSTER_TC4 ? 4 : (cluster == K3_CLUSTER_TC2 ? 2 : 1);
         pl.tc = true; pl.tcw = true; pl.C = 2 * pl.rs; pl.G = 1; pl.TM = 0; pl.KG1 = 0; pl.NA = 0; pl.RC = 128; pl.Rg = 0;
         pl.RSG = 0; pl.RSS = 0; pl.NHP = 64; pl.DB = false; pl.fast = false; pl.stage_floats = 0;
