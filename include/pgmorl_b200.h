@@ -142,6 +142,8 @@ int pgm_ppo_grad_f32(const float *params, const float *obs, size_t obs_task_stri
  *   x, y, w [F,Kmax]: per fit the training weights / objective gains / Gaussian point weights,
  *   k_len [F] valid points per fit, ub [F,4] upper bounds (A_ub, 20, 5, 500)
  *   theta [F,4], status [F] (scipy codes 0..4), nfev [F], cost [F] out.
+ * Kmax <= 2558 (one fit's data and Jacobians stay in one CTA's shared memory); F == 0 is a no-op.
+ * The launch is asynchronous on `stream`; inputs must stay alive until it completes.
  */
 int pgm_fit_hyperbolic_f64(const double *x, const double *y, const double *w, const int32_t *k_len,
                            const double *ub, double *theta, int32_t *status, int32_t *nfev, double *cost,
