@@ -17,6 +17,7 @@ from copy import deepcopy
 import numpy as np
 import torch
 
+from . import kernels as K
 from ._lib import PpoHyper
 from .a2c_ppo_acktr import utils
 from .a2c_ppo_acktr.storage import RolloutStorage
@@ -77,6 +78,55 @@ def evaluation(args, sample):
     eval_env.close()
     objs /= args.eval_num
     return objs
+
+
+def evaluation_batch(args, samples):
+    """`evaluation` of several samples at once: the same episodes, seeds and per-sample arithmetic
+    as mopg.py:25-46, with the evaluation environments of all samples stepped in lockstep so that every environment step
+    costs ONE K1 launch (deterministic mode, one row per sample) and one read-back instead of one per sample.
+    Samples whose episode has ended wait for the others; their rows are computed and ignored. Returns a list of
+    objective vectors, identical to [evaluation(args, s) for s in samples]."""
+    P = len(samples)
+    if P == 0:
+        return []
+    policy0 = samples[0].actor_critic
+    dims, device = policy0.dims, policy0.device
+    flat = torch.stack([s.actor_critic.flat for s in samples]).contiguous()
+    envs = [_gym_make(args.env_name) for _ in samples]
+    objs = [np.zeros(args.obj_num) for _ in samples]
+    host_obs = torch.zeros(P, 1, dims.obs, dtype=torch.float32).pin_memory()
+    dev_obs = torch.empty(P, 1, dims.obs, dtype=torch.float32, device=device)
+    out = None
+    with torch.no_grad():
+        for eval_id in range(args.eval_num):
+            obs = []
+            for env in envs:
+                env.seed(args.seed + eval_id)
+                obs.append(env.reset())
+            running = list(range(P))
+            gamma = [1.0] * P
+            while running:
+                for p in running:
+                    ob = obs[p]
+                    if args.ob_rms:
+                        ob_rms = samples[p].env_params['ob_rms']
+                        ob = np.clip((ob - ob_rms.mean) / np.sqrt(ob_rms.var + 1e-8), -10.0, 10.0)
+                    host_obs[p, 0] = torch.Tensor(ob)
+                dev_obs.copy_(host_obs, non_blocking=True)
+                out = K.policy_forward(flat, dev_obs, dims, mode=K.ACT_DETERMINISTIC, out=out)
+                action = out[1].cpu()
+                still = []
+                for p in running:
+                    obs[p], _, done, info = envs[p].step(action[p])
+                    objs[p] += gamma[p] * info['obj']
+                    if not args.raw:
+                        gamma[p] *= args.gamma
+                    if not done:
+                        still.append(p)
+                running = still
+    for env in envs:
+        env.close()
+    return [o / args.eval_num for o in objs]
 
 
 def _restore_rms(envs, env_params):
@@ -198,9 +248,9 @@ def _population_update_raw(args, task_batch, pop, device, start_iter, final_iter
             agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
             agent.optimizer.step_count = int(pop.adam_step[p])
             agent.optimizer.param_groups[0]['lr'] = lr
-            sample = Sample(vn.snapshot(p), ac, agent)
-            sample.objs = evaluation(args, sample)
-            offspring[p].append(sample)
+            offspring[p].append(Sample(vn.snapshot(p), ac, agent))
+        for p, objs in enumerate(evaluation_batch(args, [off[-1] for off in offspring])):
+            offspring[p][-1].objs = objs
     for envs in envs_all:
         envs.close()
     return offspring
@@ -269,9 +319,9 @@ def mopg_population_update(args, task_batch, device, iteration, num_updates, sta
             agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
             agent.optimizer.step_count = int(pop.adam_step[p])
             agent.optimizer.param_groups[0]['lr'] = lr
-            sample = Sample(_snapshot_rms(envs), ac, agent)
-            sample.objs = evaluation(args, sample)
-            offspring[p].append(sample)
+            offspring[p].append(Sample(_snapshot_rms(envs), ac, agent))
+        for p, objs in enumerate(evaluation_batch(args, [off[-1] for off in offspring])):
+            offspring[p][-1].objs = objs
     for envs in envs_all:
         envs.close()
     return offspring

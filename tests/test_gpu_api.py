@@ -153,3 +153,39 @@ def test_pipelined_uploads_match_blocking_path():
             torch.cuda.synchronize()
         outs.append(pop.params.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_batched_evaluation_equals_per_sample_evaluation():
+    """evaluation_batch steps the evaluation environments of all offspring in lockstep (one K1 launch per step): same
+    objective vectors, bit for bit, as evaluation() sample by sample -- with episodes of different lengths, observation
+    normalisation, several evaluation episodes and discounting."""
+    from pgmorl_b200 import mopg
+    from pgmorl_b200.a2c_ppo_acktr.model import Policy
+    z, meta = load_mopg_case("mopg_walker_small.npz")
+    d = meta["dims"]
+
+    class RaggedEnv(synthetic.ToyEvalEnv):
+        def step(self, action):
+            ob, r, done, info = super().step(action)
+            a = np.asarray(action, dtype=np.float64).reshape(-1)
+            return ob, r, self.k >= 3 + int(abs(a[0]) * 50) % 9, info       # length depends on the policy's own actions
+
+    mopg.set_env_hooks(gym_make=lambda name: RaggedEnv(d))
+    rng = np.random.RandomState(0)
+    samples = []
+    for t in range(5):
+        torch.manual_seed(50 + t)
+        pol = Policy((d.obs,), synthetic._Box(d.act), base_kwargs={"layernorm": False}, obj_num=d.obj)
+        pol.flat.mul_(3.0)                                                     # spread the actions (and episode lengths)
+        rms = synthetic._Rms(rng.normal(0, 0.3, d.obs), rng.uniform(0.5, 2.0, d.obs))
+        samples.append(SimpleNamespace(actor_critic=pol, env_params={"ob_rms": rms, "ret_rms": None, "obj_rms": None}))
+    for raw, ob_rms in ((True, True), (False, True), (False, False)):
+        args = make_args(meta, 0)
+        args.eval_num, args.raw, args.ob_rms, args.seed = 3, raw, ob_rms, 11
+        single = [mopg.evaluation(args, s) for s in samples]
+        batch = mopg.evaluation_batch(args, samples)
+        assert len(batch) == len(samples)
+        for a, b in zip(single, batch):
+            assert np.array_equal(a, b), (raw, ob_rms, a, b)
+        assert len({tuple(np.round(a, 6)) for a in single}) > 1              # the samples really differ
+    assert mopg.evaluation_batch(args, []) == []
