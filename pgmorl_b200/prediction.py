@@ -58,9 +58,24 @@ def fit_inputs(view, k, obj_num, cap_threshold):
     ok = view.objs[k]
     aok = np.abs(ok)
     rel = np.abs(ok - view.objs)                              # |objs_k - objs_i| for every node i, reused by each widening
+    has_edges = len(view.parent) > 0
+    near_block = None
+    step = 0
     while True:
-        near = np.all(rel < aok * threshold, axis=1)
-        e = np.nonzero(near[view.parent])[0] if len(view.parent) else np.zeros(0, dtype=np.int64)
+        if step == 0:
+            lt = rel < aok * threshold
+            near = lt[:, 0]
+            for m in range(1, lt.shape[1]):
+                near = near & lt[:, m]
+        else:
+            if (step - 1) % 4 == 0:                           # neighbourhoods of the next four thresholds in one comparison
+                thr = threshold * np.array([1.0, 2.0, 4.0, 8.0])     # exact doublings: the values `threshold *= 2` goes through
+                lt = rel[None, :, :] < aok[None, None, :] * thr[:, None, None]
+                near_block = lt[:, :, 0]
+                for m in range(1, lt.shape[2]):
+                    near_block = near_block & lt[:, :, m]
+            near = near_block[(step - 1) % 4]
+        e = np.nonzero(near[view.parent])[0] if has_edges else np.zeros(0, dtype=np.int64)
         wd = view.edge_w[e]
         if _enough_distinct(wd) or (cap_threshold and threshold >= 1.0):
             break
@@ -68,21 +83,24 @@ def fit_inputs(view, k, obj_num, cap_threshold):
             break                               # in the whole graph); fits are launched for every sample, so stop instead
         threshold *= 2.0
         sigma *= 2.0
+        step += 1
     q = rel / aok                                             # same element-wise operations as population_2d.py:92-93
     coef = np.empty(len(e))
     node_coef = {}
-    for r in range(len(e)):                                   # one Gaussian weight per source node, shared by its edges
-        i = view.parent[e[r]]
+    parents = view.parent[e].tolist()
+    for r, i in enumerate(parents):                           # one Gaussian weight per source node, shared by its edges
         c = node_coef.get(i)
         if c is None:
             dist = norm2(q[i])
             c = node_coef[i] = np.exp(-((dist / sigma) ** 2) / 2.0)
         coef[r] = c
     out = []
+    dy = view.edge_dy[e]
     for dim in range(obj_num):
         x = wd[:, dim].copy()
-        y = view.edge_dy[e][:, dim].copy()
-        ub = np.array([np.clip(np.max(y) - np.min(y), 1.0, 500.0), 20.0, 5.0, 500.0])
+        y = dy[:, dim].copy()
+        span = y.max() - y.min()                              # np.clip(max - min, 1, 500) of population_2d.py:100
+        ub = np.array([min(max(span, 1.0), 500.0), 20.0, 5.0, 500.0])
         out.append((x, y, coef.copy(), ub))
     return out
 
