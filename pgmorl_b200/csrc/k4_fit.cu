@@ -192,7 +192,7 @@ __device__ __forceinline__ void wsum4(double &a, double &b, double &c, double &d
 // (identity when they already are orthogonal to 1e-16); returns whether it rotated.
 __device__ __forceinline__ bool jacobi_angle(double al, double be, double ga, double &cs, double &sn) {
     cs = 1.0; sn = 0.0;
-    if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) return false;
+    if (ga == 0.0 || ga * ga <= 1e-32 * (al * be)) return false;      // |ga| <= 1e-16 sqrt(al be), without the square root
     // tan of the rotation angle, t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (be - al) / (2 ga),
     // written with one square root and one division: t = sign(d) h / (|d| + sqrt(d^2 + h^2)), d = be - al, h = 2 ga
     const double d = be - al, h = 2.0 * ga;
