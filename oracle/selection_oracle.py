@@ -555,7 +555,7 @@ def qr_jacobi_svd(A, sweeps=60):
         rotated = False
         for p, q in ((0, 1), (2, 3), (0, 2), (1, 3), (0, 3), (1, 2)):
             al, be, ga = B[:, p] @ B[:, p], B[:, q] @ B[:, q], B[:, p] @ B[:, q]
-            if ga == 0.0 or abs(ga) <= 1e-16 * np.sqrt(al * be):
+            if ga == 0.0 or ga * ga <= 1e-32 * (al * be):          # |ga| <= 1e-16 sqrt(al be)
                 continue
             rotated = True
             d, h = be - al, 2.0 * ga
