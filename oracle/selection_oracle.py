@@ -201,6 +201,41 @@ def greedy_select_3d(ep_objs, preds, alpha, num_tasks):
     return best_ids, hvs, sps
 
 
+def hv2d_inner(front):
+    """utils.compute_hypervolume (InnerHyperVolume, round(hv, 4)) of a 2-objective front, as the fork copy's scorer
+    calls it (WorkingMorl/morl/population_2d.py:213-214). The dimension sweep on 2-D points is the per-slice area
+    routine of the 3-D case; lifting the points to z = 1 gives the same bits (checked against the reference's
+    InnerHyperVolume in both dimensions when the fork golden was made)."""
+    return hv3d([[float(p[0]), float(p[1]), 1.0] for p in front])
+
+
+def greedy_select_2d_fork(ep_objs, preds, alpha, num_tasks):
+    """The fork copy's 2-objective greedy loop (WorkingMorl/morl/population_2d.py:207-226, 266-306): candidates scored
+    with update_ep + InnerHyperVolume + M-D sparsity; the virtual front is still rebuilt with get_ep_indices."""
+    vep = [np.asarray(p, dtype=np.float64) for p in ep_objs]
+    preds = np.asarray(preds, dtype=np.float64)
+    mask = np.ones(len(preds), dtype=bool)
+    best_ids, hvs, sps = [], [], []
+    for _ in range(num_tasks):
+        hv = np.zeros(len(preds)); sp = np.zeros(len(preds))
+        for i in range(len(preds)):
+            if mask[i]:
+                new_ep = update_ep(vep, preds[i])
+                hv[i] = hv2d_inner(new_ep); sp[i] = sparsity_md(new_ep)
+        hvs.append(hv); sps.append(sp)
+        best, best_v = -1, -np.inf
+        for i in range(len(preds)):
+            if mask[i] and hv[i] - alpha * sp[i] > best_v:
+                best, best_v = i, hv[i] - alpha * sp[i]
+        if best == -1:
+            break
+        best_ids.append(best)
+        mask[best] = False
+        batch = np.array(vep + [preds[best]])
+        vep = [batch[i] for i in get_ep_indices(batch)]
+    return best_ids, hvs, sps
+
+
 # ------------------------------------------------------------------------------------------------
 # hyperbolic prediction model (population_2d.py:56-108)
 # ------------------------------------------------------------------------------------------------

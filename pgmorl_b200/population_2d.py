@@ -10,7 +10,7 @@ import numpy as np
 
 from . import kernels as K
 from .prediction import finish_predictions, launch_fits
-from .utils import norm2
+from .utils import get_ep_indices, norm2
 
 
 class Population:
@@ -71,6 +71,19 @@ class Population:
             hv[mask], sp[mask] = h[0], s[0]
         return hv, sp
 
+    def _score_fork(self, cand_pred, mask, virtual_ep_objs_batch):
+        """Scorer of the reference's fork copy (WorkingMorl/morl/population_2d.py:207-226): update_ep with its 1e-5
+        tolerances, InnerHyperVolume (round(hv, 4)) and the M-D sparsity. The dimension sweep over 2-objective points is
+        the per-slice area routine of the 3-objective kernel, so the points are lifted to z = 1 (x * 1.0 and + 0.0 are
+        exact) and scored by the 3-D kernel: one CTA per candidate, one launch per round."""
+        mask = np.asarray(mask, dtype=bool)
+        hv, sp = np.zeros(len(cand_pred)), np.zeros(len(cand_pred))
+        if mask.any():
+            lift = lambda a: np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1, 2), np.ones((len(a), 1))], axis=1)
+            _, h, s, _ = K.select_greedy(lift(virtual_ep_objs_batch), lift(cand_pred[mask]), 0.0, 1)
+            hv[mask], sp[mask] = h[0], s[0]
+        return hv, sp
+
     def evaluate_hv(self, candidates, mask, virtual_ep_objs_batch):
         return self._score(candidates, mask, virtual_ep_objs_batch)[0].tolist()
 
@@ -102,11 +115,12 @@ class Population:
         N = args.num_tasks
         # ---- prediction: candidates = (sample, weight) pairs with their predicted objectives
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
-        pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=False)
+        fork = bool(getattr(args, 'fork_scoring', False))     # the WorkingMorl/ copy's variant of this routine
+        pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=fork)
         all_tests = [self._test_weights(opt_graph, sample, args.num_weight_candidates) for sample in self.sample_batch]
         samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
         tests = [tw for tw in all_tests if len(tw) > 0]
-        preds, self.last_fits = finish_predictions(pending, all_tests)
+        preds, self.last_fits = finish_predictions(pending, all_tests, zero_if_degenerate=fork)
         candidates = []
         for sample, tw, pr in zip(samples, tests, preds):
             for w, p in zip(tw, pr):
@@ -118,7 +132,10 @@ class Population:
             print('Too few candidates')
             return elite_batch, scalarization_batch, predicted_offspring_objs
         cand_pred = np.array([c['prediction'] for c in candidates], dtype=np.float64)
-        best_ids, self.last_hv, self.last_sparsity, _ = K.select_greedy(virtual_ep, cand_pred, args.sparsity, N)
+        if fork:
+            best_ids, self.last_hv, self.last_sparsity = self._greedy_fork(virtual_ep, cand_pred, args.sparsity, N)
+        else:
+            best_ids, self.last_hv, self.last_sparsity, _ = K.select_greedy(virtual_ep, cand_pred, args.sparsity, N)
         for best_id in best_ids:
             if best_id == -1:
                 print('Too few candidates')
@@ -131,6 +148,27 @@ class Population:
             predicted_offspring_objs.append(deepcopy(c['prediction']))
         self.last_candidates = candidates
         return elite_batch, scalarization_batch, predicted_offspring_objs
+
+    def _greedy_fork(self, virtual_ep, cand_pred, alpha, N):
+        """Greedy loop of the fork copy (WorkingMorl/morl/population_2d.py:266-306): scores from `_score_fork`, arg-max of
+        hv - alpha * sparsity with strict `>`, virtual front rebuilt with get_ep_indices after every pick."""
+        mask = np.ones(len(cand_pred), dtype=bool)
+        vep = [np.asarray(p, dtype=np.float64) for p in virtual_ep]
+        best_ids, hvs, sps = [], [], []
+        for _ in range(N):
+            hv, sp = self._score_fork(cand_pred, mask, vep)
+            hvs.append(hv); sps.append(sp)
+            best_id, max_metrics = -1, -np.inf
+            for i in np.nonzero(mask)[0]:
+                if hv[i] - alpha * sp[i] > max_metrics:
+                    max_metrics, best_id = hv[i] - alpha * sp[i], int(i)
+            best_ids.append(best_id)
+            if best_id == -1:
+                break
+            mask[best_id] = False
+            batch = np.array(vep + [cand_pred[best_id]])
+            vep = [batch[i] for i in get_ep_indices(batch)]
+        return best_ids, np.array(hvs), np.array(sps)
 
     def random_selection(self, args, scalarization_template):
         """population_2d.py:309-319 (numpy global RNG, like the reference)."""

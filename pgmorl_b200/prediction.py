@@ -121,10 +121,11 @@ def launch_fits(opt_graph, node_ids, obj_num, cap_threshold):
                 fits=K.fit_hyperbolic_launch(xs, ys, ws, ubs))                    # all fits in one launch
 
 
-def finish_predictions(handle, test_weights_per_node):
+def finish_predictions(handle, test_weights_per_node, zero_if_degenerate=False):
     """Second half of `predict_population`. test_weights_per_node[i] is an array [n_i, M] for node_ids[i] (any
     positive scaling; normalised to sum 1 here, as population_2d.py:28-32) or None / empty: that node then
-    contributes neither predictions nor fit records (the reference never fits a sample without test weights)."""
+    contributes neither predictions nor fit records (the reference never fits a sample without test weights).
+    `zero_if_degenerate`: the fork copy's fallback (WorkingMorl/morl/population_2d.py:112-117)."""
     theta, status, nfev, cost = K.fit_hyperbolic_collect(handle["fits"])
     view, M = handle["view"], handle["obj_num"]
     preds, keep = [], []
@@ -135,7 +136,14 @@ def finish_predictions(handle, test_weights_per_node):
         tw = np.array(test_weights_per_node[i], dtype=np.float64)
         for row in tw:
             row /= np.sum(row)
-        delta = np.transpose(np.array([model(tw.T[dim], *theta[i * M + dim]) for dim in range(M)]))
+        cols = []
+        for dim in range(M):
+            x = handle["x"][i * M + dim]
+            if zero_if_degenerate and (len(x) == 0 or len(np.unique(x)) < 2):
+                cols.append(np.zeros(len(tw)))       # the fork copy predicts no change without usable data (:112-117)
+            else:
+                cols.append(model(tw.T[dim], *theta[i * M + dim]))
+        delta = np.transpose(np.array(cols))
         preds.append(np.array([view.objs[k] + delta[j] for j in range(len(tw))]))
     pick = lambda seq: [seq[j] for j in keep]
     return preds, dict(x=pick(handle["x"]), y=pick(handle["y"]), w=pick(handle["w"]), ub=pick(handle["ub"]),

@@ -241,3 +241,46 @@ def test_selection_at_full_population_size(M, n_pop, n_ep):
                              rtol=1e-6, atol=1e-9).all()) for i in sel)
     print(f"M={M}: {len(cand)} candidates, archive {n_ep}; {ok}/60 sampled fits within 1e-6 of scipy")
     assert ok >= 54
+
+
+def test_fork_scoring_variant_matches_the_fork_reference():
+    """the 2-objective scorer of the reference's fork copy (WorkingMorl/morl/population_2d.py:
+    update_ep + InnerHyperVolume + M-D sparsity), selected with args.fork_scoring. (1) With the fork's own candidate
+    predictions every round's hv / sparsity array and every pick is bit-exact; (2) the whole product path (host
+    candidates -> K4 -> scoring) reproduces the fork's elites and weights on the recorded generations, with the same
+    allowance for chaotic fits as the main end-to-end test."""
+    import torch
+    from tests.helpers import rebuild_selection_state
+    from pgmorl_b200.scalarization_methods import WeightedSumScalarization
+    z = np.load(os.path.join(GOLDEN, "selection_2d_fork.npz"))
+    gens = int(z["meta"][1])
+    alpha = float(z["args_f"][0]); num_tasks = int(z["args"][0])
+    exact = 0
+    torch.set_default_dtype(torch.float64)
+    try:
+        for g in range(gens):
+            args, graph, pop, ep = rebuild_selection_state(z, g, 2)
+            args.fork_scoring = True
+            pred = z[f"g{g}_cand_pred"]
+            best, hv, sp = pop._greedy_fork(z[f"g{g}_round0_vep"], pred, alpha, num_tasks)
+            for r in range(num_tasks):
+                assert np.array_equal(hv[r], z[f"g{g}_round{r}_hv"]), (g, r)
+                assert np.array_equal(sp[r], z[f"g{g}_round{r}_sparsity"]), (g, r)
+                assert np.array_equal(pred[best[r]], z[f"g{g}_predicted"][r]), (g, r)
+            np.random.seed(1000 + g)
+            template = WeightedSumScalarization(num_objs=2, weights=np.ones(2) / 2)
+            elites, scals, predicted = pop.prediction_guided_selection(args, g, ep, graph, template)
+            ids = [s.optgraph_id for s in elites]
+            w = np.array([sc.weights.numpy() for sc in scals])
+            ref_theta = np.array([z[f"g{g}_fit{i}_theta"] for i in range(int(z[f"g{g}_n_fits"]))])
+            assert len(pop.last_fits["theta"]) == len(ref_theta)
+            fits_ok = np.isclose(pop.last_fits["theta"], ref_theta, rtol=1e-6, atol=1e-9).all(axis=1)
+            same = ids == z[f"g{g}_elite_ids"].tolist() and np.array_equal(w, z[f"g{g}_elite_w"])
+            if same:
+                exact += 1
+            else:
+                assert not fits_ok.all(), f"generation {g}: selection differs although every fit matches scipy"
+            print(f"fork gen {g}: picks {'identical' if same else 'DIFFER'}; fits matching scipy {int(fits_ok.sum())}/{len(fits_ok)}")
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert exact >= gens - 1

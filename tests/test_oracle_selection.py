@@ -113,3 +113,21 @@ def test_trf_with_the_cuda_ports_svd_agrees_with_scipy():
         ok += bool(np.isclose(th, theta, rtol=1e-6, atol=1e-9).all())
         tot += 1
     assert ok >= 0.9 * tot, (ok, tot)
+
+
+def test_fork_scoring_variant_bit_exact():
+    """The fork copy (WorkingMorl/) scores 2-objective candidates with update_ep + InnerHyperVolume + M-D sparsity; the
+    restatement reproduces every recorded round of its golden history bit for bit."""
+    z = np.load(os.path.join(GOLDEN, "selection_2d_fork.npz"))
+    gens = int(z["meta"][1])
+    alpha = float(z["args_f"][0]); num_tasks = int(z["args"][0])
+    for g in range(gens):
+        pred = z[f"g{g}_cand_pred"]
+        best, hvs, sps = so.greedy_select_2d_fork(z[f"g{g}_round0_vep"], pred, alpha, num_tasks)
+        assert int(z[f"g{g}_n_rounds"]) == num_tasks
+        for r in range(num_tasks):
+            assert np.array_equal(hvs[r], z[f"g{g}_round{r}_hv"]), (g, r)
+            assert np.array_equal(sps[r], z[f"g{g}_round{r}_sparsity"]), (g, r)
+            assert np.array_equal(pred[best[r]], z[f"g{g}_predicted"][r])
+            if r + 1 < num_tasks:
+                assert np.array_equal(np.array(z[f"g{g}_round{r + 1}_vep"]).shape[1:], (2,))
