@@ -134,8 +134,7 @@ def finish_predictions(handle, test_weights_per_node, zero_if_degenerate=False):
             continue
         keep.extend(range(i * M, (i + 1) * M))
         tw = np.array(test_weights_per_node[i], dtype=np.float64)
-        for row in tw:
-            row /= np.sum(row)
+        tw = tw / tw.sum(axis=1, keepdims=True)                   # row /= np.sum(row), population_2d.py:28-32 (same bits)
         cols = []
         for dim in range(M):
             x = handle["x"][i * M + dim]
@@ -144,7 +143,7 @@ def finish_predictions(handle, test_weights_per_node, zero_if_degenerate=False):
             else:
                 cols.append(model(tw.T[dim], *theta[i * M + dim]))
         delta = np.transpose(np.array(cols))
-        preds.append(np.array([view.objs[k] + delta[j] for j in range(len(tw))]))
+        preds.append(view.objs[k][None, :] + delta)
     pick = lambda seq: [seq[j] for j in keep]
     return preds, dict(x=pick(handle["x"]), y=pick(handle["y"]), w=pick(handle["w"]), ub=pick(handle["ub"]),
                        theta=theta[keep], status=status[keep], nfev=nfev[keep], cost=cost[keep])
