@@ -3,19 +3,32 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|...]
 
-One "step" = one MOPG iteration of the population shard on one batch of synthetic
-trajectories: rollout inference (K1) + vector GAE / advantage (K2) + PPO update of
-E epochs x B minibatches with Adam (K3). Workload at N=1 = BASELINE.json configs[1]:
-HalfCheetah shape, 6 tasks x 4 envs x 2048 steps, 10 epochs x 32 minibatches. With N > 1
-(torchrun, one rank per GPU) every rank owns its own 6 tasks (weak scaling) and the ranks
-all-gather the per-task objective/loss records once per generation (every 20th step).
+One "step" = one MOPG iteration of the population shard on one batch of synthetic trajectories: rollout inference
+(K1) + vector GAE / advantage (K2) + PPO update of E epochs x B minibatches with Adam (K3). Every GEN_ITERS-th step
+closes a GENERATION (morl/morl.py:62-177): the ranks all-gather the packed per-task records (task id, parent node,
+weight, objective vector of every iteration), every rank updates opt-graph / Pareto archive / population and runs the
+prediction-guided selection (K4 fits + K5 greedy scoring) redundantly on the gathered table, and the (policy, Adam,
+moments) state of elites that change owner moves point to point -- INSIDE the timed region, at every N (N = 1: no
+collective, same selection). Workload at N=1 = BASELINE.json configs[1]: HalfCheetah shape, 6 tasks x 4 envs x 2048
+steps, 10 epochs x 32 minibatches. With N > 1 (torchrun, one rank per GPU) every rank owns its own tasks: 6 per GPU for
+the weak configs, 64 / N for `--config humanoid64` (BASELINE.json configs[3], strong split).
 
-Prints ONE JSON line (rank 0). `value` = device-timed throughput with inputs resident in HBM;
-`e2e` = the same through the public host-buffer API (pinned H2D of every input + D2H of the
-losses inside the timed region). `--impl reference` times the reference's CPU path (oracle
-port with the reference's op sequence, process per task, one thread each) on the host cores.
+Prints ONE JSON line (rank 0):
+  value       device-timed throughput of the K timed steps (CUDA events on the launching stream, max over ranks), inputs
+              resident in HBM, generation boundaries included; `mopg_only` = the same without the boundary steps' extra
+  e2e         the same metric through the host-buffer API: every step does a BLOCKING H2D copy of THAT step's inputs from
+              pinned memory, K1-K3, a D2H read of the losses and a host wait -- host wall clock, nothing overlapped
+  generation  one whole generation (GEN_ITERS e2e steps + exchange + selection + migration) as one wall-clock unit
+  api         one iteration through the drop-in `mopg_population_update` (per-step K1 / K6 over replay environments)
+  roofline / cpu_baseline / selection / clocks as the task statement prescribes.
+`--impl reference` times the reference's CPU path on the host cores: the UNMODIFIED reference where /root/reference is
+importable (kind "reference"), else the oracle port with the reference's op sequence (kind "port"; the GPU box has no
+/root/reference), process per task, one thread each, tasks = tasks/GPU x WORLD_SIZE, selection at the generation boundary
+by the CPU oracle (scipy least_squares + python scoring).
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -27,17 +40,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))      # synth_envs (synthetic selection states, replay environments)
 
 CONFIGS = {
-    # name: (env shape, P per GPU, T, N, E, B, gamma)
-    "c2": ("halfcheetah", 6, 2048, 4, 10, 32, 0.995),       # BASELINE.json configs[1]
-    "walker64": ("walker2d", 64, 2048, 4, 10, 32, 0.995),    # population sweep points (configs[4])
-    "walker256": ("walker2d", 256, 2048, 4, 10, 32, 0.995),
-    "walker1024": ("walker2d", 1024, 2048, 4, 10, 32, 0.995),
-    "hopper3": ("hopper3", 15, 2048, 4, 10, 32, 0.995),
-    "humanoid8": ("humanoid", 8, 2048, 8, 10, 32, 0.99),     # BASELINE.json configs[3] shape: 64 tasks over 8 GPUs
-    "humanoid16": ("humanoid", 16, 2048, 8, 10, 32, 0.99),   # ... over 4 GPUs
-    "humanoid32": ("humanoid", 32, 2048, 8, 10, 32, 0.99),   # ... over 2 GPUs
+    # name: (env shape, tasks per GPU (weak) or in total (strong), T, N, E, B, gamma, scaling)
+    "c2": ("halfcheetah", 6, 2048, 4, 10, 32, 0.995, "weak"),       # BASELINE.json configs[1]
+    "walker64": ("walker2d", 64, 2048, 4, 10, 32, 0.995, "weak"),    # population sweep points (configs[4])
+    "walker256": ("walker2d", 256, 2048, 4, 10, 32, 0.995, "weak"),
+    "walker1024": ("walker2d", 1024, 2048, 4, 10, 32, 0.995, "weak"),
+    "hopper3": ("hopper3", 15, 2048, 4, 10, 32, 0.995, "weak"),
+    "humanoid8": ("humanoid", 8, 2048, 8, 10, 32, 0.99, "weak"),
+    "humanoid16": ("humanoid", 16, 2048, 8, 10, 32, 0.99, "weak"),
+    "humanoid32": ("humanoid", 32, 2048, 8, 10, 32, 0.99, "weak"),
+    "humanoid64": ("humanoid", 64, 2048, 8, 10, 32, 0.99, "strong"),  # BASELINE.json configs[3]: 64 tasks over 2/4/8 GPUs
 }
 GEN_ITERS = 20           # update_iter of the reference's launch scripts (scripts/walker2d-v2.py:40)
 
@@ -102,35 +117,195 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_inputs(d, P, T, N, E, seed):
+def synthetic_inputs(d, P, T, N, E, seed, first_task=0):
+    """Seeded synthetic trajectories / noise / permutations / weights / initial policies of tasks
+    first_task .. first_task + P - 1 (identical bytes for the GPU path and the CPU arm)."""
     from pgmorl_b200 import synthetic
     traj = synthetic.make_trajectories(P, T, N, d, seed=seed)
     eps, perm = synthetic.host_rng_streams(0, T, N, d.act, E)
     w = synthetic.simplex_weights(d.obj, 0.2 if d.obj == 2 else 0.25)
-    weights = np.stack([w[p % len(w)] for p in range(P)])
+    weights = np.stack([w[(first_task + p) % len(w)] for p in range(P)])
     obj_var = np.tile(np.array([1.3, 0.7, 0.9][:d.obj]), (P, 1))
-    flats = [synthetic.init_policy_flat(d, seed=1000 + p).numpy() for p in range(P)]
+    flats = [synthetic.init_policy_flat(d, seed=1000 + first_task + p).numpy() for p in range(P)]
     return traj, eps, perm, weights, obj_var, flats
 
 
-def cpu_reference_leg(d, P, T, N, E, B, gamma, steps, warmup):
-    """Reference CPU path on the host cores (oracle port, reference op sequence, process per task,
-    one torch thread each -- morl/morl.py:34,84-88). Returns (env_steps_per_s, ms_per_step, cores, sample)."""
-    from oracle.mopg_torch_port import timed_population_iteration
+# ------------------------------------------------------------------------------------------------------------------
+# The generation boundary on synthetic objectives (environment evaluation is host work outside the scope): the REAL
+# exchange / bookkeeping / selection / migration code of pgmorl_b200.morl + dist on a synthetic optimisation history.
+# ------------------------------------------------------------------------------------------------------------------
+class GenerationBoundary:
+    def __init__(self, d, n_tasks, world, rank, pop=None, cpu=False, seed=3):
+        import synth_envs
+        from pgmorl_b200 import dist as pdist
+        from pgmorl_b200.scalarization_methods import WeightedSumScalarization
+        self.pd, self.d, self.M, self.W, self.rank, self.pop, self.cpu = pdist, d, d.obj, world, rank, pop, cpu
+        self.n_tasks = n_tasks
+        M = d.obj
+        # steady-state sizes: the recorded 6-task history holds 48 population members (8 per task) and the 2-objective
+        # performance buffers cap the population at 200 (100 x 2), the 3-objective ones at 420 (210 x 2)
+        n_pop = min(8 * n_tasks, 200 if M == 2 else 420)
+        self.args, self.graph, self.population, self.ep = synth_envs.make_selection_state(
+            M, max(n_pop, n_tasks), 50, seed=seed, num_tasks=n_tasks)
+        self.args.update_iter = GEN_ITERS
+        for s in list(self.population.sample_batch) + list(self.ep.sample_batch):
+            s.owner = (s.optgraph_id or 0) % world
+        self.template = WeightedSumScalarization(num_objs=M, weights=np.ones(M) / M)
+        grid = [w for w in __import__("pgmorl_b200.synthetic", fromlist=["x"]).simplex_weights(M, 0.2 if M == 2 else 0.25)]
+        self.elites = list(self.population.sample_batch[:n_tasks])
+        self.weights = [np.asarray(grid[i % len(grid)], dtype=np.float64) for i in range(n_tasks)]
+        self.mine = pdist.shard_tasks(n_tasks, world, rank)
+        self.gen = 0
+        self.n_state = pdist.sample_state_len(d)
+        self.picks = []
+        if cpu:   # CPU arm: the archive's dominance filter and the selection come from the oracle (no GPU visible)
+            from oracle import selection_oracle as so
+            from pgmorl_b200 import ep as ep_mod
+            ep_mod.get_ep_indices = lambda objs: list(so.get_ep_indices(np.asarray(objs, dtype=np.float64)))
+
+    def _objs(self, task):
+        """Synthetic objective vectors of the GEN_ITERS offspring of `task` this generation (seeded per task and
+        generation: independent of how the tasks are sharded)."""
+        import synth_envs
+        rng = np.random.RandomState(100003 * (self.gen + 1) + task)
+        o = np.array(self.elites[task].objs, dtype=np.float64)
+        out = []
+        for _ in range(GEN_ITERS):
+            o = o + synth_envs._response(rng, o, self.weights[task]) / GEN_ITERS
+            out.append(o.copy())
+        return np.stack(out)
+
+    def _select_cpu(self):
+        """prediction_guided_selection with the CPU oracle: scipy least_squares for every fit, python greedy scoring."""
+        from copy import deepcopy
+        from oracle import selection_oracle as so
+        from pgmorl_b200.prediction import GraphView, fit_inputs, model
+        pop, graph, args, M = self.population, self.graph, self.args, self.M
+        view = GraphView(graph)
+        cands = []
+        for s in pop.sample_batch:
+            tw = pop._test_weights(graph, s, args.num_weight_candidates) if M == 2 else None
+            if M != 2:
+                raise NotImplementedError("CPU boundary: 2-objective configs only")
+            if len(tw) == 0:
+                continue
+            theta = [so.fit_scipy(x, y, w, ub)[0] for x, y, w, ub in fit_inputs(view, s.optgraph_id, M, False)]
+            t = np.array(tw, dtype=np.float64)
+            t = t / t.sum(axis=1, keepdims=True)
+            pred = view.objs[s.optgraph_id][None, :] + np.stack([model(t[:, m], *theta[m]) for m in range(M)], axis=1)
+            cands += [(s, w, p) for w, p in zip(tw, pred)]
+        best = so.greedy_select_2d(np.asarray(self.ep.obj_batch), np.array([c[2] for c in cands]), args.sparsity,
+                                   args.num_tasks)[0]
+        elites, scals = [], []
+        for b in best:
+            if b < 0:
+                break
+            sc = deepcopy(self.template)
+            sc.update_weights(cands[int(b)][1] / np.sum(cands[int(b)][1]))
+            elites.append(cands[int(b)][0]); scals.append(sc)
+        return elites, scals
+
+    def run(self):
+        """One generation boundary; returns the seconds spent in (exchange, bookkeeping, selection, migration)."""
+        import synth_envs
+        import torch
+        pd, M, W, rank = self.pd, self.M, self.W, self.rank
+        t0 = time.perf_counter()
+        local = pd.pack_records(self.mine, [self.elites[i].optgraph_id for i in self.mine],
+                                [self.weights[i] for i in self.mine], [self._objs(i) for i in self.mine])
+        table = pd.all_gather_records(local, self.n_tasks)
+        t1 = time.perf_counter()
+        all_samples, offspring = [], []
+        for task, parent, w, objs in pd.unpack_records(table, M):
+            prev = parent
+            for it, o in enumerate(objs):
+                s = synth_envs.ObjSample(o.copy())
+                s.owner = pd.owner_of(task, W)
+                all_samples.append(s)
+                if (it + 1) % self.args.update_iter == 0:
+                    prev = self.graph.insert(w.copy(), o.copy(), prev)
+                    s.optgraph_id = prev
+                    offspring.append(s)
+        self.ep.update(all_samples)
+        self.population.update(offspring)
+        t2 = time.perf_counter()
+        np.random.seed(1000 + self.gen)
+        if self.cpu:
+            elites, scals = self._select_cpu()
+        else:
+            elites, scals, _ = self.population.prediction_guided_selection(self.args, self.gen, self.ep, self.graph, self.template)
+            torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        while len(elites) < self.n_tasks:        # "Too few candidates": keep the loop full with the best remaining members
+            elites.append(self.population.sample_batch[len(elites) % len(self.population.sample_batch)])
+            scals.append(self.template)
+        # migration of the elites whose state lives on another rank than their next task (task i trains on rank i % W);
+        # the payload is the owner's device snapshot of that policy (real sizes: params + Adam moments + running moments)
+        pop = self.pop
+        plan = pd.plan_migration([e.owner for e in elites], W)
+        if pop is not None and W > 1:
+            def get_state(task):
+                p = task % pop.P
+                par, m, v, step = pop.snapshot_state(self.gen, p)
+                out = torch.zeros(self.n_state, dtype=torch.float64, device=pop.device)
+                n = self.d.n_par
+                out[:n], out[n:2 * n], out[2 * n:3 * n] = par, m, v
+                out[3 * n] = step
+                return out
+
+            def put_state(task, t):
+                p, n = task // W, self.d.n_par
+                pop.params[p].copy_(t[:n]); pop.adam_m[p].copy_(t[n:2 * n]); pop.adam_v[p].copy_(t[2 * n:3 * n])
+            pd.migrate_states(plan, get_state, put_state, self.n_state, device=pop.device)
+        if pop is not None:
+            w32 = torch.as_tensor(np.stack([np.asarray(scals[i].weights, dtype=np.float64) for i in self.mine]), dtype=torch.float32)
+            pop.weights.copy_(w32)
+            torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        self.elites = elites
+        self.weights = [np.asarray(s.weights, dtype=np.float64) for s in scals]
+        self.picks.append([(e.optgraph_id, tuple(np.round(w, 12))) for e, w in zip(elites, self.weights)])
+        self.gen += 1
+        return {"exchange_s": t1 - t0, "bookkeeping_s": t2 - t1, "selection_s": t3 - t2, "migration_s": t4 - t3,
+                "migrated": len(plan), "n_pop": len(self.population.sample_batch), "archive": int(len(self.ep.obj_batch))}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm (CPU)
+# ------------------------------------------------------------------------------------------------------------------
+def reference_available():
+    return os.path.isdir("/root/reference/morl") and os.path.isdir("/root/reference/externals/pytorch-a2c-ppo-acktr-gail")
+
+
+def cpu_reference_leg(d, P_total, T, N, E, B, gamma, steps, warmup, boundary=True):
+    """Reference CPU path on the host cores: process per task, one torch thread each (morl/morl.py:34,84-88), the
+    unmodified reference's Policy / RolloutStorage / PPO.update where /root/reference is importable, else the oracle
+    port (same op sequence). Returns a dict with env-steps/s, ms per step, processes, kind, per-step times."""
+    kind = "reference" if reference_available() else "port"
+    if kind == "reference":
+        from oracle.ref_mopg_runner import timed_population_iteration
+    else:
+        from oracle.mopg_torch_port import timed_population_iteration
     cores = os.cpu_count() or 1
-    procs = min(P, cores)
-    traj, eps, perm, weights, obj_var, flats = synthetic_inputs(d, P, T, N, E, seed=1)
-    trajs = [{k: v[p].numpy() for k, v in traj.items()} for p in range(P)]
+    procs = min(P_total, cores)
+    traj, eps, perm, weights, obj_var, flats = synthetic_inputs(d, P_total, T, N, E, seed=1)
+    trajs = [{k: v[p].numpy() for k, v in traj.items()} for p in range(P_total)]
     dims = (d.obs, d.act, d.obj)
     kw = dict(gamma=gamma, lam=0.95, ppo_epoch=E, num_mini_batch=B)
     for _ in range(warmup):
         timed_population_iteration(flats[:procs], dims, trajs[:procs], 0, 3e-4, weights, obj_var, procs, **kw)
-    walls = []
+    gb = GenerationBoundary(d, P_total, 1, 0, pop=None, cpu=True) if boundary and d.obj == 2 else None
+    walls, bnd = [], []
     for i in range(steps):
         wall, per_task, _ = timed_population_iteration(flats, dims, trajs, i, 3e-4, weights, obj_var, procs, **kw)
+        if gb is not None and (i + 1) % GEN_ITERS == 0:
+            t0 = time.perf_counter()
+            gb.run()
+            bnd.append(time.perf_counter() - t0)
         walls.append(wall)
-    ms = 1e3 * float(np.mean(walls))
-    return P * T * N / (ms / 1e3), ms, procs
+    total = float(np.sum(walls) + np.sum(bnd))
+    return {"value": P_total * T * N * steps / total, "ms_per_step": 1e3 * total / steps, "procs": procs, "kind": kind,
+            "mopg_only_ms_per_step": 1e3 * float(np.mean(walls)), "boundary_ms": [1e3 * b for b in bnd]}
 
 
 def selection_leg(cpu=True):
@@ -139,8 +314,8 @@ def selection_leg(cpu=True):
     greedy loop; CPU = oracle port (scipy least_squares + python scoring; 3-D scoring timed on ONE of the 15 rounds
     and scaled, stated in `cpu_sample`)."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from tests.helpers import rebuild_selection_state
+    from helpers import rebuild_selection_state
+    from synth_envs import make_selection_state
     from pgmorl_b200.scalarization_methods import WeightedSumScalarization
     out = {}
     torch.set_default_dtype(torch.float64)
@@ -181,8 +356,7 @@ def selection_leg(cpu=True):
                 out[key]["cpu_sample"] = ("scipy least_squares on every fit + python scoring, 1 core"
                                           + ("" if M == 2 else "; scoring timed on 1 of 15 greedy rounds and scaled"))
         # full performance buffers (n_pop 200 / 1 400 candidates / archive 300 and
-        # n_pop 420 / 2 940 candidates / archive 500), built directly by synthetic.make_selection_state
-        from pgmorl_b200.synthetic import make_selection_state
+        # n_pop 420 / 2 940 candidates / archive 500), built directly by tests/synth_envs.make_selection_state
         for M, n_pop, n_ep in ((2, 200, 300), (3, 420, 500)):
             times = []
             for rep in range(3):
@@ -218,18 +392,91 @@ def selection_leg(cpu=True):
     return out
 
 
+def api_leg(d, P, T, N, E, B, gamma, device, cluster):
+    """One MOPG iteration through the DROP-IN call `mopg.mopg_population_update` (the per-step loop of
+    morl/mopg.py:103-144: one K1 launch per environment step for all tasks, the K2 / K3 update, the Sample snapshots),
+    over replay environments that hand back pre-generated observations (environment time ~ 0), in both modes:
+    host-normalised observations (`make_vec_envs`) and raw simulator output normalised on the device by K6."""
+    import torch
+    from types import SimpleNamespace
+    import synth_envs
+    from pgmorl_b200 import mopg, synthetic
+    from pgmorl_b200.a2c_ppo_acktr import algo
+    from pgmorl_b200.a2c_ppo_acktr.model import Policy
+    from pgmorl_b200.sample import Sample, Task
+    from pgmorl_b200.scalarization_methods import WeightedSumScalarization
+    traj = synthetic.make_trajectories(P, T, N, d, seed=1)
+    trajs = [{k: v[p].numpy() for k, v in traj.items()} for p in range(P)]
+    args = SimpleNamespace(env_name="replay", seed=0, obj_num=d.obj, num_steps=T, num_processes=N,
+                           num_env_steps=40 * T * N, ppo_epoch=E, num_mini_batch=B, gamma=gamma, gae_lambda=0.95, lr=3e-4,
+                           use_linear_lr_decay=True, lr_decay_ratio=1.0, obj_rms=True, ob_rms=True, eval_num=1, raw=True,
+                           update_iter=GEN_ITERS, rl_log_interval=0)
+    order = iter(range(10 ** 9))
+    mopg.set_env_hooks(make_vec_envs=lambda **kw: synth_envs.ReplayVecEnv(trajs[next(order) % P], d, [1.3, 0.7, 0.9][:d.obj]),
+                       gym_make=lambda name: synth_envs.ToyEvalEnv(d, horizon=1), make_raw_vec_envs=False)
+    w = synthetic.simplex_weights(d.obj, 0.2 if d.obj == 2 else 0.25)
+    tasks = []
+    for p in range(P):
+        torch.manual_seed(1000 + p)
+        ac = Policy((d.obs,), synth_envs._Box(d.act), obj_num=d.obj, device=device)
+        agent = algo.PPO(ac, 0.2, E, B, 0.5, 0.0, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+        env = synth_envs.ReplayVecEnv(trajs[p], d, [1.3, 0.7, 0.9][:d.obj])
+        s = Sample({k: getattr(env, k) for k in ("ob_rms", "ret_rms", "obj_rms")}, ac, agent, objs=np.ones(d.obj), optgraph_id=0)
+        tasks.append(Task(s, WeightedSumScalarization(num_objs=d.obj, weights=w[p % len(w)])))
+    out = {}
+    times = []
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mopg.mopg_population_update(args, tasks, device, it, 1, cluster=cluster)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * min(times[1:])
+    out["host_normalised"] = {"ms_per_iteration": ms, "env_steps_per_s": P * T * N / (ms * 1e-3),
+                              "us_per_env_time_step": 1e3 * ms / T}
+    out["note"] = ("wall clock of mopg_population_update(num_updates=1) incl. the replay environments' Python stepping, "
+                   "the per-iteration Sample snapshots and one toy evaluation episode per task; best of 2 after 1 warm-up")
+    return out
+
+
+def k3_source_hash():
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "pgmorl_b200", "csrc", "*"))):
+        if os.path.basename(f).startswith(("k3_", "net.", "common.", "tc.", "tc_pair.")):
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json, written by
+    profiles/ncu_traffic.py next to the raw CSV it was read from). null when no capture exists for this kernel or when the
+    K3 sources changed since the capture (stale)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except OSError:
+        return None, None
+    e = t.get(kernel)
+    if not e:
+        return None, None
+    if e.get("source_sha") != k3_source_hash():
+        return None, f"stale: {e.get('csv')} was captured at source hash {e.get('source_sha')}"
+    return e["dram_bytes"], e.get("csv")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--cluster", type=int, default=int(os.environ.get("PGM_PPO_CLUSTER", "0")))
+    ap.add_argument("--cluster", type=lambda s: int(s, 0), default=int(os.environ.get("PGM_PPO_CLUSTER", "0"), 0))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selection", action="store_true")
-    ap.add_argument("--full-sample", action="store_true",
-                    help="reference arm: time the full-size iteration instead of the T/4 bounded sample")
+    ap.add_argument("--no-api", action="store_true")
+    ap.add_argument("--no-boundary", action="store_true", help="leave the generation boundary out of the timed loops")
+    ap.add_argument("--quarter-sample", action="store_true",
+                    help="reference arm: T/4 steps per iteration (same minibatch size) instead of the full-size iteration")
     args = ap.parse_args()
     if args.impl == "reference":
         # CPU-only arm: hide the GPUs before torch is imported (fork-based worker pools cannot follow the CUDA
@@ -237,11 +484,16 @@ def main():
         os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
     from pgmorl_b200.layout import ENV_SHAPES
-    env, P, T, N, E, B, gamma = CONFIGS[args.config]
+    env, P_cfg, T, N, E, B, gamma, scaling = CONFIGS[args.config]
     d = ENV_SHAPES[env]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if scaling == "strong":
+        assert P_cfg % world == 0, f"{args.config}: {P_cfg} tasks do not split over {world} ranks"
+        P, n_tasks = P_cfg // world, P_cfg
+    else:
+        P, n_tasks = P_cfg, P_cfg * world
     # stdout carries exactly ONE JSON line: whatever native libraries write to file descriptor 1 (NCCL prints its version
     # banner / debug output there) is sent to stderr, and the JSON line goes to a private duplicate of the real stdout
     sys.stdout.flush()
@@ -249,26 +501,33 @@ def main():
     os.dup2(2, 1)
     S = T * N
     metric = "MOPG env-steps/sec (rollout infer + GAE + PPO update)"
+    boundary_on = not args.no_boundary and d.obj == 2
     workload = {"workload": f"{env}-shape population MOPG update: {P} tasks/GPU x {N} envs x {T} steps, "
-                            f"{E} PPO epochs x {B} minibatches, obs {d.obs} act {d.act} obj {d.obj}, 64-64 tanh MLP",
-                "tasks_per_gpu": P, "envs": N, "steps": T, "ppo_epochs": E, "minibatches": B,
-                "l2": "flushed between timed iterations (256 MiB write)"}
+                            f"{E} PPO epochs x {B} minibatches, obs {d.obs} act {d.act} obj {d.obj}, 64-64 tanh MLP"
+                            + (f"; every {GEN_ITERS}th step closes a generation (record all-gather + prediction-guided selection "
+                               f"+ elite migration over all {n_tasks} tasks) inside the timed region" if boundary_on else ""),
+                "tasks_per_gpu": P, "tasks_total": n_tasks, "envs": N, "steps": T, "ppo_epochs": E, "minibatches": B,
+                "generation_iters": GEN_ITERS, "l2": "flushed between timed iterations (256 MiB write)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: same per-row work (minibatch of 256 rows, 10 epochs) on T/4 steps
-        Ts, Bs = (T, B) if args.full_sample else (max(T // 4, 1), max(B // 4, 1))
-        v, ms, cores = cpu_reference_leg(d, P, Ts, N, E, Bs, gamma, args.steps, min(args.warmup, 1))
-        sample = (f"each step = one MOPG iteration of {P} tasks on T={Ts} steps x {N} envs with {Bs} minibatches "
-                  f"of {Ts * N // Bs} rows x {E} epochs (same minibatch size as the full workload), "
-                  f"process per task, 1 torch thread each")
-        line = {"impl": "reference", "metric": metric, "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
-                "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        Ts, Bs = (max(T // 4, 1), max(B // 4, 1)) if args.quarter_sample else (T, B)
+        r = cpu_reference_leg(d, n_tasks, Ts, N, E, Bs, gamma, args.steps, min(args.warmup, 1), boundary=boundary_on)
+        sample = (f"each step = one MOPG iteration of ALL {n_tasks} tasks ({P} per GPU x {world} GPUs) on T={Ts} steps x {N} envs with "
+                  f"{Bs} minibatches of {Ts * N // Bs} rows x {E} epochs, process per task, 1 torch thread each, {r['procs']} processes"
+                  + (f"; CPU-oracle selection (scipy least_squares + python scoring) at every {GEN_ITERS}th step" if boundary_on else ""))
+        workload_ref = dict(workload, steps=Ts, minibatches=Bs)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_ref,
+                "mopg_only": {"ms_per_step": r["mopg_only_ms_per_step"],
+                              "value": n_tasks * Ts * N / (r["mopg_only_ms_per_step"] * 1e-3)},
+                "boundary_ms": r["boundary_ms"],
+                "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["procs"], "kind": r["kind"],
+                                 "host_cores": os.cpu_count(), "sample": sample},
+                "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
         return 0
@@ -283,55 +542,60 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pop = PopulationMOPG(d, P, T, N, ppo_epoch=E, num_mini_batch=B, gamma=gamma, device=dev, cluster=args.cluster)
-    traj, eps, perm, weights, obj_var, flats = synthetic_inputs(d, P, T, N, E, seed=1 + rank)
+    pop.alloc_snapshots(GEN_ITERS)
+    # rank r owns the global tasks {r, r + W, ...} (dist.shard_tasks); inputs seeded per rank
+    traj, eps, perm, weights, obj_var, flats = synthetic_inputs(d, P, T, N, E, seed=1 + rank, first_task=rank * P)
     for p in range(P):
         pop.load_task(p, flats[p], weights=weights[p], obj_var=obj_var[p])
     pop.set_lr(3e-4)
     host = dict(obs=traj["obs"], rewards=traj["rewards"], masks=traj["masks"], bad_masks=traj["bad_masks"],
                 eps=eps.to(torch.float32), perm=perm.to(torch.int32))
-    pop.upload(**host)
+    pop.upload(**host)                      # also leaves the inputs in the pinned staging buffers
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_buf = torch.empty(world * P, 3, device=dev) if world > 1 else None
+    gb = GenerationBoundary(d, n_tasks, world, rank, pop=pop) if boundary_on else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def exchange(i):
-        # once per generation the ranks all-gather the per-task records
-        if world > 1 and (i + 1) % GEN_ITERS == 0:
-            dist.all_gather_into_tensor(gather_buf, pop.losses)
-
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    bnd_log = []
 
-    def run(steps, e2e):
-        """-> (device ms per step, list of per-stage ms or None)"""
+    def boundary(i):
+        if gb is not None and (i + 1) % GEN_ITERS == 0:
+            bnd_log.append(gb.run())
+
+    def run_device(steps):
+        """-> (device ms per step incl. boundaries, device ms per step of the MOPG part alone)"""
         marks = []
-        if e2e:
-            pop.upload_staged_async()                  # inputs of the first iteration
         for i in range(steps):
             flush.fill_(i & 0xFF)                      # evict L2 between timed iterations (not timed)
-            s, e = ev(), ev()
-            if e2e:
-                # every timed iteration: wait for ITS inputs' H2D copy, start the next iteration's copy on the copy stream
-                # (it runs under this iteration's kernels), compute, read the losses back to the host
-                s.record()
-                pop.swap_inputs()
-                pop.upload_staged_async()
-                pop.step()
-                pop._h_losses.copy_(pop.losses, non_blocking=True)
-                exchange(i)
-                e.record()
-                e.synchronize()                        # the caller reads the losses on the host
-            else:
-                s.record()
-                pop.step()
-                exchange(i)
-                e.record()
-            marks.append((s, e))
+            s, m, e = ev(), ev(), ev()
+            s.record()
+            pop.step()
+            pop.snapshot(i)
+            m.record()
+            boundary(i)
+            e.record()
+            marks.append((s, m, e))
         torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in marks) / steps
+        return (sum(s.elapsed_time(e) for s, m, e in marks) / steps, sum(s.elapsed_time(m) for s, m, e in marks) / steps)
+
+    def run_e2e(steps):
+        """Host wall clock: blocking H2D of this step's inputs (pinned) -> K1-K3 -> D2H of the losses -> host wait, plus
+        the generation boundary. -> (ms per step incl. boundaries, ms per step of the MOPG part alone)"""
+        tot = mopg = 0.0
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pop.step_from_staged(snapshot_slot=i)
+            t1 = time.perf_counter()
+            boundary(i)
+            t2 = time.perf_counter()
+            tot += t2 - t0; mopg += t1 - t0
+        return 1e3 * tot / steps, 1e3 * mopg / steps
 
     # stage breakdown (K1 / K2 / K3) with events around each launch, a few steps, outside the timed runs
     def stage_times(steps=10):
@@ -354,23 +618,50 @@ def main():
             acc += (e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3))
         return acc / steps
 
-    run(args.warmup, False)
-    run(min(args.warmup, 3), True)
+    run_device(max(args.warmup, 3))
+    run_e2e(3)
+    if gb is not None:
+        gb.run()                       # one untimed boundary: K4 / K5 / NCCL warm-up
+    bnd_log.clear()
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     t0 = time.perf_counter()
-    ms = run(args.steps, False)
+    ms, ms_mopg = run_device(args.steps)
+    n_bnd_device = len(bnd_log)
     barrier()
-    ms_e2e = run(args.steps, True)
+    ms_e2e, ms_e2e_mopg = run_e2e(args.steps)
     barrier()
     t1 = time.perf_counter()
     clk = clocks.stop(t0, t1)
+    bnd_timed = list(bnd_log)
+    # one whole generation as a unit: GEN_ITERS e2e steps + the boundary, wall clock (skipped steps never happen: the
+    # boundary fires on the last of the GEN_ITERS steps)
+    gen = None
+    if gb is not None:
+        bnd_log.clear()
+        barrier()
+        tg0 = time.perf_counter()
+        for i in range(GEN_ITERS):
+            pop.step_from_staged(snapshot_slot=i)
+            boundary(i)
+        barrier()
+        gen_s = time.perf_counter() - tg0
+        gen = {"wall_ms": 1e3 * gen_s, "iterations": GEN_ITERS, "boundary": bnd_log[-1] if bnd_log else None}
     stages = stage_times()
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_mopg, ms_e2e_mopg, gen["wall_ms"] if gen else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        ms, ms_e2e, ms_mopg, ms_e2e_mopg, gw = t.tolist()
+        if gen:
+            gen["wall_ms"] = gw
+    picks_equal = None
+    if gb is not None and world > 1:      # every rank must have picked the same (elite, weight) pairs in every generation
+        hsh = int(hashlib.sha256(repr(gb.picks).encode()).hexdigest()[:15], 16)
+        tt = torch.tensor([hsh], device=dev, dtype=torch.int64)
+        lst = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(lst, tt)
+        picks_equal = bool(all(int(x) == hsh for x in lst))
     finite = bool(torch.isfinite(pop.params).all() and torch.isfinite(pop.losses).all())
 
     if rank == 0:
@@ -390,59 +681,75 @@ def main():
         # which K3 kernel ran: the tensor-core path (tcgen05 on FP16 operand pairs) is chosen explicitly (cluster 32) or by
         # the library from 8 tasks on for the shapes it is built for; otherwise the FP32 FFMA cluster kernels
         wide = (d.obs, d.act, d.obj) == (376, 17, 2)          # Humanoid: the streamed tensor-core kernel (csrc/k3_tcw.cuh)
-        tc = (args.cluster in (32, 64) or (wide and args.cluster in (0, 128)) or
-              (args.cluster == 0 and P >= 8 and (d.obs, d.act, d.obj) in ((17, 6, 2), (11, 3, 3))))
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures (profiles/): only the
-        # two configurations that were captured, null otherwise
-        traffic = {("c2", False): 7.5e6, ("walker64", True): 81.4e6}.get((args.config, tc))
-        common = {"unit": "TFLOP/s", "achieved": k3_tflops, "traffic": traffic,
-                  "traffic_source": ("profiles/README_r01.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
-                                     if traffic else None),
+        cl = args.cluster & 0xFF
+        tc = (cl in (32, 64) or (wide and cl in (0, 128)) or
+              (cl == 0 and P >= 8 and (d.obs, d.act, d.obj) in ((17, 6, 2), (11, 3, 3))))
+        kernel = "k3_tcw_kernel" if (tc and wide) else ("k3_tc_kernel" if tc else "k3_ppo_fast_kernel")
+        traffic, traffic_src = measured_traffic(f"{kernel}:{args.config}")
+        common = {"unit": "TFLOP/s", "achieved": k3_tflops, "traffic": traffic, "traffic_source": traffic_src,
                   "algorithmic_bytes_per_launch": P * S * k3b / E, "algorithmic_flops_per_launch": P * S * upd,
                   "launch_ms": k3_ms, "hbm_achieved_gbs": P * S * k3b / (k3_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                   "hbm_peak_source": "measured" if peaks else "fallback",
                   "fp32_ffma_peak_tflops": ffma_peak, "frac_of_fp32_ffma_peak": k3_tflops / ffma_peak}
         if tc:
             tpeak = peaks.get("bf16_tflops_sustained", 1400.0)    # FP16 and BF16 UMMA run at the same rate
-            roofline = dict(common, kernel="k3_tcw_kernel" if wide else "k3_tc_kernel", bound="tensor", peak=tpeak, frac=k3_tflops / tpeak,
+            roofline = dict(common, kernel=kernel, bound="tensor", peak=tpeak, frac=k3_tflops / tpeak,
                             peak_source=("measured" if peaks else "fallback") + " dense 16-bit tensor peak (sustained)",
                             note="algorithmic FLOPs; the kernel executes 3 MMAs per product (FP16 operand pairs, FP32-level "
                                  "accuracy) on 128xNx16 tiles with N <= 64, which are shared-memory-operand bound (113 B/clk "
                                  "measured, profiles/tc_mma_bench.py), and its tanh epilogues are XU-pipe bound: see "
                                  "profiles/README_r01.md")
         else:
-            roofline = dict(common, kernel="k3_ppo_fast_kernel", bound="fp32-ffma", peak=ffma_peak, frac=k3_tflops / ffma_peak,
-                            peak_source=f"2*128 lanes*148 SMs*{sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json)",
+            roofline = dict(common, kernel=kernel, bound="fp32-ffma", peak=ffma_peak, frac=k3_tflops / ffma_peak,
+                            peak_source=f"2*128 lanes*148 SMs*{sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json; "
+                                        "profiles/micro/ffma_rate.cu measures 127.7 FMA/clk/SM)",
                             note="small populations are latency/occupancy bound: 6 chains of 320 dependent Adam steps")
+        launches_per_step = pop.GPU_LAUNCHES_PER_STEP
         line = {
             "metric": metric, "value": env_steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
             "clocks": clk,
+            "mopg_only": {"value": env_steps / (ms_mopg * 1e-3), "ms_per_step": ms_mopg,
+                          "note": "the same timed steps without the generation-boundary work (round-1 definition of value)"},
             "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_e2e,
+                    "mopg_only_ms_per_step": ms_e2e_mopg, "timer": "host wall clock, blocking H2D -> K1-K3 -> D2H per step",
                     "h2d_bytes_per_step": pop.h2d_bytes, "d2h_bytes_per_step": pop.d2h_bytes},
-            "gpu_launches": pop.GPU_LAUNCHES_PER_STEP * args.steps * 2,
+            "gpu_launches": launches_per_step * args.steps * 2,
             "roofline": roofline,
             "stages_ms": {"k1_forward": float(stages[0]), "k2_gae_adv": float(stages[1]), "k3_pack_ppo": k3_ms},
             "stage_hbm_gbs": {"k1_forward": P * (S + N) * k1b / (stages[0] * 1e-3) / 1e9,
                               "k2_gae_adv": P * S * k2b / (stages[1] * 1e-3) / 1e9},
             "ppo_cluster": args.cluster, "k3_path": "tensor-core" if tc else "fp32-ffma", "finite": finite,
         }
+        if gen is not None:
+            gen["env_steps_per_s"] = env_steps * GEN_ITERS / (gen["wall_ms"] * 1e-3)
+            gen["unit"] = "env-steps/s over one generation (GEN_ITERS x [H2D + K1-K3 + D2H] + record exchange + selection + migration), wall clock"
+            line["generation"] = gen
+            line["boundaries_in_timed_region"] = {"device_loop": n_bnd_device, "e2e_loop": len(bnd_timed) - n_bnd_device,
+                                                  "per_boundary": bnd_timed, "picks_identical_on_all_ranks": picks_equal}
         if world == 1 and not args.no_selection:
             try:
                 line["selection"] = selection_leg(cpu=not args.no_cpu_baseline)
             except Exception as ex:
                 line["selection"] = {"error": repr(ex)[:200]}
+        if world == 1 and not args.no_api and d.obj == 2:
+            try:
+                line["api"] = api_leg(d, P, T, N, E, B, gamma, dev, args.cluster)
+                line["api"]["bulk_ms_per_iteration"] = ms_e2e_mopg
+            except Exception as ex:
+                line["api"] = {"error": repr(ex)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             # fresh CPU-only process: fork-based worker pools cannot follow CUDA/autograd use in this one
             env_cpu = dict(os.environ, CUDA_VISIBLE_DEVICES="")
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                                    "--warmup", "0", "--config", args.config, "--full-sample"],
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                                    "--warmup", "1", "--config", args.config, "--no-boundary"],
                                    capture_output=True, text=True, env=env_cpu, timeout=900)
                 ref = json.loads(r.stdout.strip().splitlines()[-1])
                 line["cpu_baseline"] = ref["cpu_baseline"]
                 line["cpu_baseline"]["ms_per_step"] = ref["ms_per_step"]
+                line["cpu_baseline"]["sample"] += "; 2 timed steps after 1 warm-up, no generation boundary in this sample"
             except Exception as ex:   # keep the GPU numbers even if the CPU leg fails
                 line["cpu_baseline"] = {"error": repr(ex)[:200]}
         json_out.write(json.dumps(line) + "\n")

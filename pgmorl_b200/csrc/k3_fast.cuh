@@ -28,6 +28,9 @@ __device__ __forceinline__ float4 ld_dsmem4(uint32_t addr) {
 __device__ __forceinline__ void st_dsmem4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_dsmem2x64(uint32_t addr, ulonglong2 v) {
+    asm volatile("st.shared::cluster.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(v.x), "l"(v.y) : "memory");
+}
 __device__ __forceinline__ void st_dsmem1(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -99,7 +102,12 @@ __device__ __forceinline__ void layer_fwd_fast(const float *__restrict__ in, int
     }
 }
 
-template <int C, int TM>
+// RA = false: sliced Adam, three cluster barriers per step (partials pulled from the peers' images, new parameters pushed).
+// RA = true : partial gradient tiles go straight from registers into the slice OWNER's per-source slots, the owner adds its
+//             G slots in fixed order and pushes the reduced slice to every CTA of the half, and every CTA runs Adam on the whole
+//             half redundantly (moments of the whole half resident) -- two cluster barriers per step, nothing is pulled.
+//             Same operations in the same order as RA = false: results are bit-identical.
+template <int C, int TM, bool RA>
 __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a) {
     constexpr int RC = 16 * TM;
     constexpr int G = C / 2;
@@ -136,26 +144,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
     float *dlpS = p; p += RC;
     float *stg = p; p += round_up(a.stage_floats, 4);
     float *recb = p; p += 2 * RC * RSS;
-    float *gP = p; p += a.NHP;                      // this CTA's partial gradient (image layout), read by peers
     const int n4 = NIMG >> 2;                       // float4s in the image
     const int per4 = (n4 + G - 1) / G;              // float4s per slice
     const int sl0 = g * per4, sl1 = min(n4, sl0 + per4);   // my slice [sl0, sl1) in float4 units
-    float *mS = p, *vS = p + 4 * per4, *gS = p + 8 * per4;  // moments + reduced gradient of my slice
+    // RA = false: gP = this CTA's partial gradient (image layout), read by peers; moments + reduced gradient of my slice
+    // RA = true : gP = G per-source slots of my slice (written by the peers), gS = reduced gradient of the whole half
+    //             (written by the slice owners), mS / vS = moments of the whole half
+    float *gP = p; p += RA ? G * 4 * per4 : a.NHP;
+    float *gS = p; p += RA ? G * 4 * per4 : 4 * per4;
+    const int nmom = RA ? NIMG : 4 * per4;
+    float *mS = p, *vS = p + nmom;
+    const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)per4 - 1) / (unsigned)per4);   // i4 / per4 == umulhi(i4, magic)
 
     float *gparams = a.params + (size_t)task * L.n_par;
     halfnet_load<false>(n, gparams, L, half);
-    for (int i = tid; i < 4 * per4; i += NTHREADS) { mS[i] = 0.f; vS[i] = 0.f; }
-    for (int i = tid; i < a.NHP; i += NTHREADS) gP[i] = 0.f;      // padding entries stay zero for the whole launch
+    for (int i = tid; i < nmom; i += NTHREADS) { mS[i] = 0.f; vS[i] = 0.f; }
+    for (int i = tid; i < (RA ? G * 4 * per4 : a.NHP); i += NTHREADS) gP[i] = 0.f;   // padding entries stay zero for the whole launch
+    if (RA) for (int i = tid; i < G * 4 * per4; i += NTHREADS) gS[i] = 0.f;
     for (int i = tid; i < RC; i += NTHREADS) dlpS[i] = 1.f;       // the critic never rewrites it
     __syncthreads();
     if (!a.grad_only) {
         const int nH = L.half_size(half);
         for (int e = tid; e < nH; e += NTHREADS) {
             const int io = half_img_off(n, L, e);
-            if (io >= 4 * sl0 && io < 4 * sl1) {
+            if (RA || (io >= 4 * sl0 && io < 4 * sl1)) {
                 const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
-                mS[io - 4 * sl0] = a.adam_m[gi];
-                vS[io - 4 * sl0] = a.adam_v[gi];
+                mS[io - (RA ? 0 : 4 * sl0)] = a.adam_m[gi];
+                vS[io - (RA ? 0 : 4 * sl0)] = a.adam_v[gi];
             }
         }
     }
@@ -453,30 +468,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             }
         }
 
-        // ---- partial gradient of this CTA -> its own smem image (peers read it through DSMEM) ----
+        // ---- partial gradient of this CTA: RA = false -> its own smem image (peers read it through DSMEM);
+        //      RA = true -> straight from registers into slot g of each piece's slice owner (st.shared::cluster) ----
         {
-            float *gp = gP;
+            const uint32_t gP_u = smem_u32(gP);
+            auto emit16 = [&](int io, ulonglong2 v) {            // io: float offset in the image, multiple of 4
+                if (RA) {
+                    const uint32_t i4 = (uint32_t)io >> 2, ow = __umulhi(i4, magic);
+                    const uint32_t loc = gP_u + 16u * ((uint32_t)g * (uint32_t)per4 + (i4 - ow * (uint32_t)per4));
+                    st_dsmem2x64(mapa_u32(loc, (uint32_t)(half * G) + ow), v);
+                } else {
+                    *reinterpret_cast<ulonglong2 *>(gP + io) = v;
+                }
+            };
+            auto emit1 = [&](int io, float v) {
+                if (RA) {
+                    const uint32_t ow = __umulhi((uint32_t)io >> 2, magic);
+                    const uint32_t loc = gP_u + 4u * ((uint32_t)g * 4u * (uint32_t)per4 + ((uint32_t)io - 4u * ow * (uint32_t)per4));
+                    st_dsmem1(mapa_u32(loc, (uint32_t)(half * G) + ow), v);
+                } else {
+                    gP[io] = v;
+                }
+            };
             const int tj = tid & 15, tk = tid >> 4;
             const int ob1 = (int)(n.b1 - n.W1), oW2 = (int)(n.W2 - n.W1), ob2 = (int)(n.b2 - n.W1);
             const int oWh = (int)(n.Wh - n.W1), obh = (int)(n.bh - n.W1), ols = (int)(n.ls - n.W1);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-                *reinterpret_cast<ulonglong2 *>(gp + oW2 + (4 * tj + jj) * LDH + 4 * tk) = make_ulonglong2(gW2[jj][0], gW2[jj][1]);
-            if (tk == 0) sts4(gp + ob2 + 4 * tj, make_float4(gb2[0], gb2[1], gb2[2], gb2[3]));
+                emit16(oW2 + (4 * tj + jj) * LDH + 4 * tk, make_ulonglong2(gW2[jj][0], gW2[jj][1]));
+            if (tk == 0) emit16(ob2 + 4 * tj, make_ulonglong2(pack2(gb2[0], gb2[1]), pack2(gb2[2], gb2[3])));
             if (isW1 && rs1 == 0) {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
-                    *reinterpret_cast<ulonglong2 *>(gp + (4 * l16 + jj) * L.ldw1 + 4 * kg1) = make_ulonglong2(gW1[jj][0], gW1[jj][1]);
-                if (kg1 == 0) sts4(gp + ob1 + 4 * l16, make_float4(gb1[0], gb1[1], gb1[2], gb1[3]));
+                    emit16((4 * l16 + jj) * L.ldw1 + 4 * kg1, make_ulonglong2(gW1[jj][0], gW1[jj][1]));
+                if (kg1 == 0) emit16(ob1 + 4 * l16, make_ulonglong2(pack2(gb1[0], gb1[1]), pack2(gb1[2], gb1[3])));
             }
             if (isWh && rsh == 0) {
 #pragma unroll
                 for (int ia = 0; ia < 4; ++ia) {
                     const int aa = aslot + ia * fp.nA;
                     if (aa < KH) {
-                        *reinterpret_cast<ulonglong2 *>(gp + oWh + aa * LDH + 4 * l16) = make_ulonglong2(gWh[ia][0], gWh[ia][1]);
-                        if (l16 == 0) gp[obh + aa] = gbh[ia];
-                        if (half == 0 && l16 == 1) gp[ols + aa] = gls[ia];
+                        emit16(oWh + aa * LDH + 4 * l16, make_ulonglong2(gWh[ia][0], gWh[ia][1]));
+                        if (l16 == 0) emit1(obh + aa, gbh[ia]);
+                        if (half == 0 && l16 == 1) emit1(ols + aa, gls[ia]);
                     }
                 }
             }
@@ -495,14 +529,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             const uint32_t gP_u = smem_u32(gP);
             uint32_t peer[G];
 #pragma unroll
-            for (int gg = 0; gg < G; ++gg) peer[gg] = mapa_u32(gP_u, (uint32_t)(half * G + gg));
+            for (int gg = 0; gg < G; ++gg) peer[gg] = mapa_u32(RA ? smem_u32(gS) : gP_u, (uint32_t)(half * G + gg));
             const int ls4 = (int)(n.ls - n.W1) >> 2;
             float sq = 0.f;
             for (int i4 = sl0 + tid; i4 < sl1; i4 += NTHREADS) {
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg) {
-                    const float4 t = ld_dsmem4(peer[gg] + 16u * (uint32_t)i4);
+                    // RA: slot gg of my slice (local, filled by CTA gg of my half); else CTA gg's image through DSMEM
+                    const float4 t = RA ? lds4(gP + 4 * (gg * per4 + (i4 - sl0))) : ld_dsmem4(peer[gg] + 16u * (uint32_t)i4);
                     acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
                 }
                 if (ecoef != 0.f && half == 0 && i4 >= ls4) {   // d(-ecoef * entropy)/d logstd
@@ -514,7 +549,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                 }
                 sq = fmaf(acc.x, acc.x, sq); sq = fmaf(acc.y, acc.y, sq);
                 sq = fmaf(acc.z, acc.z, sq); sq = fmaf(acc.w, acc.w, sq);
-                sts4(gS + 4 * (i4 - sl0), acc);
+                if (RA) {
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) st_dsmem4(peer[gg] + 16u * (uint32_t)i4, acc);   // reduced slice -> every CTA of the half
+                } else {
+                    sts4(gS + 4 * (i4 - sl0), acc);
+                }
             }
             sq = block_sum(sq, red);
             PGM_TR(9)
@@ -526,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             for (int e = tid; e < nH; e += NTHREADS) {
                 const int io = half_img_off(n, L, e);
                 if (io >= 4 * sl0 && io < 4 * sl1)
-                    a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gS[io - 4 * sl0];
+                    a.grad_out[(size_t)task * L.n_par + L.to_global(half, e)] = gS[io - (RA ? 0 : 4 * sl0)];
             }
             break;
         }
@@ -544,14 +584,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             const float coef = fminf(1.f, (float)a.hy.max_grad_norm / (sqrtf(tot) + 1e-6f));
             const float step_size = (float)sh_d[0], ibc2 = (float)sh_d[1];
             float *pimg = n.W1;
-            const uint32_t pimg_u = smem_u32(pimg);
-            uint32_t peer[G];
-#pragma unroll
-            for (int gg = 0; gg < G; ++gg) peer[gg] = mapa_u32(pimg_u, (uint32_t)(half * G + gg));
-            for (int i4 = sl0 + tid; i4 < sl1; i4 += NTHREADS) {
-                const int j4 = i4 - sl0;
-                const float4 g4 = lds4(gS + 4 * j4);
-                float4 m4 = lds4(mS + 4 * j4), v4 = lds4(vS + 4 * j4), p4 = lds4(pimg + 4 * i4);
 #define PGM_ADAM1(cc)                                                                                  \
                 {                                                                                      \
                     const float gr = g4.cc * coef;                                                     \
@@ -560,14 +592,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                     const float denom = fmaf(fast_sqrt(v4.cc), ibc2, aeps);                            \
                     p4.cc -= step_size * __fdividef(m4.cc, denom);                                     \
                 }
-                PGM_ADAM1(x) PGM_ADAM1(y) PGM_ADAM1(z) PGM_ADAM1(w)
-#undef PGM_ADAM1
-                sts4(mS + 4 * j4, m4); sts4(vS + 4 * j4, v4);
+            if (RA) {   // the whole half, redundantly in every CTA of the half: nothing to publish, no third barrier
+                for (int i4 = tid; i4 < n4; i4 += NTHREADS) {
+                    const float4 g4 = lds4(gS + 4 * i4);
+                    float4 m4 = lds4(mS + 4 * i4), v4 = lds4(vS + 4 * i4), p4 = lds4(pimg + 4 * i4);
+                    PGM_ADAM1(x) PGM_ADAM1(y) PGM_ADAM1(z) PGM_ADAM1(w)
+                    sts4(mS + 4 * i4, m4); sts4(vS + 4 * i4, v4); sts4(pimg + 4 * i4, p4);
+                }
+                // the next step's first __syncthreads orders these writes before any read of the parameters
+            } else {
+                const uint32_t pimg_u = smem_u32(pimg);
+                uint32_t peer[G];
 #pragma unroll
-                for (int gg = 0; gg < G; ++gg) st_dsmem4(peer[gg] + 16u * (uint32_t)i4, p4);   // incl. my own image
+                for (int gg = 0; gg < G; ++gg) peer[gg] = mapa_u32(pimg_u, (uint32_t)(half * G + gg));
+                for (int i4 = sl0 + tid; i4 < sl1; i4 += NTHREADS) {
+                    const int j4 = i4 - sl0;
+                    const float4 g4 = lds4(gS + 4 * j4);
+                    float4 m4 = lds4(mS + 4 * j4), v4 = lds4(vS + 4 * j4), p4 = lds4(pimg + 4 * i4);
+                    PGM_ADAM1(x) PGM_ADAM1(y) PGM_ADAM1(z) PGM_ADAM1(w)
+                    sts4(mS + 4 * j4, m4); sts4(vS + 4 * j4, v4);
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) st_dsmem4(peer[gg] + 16u * (uint32_t)i4, p4);   // incl. my own image
+                }
             }
+#undef PGM_ADAM1
         }
-        sync_group<C>();   // (3) every resident image holds the new parameters
+        if (!RA) sync_group<C>();   // (3) every resident image holds the new parameters
         PGM_TR(11)
     }
 
@@ -577,9 +627,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             const size_t gi = (size_t)task * L.n_par + L.to_global(half, e);
             const int io = half_img_off(n, L, e);
             if (g == 0) a.params[gi] = n.W1[io];
-            if (io >= 4 * sl0 && io < 4 * sl1) {
-                a.adam_m[gi] = mS[io - 4 * sl0];
-                a.adam_v[gi] = vS[io - 4 * sl0];
+            if (RA ? g == 0 : (io >= 4 * sl0 && io < 4 * sl1)) {
+                a.adam_m[gi] = mS[io - (RA ? 0 : 4 * sl0)];
+                a.adam_v[gi] = vS[io - (RA ? 0 : 4 * sl0)];
             }
         }
     }
@@ -608,13 +658,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
     }
 }
 
-__host__ inline size_t k3_fast_smem_bytes(const NetLayout &L, int TM, int RSS, int NHP, int stage_floats, int G) {
+__host__ inline size_t k3_fast_smem_bytes(const NetLayout &L, int TM, int RSS, int NHP, int stage_floats, int G, bool ra) {
     const int RC = 16 * TM;
     const int ldo = ((L.A > L.M ? L.A : L.M) | 1);
     const int img = halfnet_smem_floats(L, 0) > halfnet_smem_floats(L, 1) ? halfnet_smem_floats(L, 0) : halfnet_smem_floats(L, 1);
     // image + activations + loss arrays + staging + records + partial-gradient image + slice buffers (G >= 1)
+    const size_t per = 4 * (size_t)((img / 4 + G - 1) / G);
     size_t f = img + 4 * (size_t)RC * LDH + 3 * (size_t)round_up(RC * ldo, 4) + RC + round_up(stage_floats, 4) +
-               2 * (size_t)RC * RSS + (size_t)NHP + 3 * 4 * (size_t)((img / 4 + G - 1) / G);
+               2 * (size_t)RC * RSS + (ra ? 2 * G * per + 2 * (size_t)img : (size_t)NHP + 3 * per);
     return f * sizeof(float);
 }
 

@@ -19,6 +19,7 @@
 //
 // FP32 FFMA throughout; Adam bias corrections in double.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "net.cuh"
 
@@ -550,6 +551,7 @@ namespace pgm {
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
     bool DB, fast, tc, tcw;
+    bool ra;      // fast path: redundant-Adam step tail (two cluster barriers per step, k3_fast.cuh)
     int rs;
     int stage_floats;
     size_t smem;
@@ -609,9 +611,16 @@ static int k3_tcw_resident_clusters(int rs) {
     return cache[rs] = n;
 }
 
+// flag OR-ed into `cluster`: the two-barrier step tail of the FFMA cluster kernel (tiles pushed to the slice owner, whole-half
+// Adam in every CTA; k3_fast.cuh, RA = true). Bit-identical results; measured SLOWER than the default three-barrier sliced
+// tail at the headline configuration (4.04 vs 3.86 ms, profiles/r02/ab_k3_tail.md), so it is opt-in (A/B, tests) only.
+constexpr int K3_CLUSTER_TAIL2 = 0x100;
+
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
-    pl.tc = false; pl.tcw = false; pl.off_mv = 0;
+    const bool tail2 = (cluster & K3_CLUSTER_TAIL2) != 0;
+    cluster &= ~K3_CLUSTER_TAIL2;
+    pl.tc = false; pl.tcw = false; pl.ra = false; pl.off_mv = 0;
     // wide observations (Humanoid): the streamed tensor-core kernel; row split over as many CTAs per half as fill the SMs
     if (k3_tcw_dims(O, A, M) && (cluster == 0 || cluster == K3_CLUSTER_TC || cluster == K3_CLUSTER_TC2 || cluster == K3_CLUSTER_TC4)) {
         const int tiles = (mb + 127) / 128;
@@ -704,7 +713,11 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     if (pl.fast) {
         const int s0 = k3_fast_stage_floats(L.OP, A), s1 = k3_fast_stage_floats(L.OP, M);
         pl.stage_floats = s0 > s1 ? s0 : s1;
-        pl.smem = k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G);
+        // step tail: three-barrier sliced variant by default; the two-barrier variant on request (cluster flag, or
+        // PGM_K3_TAIL=2 in the environment for whole-program A/B runs) when its buffers fit
+        static const bool env_ra = [] { const char *e = getenv("PGM_K3_TAIL"); return e && e[0] == '2'; }();
+        pl.ra = (env_ra || tail2) && pl.G >= 2 && k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, true) <= 227 * 1024;
+        pl.smem = k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, pl.ra);
     } else {
         pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS);
     }
@@ -741,9 +754,13 @@ static int k3_launch_k(Kern kern, int C, const K3Args &a, const K3Plan &pl, int 
 template <int C>
 static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
     if constexpr (C > 1) {
-        if (pl.fast)
-            return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2>, C, a, pl, P, st)
-                              : k3_launch_k(k3_ppo_fast_kernel<C, 4>, C, a, pl, P, st);
+        if (pl.fast) {
+            if (pl.ra)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, true>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, true>, C, a, pl, P, st);
+            return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, false>, C, a, pl, P, st)
+                              : k3_launch_k(k3_ppo_fast_kernel<C, 4, false>, C, a, pl, P, st);
+        }
         if (pl.KG1 == 6) return k3_launch_k(k3_ppo_kernel<C, 2, 6, 2, false>, C, a, pl, P, st);
         return pl.TM == 2 ? k3_launch_k(k3_ppo_kernel<C, 2, 1, 1, true>, C, a, pl, P, st)
                           : k3_launch_k(k3_ppo_kernel<C, 4, 1, 1, true>, C, a, pl, P, st);
@@ -796,9 +813,16 @@ static int sm_count(int &sms) {
 
 using namespace pgm;
 
+#ifdef PGM_K3_TRACE
+static size_t g_last_trace_offset = 0;
+// instrumented builds only (libpgmorl_b200_trace.so): byte offset of the clock marks inside the workspace of the last launch
+extern "C" size_t pgm_ppo_last_trace_offset() { return g_last_trace_offset; }
+#endif
+
 extern "C" size_t pgm_ppo_workspace_bytes(int P, int S, int O, int A, int M, int cluster) {
     // upper bound over every plan the launcher may choose for these dims (cluster 0 = auto)
     NetLayout L(O, A, M);
+    cluster &= ~K3_CLUSTER_TAIL2;
     const int G = cluster == 0 ? 8 : (cluster == 1 ? 1 : cluster / 2);
     const int i0 = halfnet_smem_floats(L, 0), i1 = halfnet_smem_floats(L, 1);
     const int NHP = round_up(i0 > i1 ? i0 : i1, 64);
@@ -841,6 +865,7 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
     a.gpart = (float *)(ws + pl.off_gpart); a.ssq = (float *)(ws + pl.off_ssq); a.lpart = (float *)(ws + pl.off_lpart);
 #ifdef PGM_K3_TRACE
     a.trace = (long long *)(ws + pl.off_trace);
+    g_last_trace_offset = pl.off_trace;
 #else
     a.trace = nullptr;
 #endif

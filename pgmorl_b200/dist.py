@@ -8,8 +8,9 @@ morl/morl.py:93-118): an all-gather of a packed float64 record per task -- scala
 opt-graph node, and the objective vector of every iteration -- after which every rank holds identical
 OptGraph / Population / EP metadata and runs the deterministic float64 selection (K4 + K5) redundantly, so
 all ranks agree on the next (elite, weight) tasks without another collective. Policy state moves only when a
-selected elite is owned by a different rank than the task it will train as: point-to-point send/recv of
-(params, exp_avg, exp_avg_sq, step, lr).
+selected elite is owned by a different rank than the task it will train as: point-to-point send/recv of ONE float64
+vector per elite (params, exp_avg, exp_avg_sq, step, lr and the running observation / return / objective moments,
+`pack_sample_state`). The generation loop that uses these helpers is `pgmorl_b200.morl.run` under torchrun.
 """
 import numpy as np
 import torch
@@ -73,9 +74,81 @@ def plan_migration(elite_owner_ranks, world_size):
             if src != owner_of(i, world_size)]
 
 
-def migrate_states(plan, get_state, put_state, n_par, device=None):
-    """Execute a migration plan. get_state(new_task) -> float32 tensor [3*n_par + 2] (params, exp_avg, exp_avg_sq,
-    step, lr) on the source rank; put_state(new_task, tensor) on the destination rank."""
+RMS_KEYS = ('ob_rms', 'ret_rms', 'obj_rms')
+
+
+def _rms_cap(dims):
+    """Largest element count of each running-moment vector (ob_rms [O]; ret_rms scalar; obj_rms scalar until its first
+    update, then [M] -- running_mean_std.py:4-9, a2c/envs.py:197-211)."""
+    return {'ob_rms': dims.obs, 'ret_rms': 1, 'obj_rms': dims.obj}
+
+
+def sample_state_len(dims):
+    """Length of pack_sample_state() for the network shape `dims` (same for every sample of a run)."""
+    return 3 * dims.n_par + 2 + sum(3 + 2 * k for k in _rms_cap(dims).values())
+
+
+def pack_sample_state(sample):
+    """Everything a Sample needs to keep training on another rank, as ONE fixed-length float64 vector (lossless: the
+    float32 parameters / Adam moments are exactly representable, step and learning rate travel as float64, and the
+    float64 running moments of the observation / return / objective normalisation -- `env_params`, morl/sample.py:12,
+    mopg.py:70-75 -- go bit for bit):
+        [params n | exp_avg n | exp_avg_sq n | step | lr | per rms key: present, ndim, count, mean (padded), var (padded)]"""
+    ac, opt = sample.actor_critic, sample.agent.optimizer
+    parts = [ac.flat.detach().to(torch.float64).cpu(), opt.exp_avg.detach().to(torch.float64).cpu(),
+             opt.exp_avg_sq.detach().to(torch.float64).cpu(),
+             torch.tensor([float(opt.step_count), float(opt.param_groups[0]["lr"])], dtype=torch.float64)]
+    for key, cap in _rms_cap(ac.dims).items():
+        rms = sample.env_params[key]
+        row = np.zeros(3 + 2 * cap)
+        if rms is not None:
+            mean, var = np.asarray(rms.mean, dtype=np.float64), np.asarray(rms.var, dtype=np.float64)
+            assert mean.size <= cap and var.shape == mean.shape, (key, mean.shape, cap)
+            row[0], row[1], row[2] = 1.0, float(mean.ndim), float(getattr(rms, 'count', 0.0))
+            row[3:3 + mean.size] = mean.reshape(-1)
+            row[3 + cap:3 + cap + var.size] = var.reshape(-1)
+        parts.append(torch.from_numpy(row))
+    out = torch.cat(parts).contiguous()
+    assert out.numel() == sample_state_len(ac.dims)
+    return out
+
+
+def unpack_sample_state(payload, template, objs=None, optgraph_id=None):
+    """Inverse of pack_sample_state: a full Sample built from a deep copy of `template` (any local Sample of the same
+    run: it provides the object structure -- Policy, PPO agent, running-moment classes) with every number replaced."""
+    from .sample import Sample
+    payload = payload.detach().to(torch.float64).cpu()
+    s = Sample.copy_from(template)
+    dims = s.actor_critic.dims
+    n, dev = dims.n_par, s.actor_critic.flat.device
+    s.actor_critic.flat = payload[:n].to(torch.float32).to(dev).contiguous()
+    opt = s.agent.optimizer
+    opt.exp_avg = payload[n:2 * n].to(torch.float32).to(dev).contiguous()
+    opt.exp_avg_sq = payload[2 * n:3 * n].to(torch.float32).to(dev).contiguous()
+    opt.step_count = int(payload[3 * n].item())
+    opt.param_groups[0]["lr"] = float(payload[3 * n + 1].item())
+    off = 3 * n + 2
+    for key, cap in _rms_cap(dims).items():
+        row = payload[off:off + 3 + 2 * cap].numpy()
+        off += 3 + 2 * cap
+        rms = s.env_params[key]
+        assert (row[0] != 0.0) == (rms is not None), f"env_params[{key}] presence differs between ranks"
+        if rms is None:
+            continue
+        k = cap if row[1] else 1
+        shape = (k,) if row[1] else ()
+        if hasattr(rms, 'count'):
+            rms.count = float(row[2])
+        rms.mean = row[3:3 + k].copy().reshape(shape)
+        rms.var = row[3 + cap:3 + cap + k].copy().reshape(shape)
+    s.objs, s.optgraph_id = objs, optgraph_id
+    return s
+
+
+def migrate_states(plan, get_state, put_state, n_state, device=None, dtype=torch.float64):
+    """Execute a migration plan. get_state(new_task) -> tensor [n_state] (pack_sample_state) on the source rank;
+    put_state(new_task, tensor) on the destination rank. One batched isend/irecv round (NCCL: point-to-point over
+    NVLink, grouped)."""
     rank, W = world()
     if W == 1:
         return
@@ -83,10 +156,11 @@ def migrate_states(plan, get_state, put_state, n_par, device=None):
     ops, bufs = [], []
     for task, src, dst in plan:
         if rank == src:
-            t = get_state(task).to(dev).contiguous()
+            t = get_state(task).to(device=dev, dtype=dtype).contiguous()
+            assert t.numel() == n_state, (t.numel(), n_state)
             ops.append(dist.P2POp(dist.isend, t, dst, tag=task)); bufs.append((None, t))
         elif rank == dst:
-            t = torch.empty(3 * n_par + 2, dtype=torch.float32, device=dev)
+            t = torch.empty(n_state, dtype=dtype, device=dev)
             ops.append(dist.P2POp(dist.irecv, t, src, tag=task)); bufs.append((task, t))
     if ops:
         for req in dist.batch_isend_irecv(ops):
@@ -94,3 +168,15 @@ def migrate_states(plan, get_state, put_state, n_par, device=None):
     for task, t in bufs:
         if task is not None:
             put_state(task, t)
+
+
+def all_reduce_rows(rows, device=None):
+    """Sum a float64 table over the ranks (each rank fills the rows it owns, zeros elsewhere)."""
+    rank, W = world()
+    rows = np.asarray(rows, dtype=np.float64)
+    if W == 1:
+        return rows
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+    t = torch.from_numpy(rows.copy()).to(dev)
+    dist.all_reduce(t)
+    return t.cpu().numpy()

@@ -200,3 +200,39 @@ class PopulationMOPG:
         self._h_losses.copy_(self.losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._h_losses.numpy().copy()
+
+    def staging(self):
+        """The pinned host buffers the environment workers fill for the next iteration: obs, rewards, masks, bad_masks,
+        eps, perm (shapes of the device buffers)."""
+        return self._h
+
+    def step_from_staged(self, snapshot_slot=None):
+        """End-to-end call on the inputs sitting in the pinned staging buffers: blocking sequence H2D of THIS iteration's
+        inputs -> K1..K3 -> (optional) device snapshot of every task's state -> D2H of the losses -> host wait.
+        Nothing of the next iteration overlaps: an on-policy loop cannot have its inputs before this update is done."""
+        self.upload_staged()
+        self.step()
+        if snapshot_slot is not None:
+            self.snapshot(snapshot_slot)
+        self._h_losses.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._h_losses
+
+    # ---- per-iteration offspring snapshots (what morl/mopg.py:146-149 deep-copies into a Sample), kept on the device ----
+    def snapshot(self, slot):
+        """Copy params / Adam moments / step of every task into snapshot slot `slot` (ring of `n_slots` slots, allocated on
+        first use: one per iteration of a generation)."""
+        if not hasattr(self, "_snap"):
+            self.alloc_snapshots(20)
+        k = slot % self._snap.shape[0]
+        self._snap[k, :, 0].copy_(self.params); self._snap[k, :, 1].copy_(self.adam_m); self._snap[k, :, 2].copy_(self.adam_v)
+        self._snap_step[k].copy_(self.adam_step)
+
+    def alloc_snapshots(self, n_slots):
+        self._snap = torch.empty(n_slots, self.P, 3, self.dims.n_par, device=self.device)
+        self._snap_step = torch.empty(n_slots, self.P, dtype=torch.int32, device=self.device)
+
+    def snapshot_state(self, slot, p):
+        """-> (params, adam_m, adam_v [n_par] f32 views, step tensor) of task p in snapshot slot `slot`."""
+        k = slot % self._snap.shape[0]
+        return self._snap[k, p, 0], self._snap[k, p, 1], self._snap[k, p, 2], self._snap_step[k, p]

@@ -10,18 +10,31 @@ from copy import deepcopy
 
 
 class Sample:
-    def __init__(self, env_params, actor_critic, agent, objs=None, optgraph_id=None):
+    def __init__(self, env_params, actor_critic, agent, objs=None, optgraph_id=None, owner=None):
         self.env_params = env_params
         self.actor_critic = actor_critic
         self.agent = agent
         self.link_policy_agent()
         self.objs = objs
         self.optgraph_id = optgraph_id
+        # sharded runs (morl.run under torchrun, dist.py): rank whose HBM holds this sample's policy / Adam / moments.
+        # On every other rank the sample is a stub (actor_critic / agent / env_params None) that carries only the
+        # metadata the selection reads (objs, optgraph_id). None = single-process run.
+        self.owner = owner
 
     @classmethod
     def copy_from(cls, sample):
         return cls(deepcopy(sample.env_params), deepcopy(sample.actor_critic), deepcopy(sample.agent),
-                   deepcopy(sample.objs), sample.optgraph_id)
+                   deepcopy(sample.objs), sample.optgraph_id, getattr(sample, "owner", None))
+
+    @classmethod
+    def stub(cls, objs, optgraph_id=None, owner=None):
+        """Metadata-only sample: the state lives on rank `owner`."""
+        return cls(None, None, None, objs, optgraph_id, owner)
+
+    @property
+    def is_stub(self):
+        return self.actor_critic is None
 
     def link_policy_agent(self):
         if self.agent is None:        # objective-only samples (selection tests / replay)

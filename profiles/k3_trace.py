@@ -21,7 +21,7 @@ from pgmorl_b200._lib import lib  # noqa: E402
 from pgmorl_b200.layout import ENV_SHAPES  # noqa: E402
 from pgmorl_b200.population_state import PopulationMOPG  # noqa: E402
 
-C = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+C = int(sys.argv[1], 0) if len(sys.argv) > 1 else 8      # OR 0x100 in for the two-barrier tail
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 d = ENV_SHAPES["halfcheetah"]
 T, N, E, B = 2048, 4, 10, 32
@@ -34,10 +34,14 @@ pop.upload(traj["obs"], traj["rewards"], traj["masks"], traj["bad_masks"], eps.f
 for _ in range(3):
     pop.step()
 torch.cuda.synchronize()
-total = lib().pgm_ppo_workspace_bytes(P, T * N, d.obs, d.act, d.obj, C)
-tr_bytes = (P * 16 * 4 * 16 * 2 * 8 + 255) // 256 * 256
+import ctypes
+fn = lib().pgm_ppo_last_trace_offset            # exported by the instrumented build only
+fn.restype = ctypes.c_size_t
+t_off = fn()
+tr_bytes = P * 16 * 4 * 16 * 2 * 8
 off = (-pop.workspace.data_ptr()) % 256
-raw = pop.workspace[off + total - tr_bytes: off + total].cpu().numpy().view(np.int64)
+raw = pop.workspace[off + t_off: off + t_off + tr_bytes].cpu().numpy().view(np.int64)
+CF, C = C, C & 0xFF
 tr = raw[: P * C * 4 * 16 * 2].reshape(P * C, 4, 16, 2)
 names = ["gather", "fwd", "loss", "phA", "phB", "phC", "write", "bar1", "reduce", "bar2", "adam"]
 print(f"cluster {C}: per-phase cycles (clock64), task 0, step index 9 (2nd traced step)")

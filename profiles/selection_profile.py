@@ -27,7 +27,8 @@ for name, M in (("selection_2d.npz", 2), ("selection_3d.npz", 3)):
             pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
 
 # full performance buffers (SURVEY.md section 8(d) sizes), built by synthetic.make_selection_state
-from pgmorl_b200.synthetic import make_selection_state
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from synth_envs import make_selection_state
 for M, n_pop, n_ep in ((2, 200, 300), (3, 420, 500)):
     for rep in range(3):
         args_s, graph, pop, ep = make_selection_state(M, n_pop, n_ep, seed=3)

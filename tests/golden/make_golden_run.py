@@ -20,7 +20,8 @@ import ref_import  # noqa: E402
 ref_import.install()
 sys.modules.setdefault("environments", types.ModuleType("environments"))     # morl.py:3 only registers gym envs
 
-from pgmorl_b200 import synthetic  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import synth_envs  # noqa: E402
 from pgmorl_b200.layout import NetDims  # noqa: E402
 
 
@@ -29,7 +30,7 @@ METHODS = ("prediction-guided", "moead", "ra", "pfa", "random")     # morl/morl.
 
 def run_args(save_dir, method="prediction-guided"):
     """The configuration of the golden run; tests/test_gpu_run.py builds the same namespace."""
-    args = synthetic.run_args_2d(save_dir)
+    args = synth_envs.run_args_2d(save_dir)
     args.selection_method = method
     return args
 
@@ -44,8 +45,8 @@ def one_run(method):
     d = NetDims(17, 6, 2)
     save_dir = tempfile.mkdtemp()
     args = run_args(save_dir, method)
-    envs_mod.make_vec_envs = lambda **kw: synthetic.SeededReplayVecEnv(d, args.num_steps, args.num_processes, [1.3, 0.7], base_seed=500)
-    gym.make = lambda name: synthetic.ToyEvalEnv(d)
+    envs_mod.make_vec_envs = lambda **kw: synth_envs.SeededReplayVecEnv(d, args.num_steps, args.num_processes, [1.3, 0.7], base_seed=500)
+    gym.make = lambda name: synth_envs.ToyEvalEnv(d)
     import morl  # the reference's driver
     t0 = time.time()
     morl.run(args)

@@ -1,6 +1,6 @@
 """Generate tests/golden/selection_*.npz by running the UNMODIFIED reference selection code
 (morl/population_2d.py, population_3d.py, ep.py, utils.py, hypervolume.py, opt_graph.py) on
-synthetic optimisation histories (pgmorl_b200.synthetic.run_selection_history).
+synthetic optimisation histories (pgmorl_b200.synth_envs.run_selection_history).
 
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden_selection.py
@@ -35,12 +35,13 @@ from opt_graph import OptGraph as RefOptGraph  # noqa: E402
 from scalarization_methods import WeightedSumScalarization as RefScal  # noqa: E402
 from scipy.optimize import least_squares as scipy_lsq  # noqa: E402
 
-from pgmorl_b200 import synthetic  # noqa: E402
+sys.path.insert(0, os.path.join(HERE, ".."))
+import synth_envs  # noqa: E402
 
 
 def record_history(M, generations, seed, **argkw):
     mod = ref2d if M == 2 else ref3d
-    args = synthetic.SelectionArgs(M, **argkw)
+    args = synth_envs.SelectionArgs(M, **argkw)
     fits, rounds, cands = [], [], []
 
     def lsq(fun, x0, **kw):
@@ -102,7 +103,7 @@ def record_history(M, generations, seed, **argkw):
         fits.clear(); rounds.clear(); cands.clear()
 
     classes = dict(EP=RefEP, Population=Pop, OptGraph=RefOptGraph, Scalarization=RefScal)
-    synthetic.run_selection_history(classes, args, generations, seed, on_generation=on_gen)
+    synth_envs.run_selection_history(classes, args, generations, seed, on_generation=on_gen)
     return blob
 
 
@@ -110,7 +111,7 @@ def helper_kats():
     """Known-answer tests of the helper functions, computed by the reference."""
     rng = np.random.RandomState(0)
     out = {}
-    pop2 = ref2d.Population(synthetic.SelectionArgs(2))
+    pop2 = ref2d.Population(synth_envs.SelectionArgs(2))
     for i in range(40):
         n = int(rng.randint(1, 60))
         M = 2 if i % 2 == 0 else 3

@@ -35,7 +35,7 @@ def rebuild_selection_state(z, g, M):
     prediction_guided_selection in generation g of a golden history."""
     from pgmorl_b200.ep import EP
     from pgmorl_b200.opt_graph import OptGraph
-    from pgmorl_b200.synthetic import ObjSample, SelectionArgs
+    from synth_envs import ObjSample, SelectionArgs
     from pgmorl_b200 import population_2d, population_3d
     args = SelectionArgs(M)
     graph = OptGraph()

@@ -37,8 +37,8 @@ def _worker(rank, world, port, n_tasks, out_dir):
         owners = [(3 * i + 1) % world for i in range(n_tasks)]
         plan = pd.plan_migration(owners, world)
         got = {}
-        state = lambda task: torch.arange(3 * n_par + 2, dtype=torch.float32) + 1000.0 * task
-        pd.migrate_states(plan, state, lambda task, t: got.__setitem__(task, t.clone()), n_par)
+        state = lambda task: torch.arange(3 * n_par + 2, dtype=torch.float64) + 1000.0 * task + 1e-13   # needs float64 to survive
+        pd.migrate_states(plan, state, lambda task, t: got.__setitem__(task, t.clone()), 3 * n_par + 2)
         expect = [task for task, src, dst in plan if dst == rank]
         assert sorted(got) == sorted(expect)
         for task, t in got.items():

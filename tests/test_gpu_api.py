@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 import torch
 
+import synth_envs
 from pgmorl_b200 import synthetic
 from tests.helpers import load_mopg_case, rel_err
 
@@ -33,7 +34,7 @@ def build_task(z, meta, task):
     from pgmorl_b200.scalarization_methods import WeightedSumScalarization
     d = meta["dims"]
     torch.manual_seed(1000 + task)
-    pol = Policy((d.obs,), synthetic._Box(d.act), base_kwargs={"layernorm": False}, obj_num=d.obj)
+    pol = Policy((d.obs,), synth_envs._Box(d.act), base_kwargs={"layernorm": False}, obj_num=d.obj)
     assert rel_err(pol.flat.cpu().numpy(), z[f"t{task}_init"]) < 1e-6        # same init as the reference's Policy
     agent = PPO(pol, 0.2, meta["E"], meta["B"], 0.5, 0.0, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
     env_params = {"ob_rms": None, "ret_rms": None, "obj_rms": None}
@@ -49,9 +50,9 @@ def install_hooks(meta, z, j, tasks):
 
     def factory(**kw):
         task = next(it)
-        return synthetic.ReplayVecEnv({k: v[task].numpy() for k, v in trajs.items()}, d, z[f"t{task}_obj_var"])
+        return synth_envs.ReplayVecEnv({k: v[task].numpy() for k, v in trajs.items()}, d, z[f"t{task}_obj_var"])
 
-    mopg.set_env_hooks(make_vec_envs=factory, gym_make=lambda name: synthetic.ToyEvalEnv(d))
+    mopg.set_env_hooks(make_vec_envs=factory, gym_make=lambda name: synth_envs.ToyEvalEnv(d))
 
 
 @pytest.mark.parametrize("name", ["mopg_walker_small.npz", "mopg_hopper3_small.npz"])
@@ -112,7 +113,7 @@ def test_sample_task_lifecycle_and_state_dict_roundtrip():
     sd = s.actor_critic.state_dict()
     assert list(sd)[0] == "base.actor.0.weight" and list(sd)[-1] == "dist.logstd._bias" and sd["dist.logstd._bias"].shape == (6, 1)
     d = meta["dims"]
-    p2 = Policy((d.obs,), synthetic._Box(d.act), obj_num=d.obj)
+    p2 = Policy((d.obs,), synth_envs._Box(d.act), obj_num=d.obj)
     p2.load_state_dict(sd)
     assert torch.equal(p2.flat, s.actor_critic.flat)
     # act / get_value / evaluate_actions are consistent with each other
@@ -164,7 +165,7 @@ def test_batched_evaluation_equals_per_sample_evaluation():
     z, meta = load_mopg_case("mopg_walker_small.npz")
     d = meta["dims"]
 
-    class RaggedEnv(synthetic.ToyEvalEnv):
+    class RaggedEnv(synth_envs.ToyEvalEnv):
         def step(self, action):
             ob, r, done, info = super().step(action)
             a = np.asarray(action, dtype=np.float64).reshape(-1)
@@ -175,9 +176,9 @@ def test_batched_evaluation_equals_per_sample_evaluation():
     samples = []
     for t in range(5):
         torch.manual_seed(50 + t)
-        pol = Policy((d.obs,), synthetic._Box(d.act), base_kwargs={"layernorm": False}, obj_num=d.obj)
+        pol = Policy((d.obs,), synth_envs._Box(d.act), base_kwargs={"layernorm": False}, obj_num=d.obj)
         pol.flat.mul_(3.0)                                                     # spread the actions (and episode lengths)
-        rms = synthetic._Rms(rng.normal(0, 0.3, d.obs), rng.uniform(0.5, 2.0, d.obs))
+        rms = synth_envs._Rms(rng.normal(0, 0.3, d.obs), rng.uniform(0.5, 2.0, d.obs))
         samples.append(SimpleNamespace(actor_critic=pol, env_params={"ob_rms": rms, "ret_rms": None, "obj_rms": None}))
     for raw, ob_rms in ((True, True), (False, True), (False, False)):
         args = make_args(meta, 0)

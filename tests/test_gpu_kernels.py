@@ -138,7 +138,7 @@ def _ppo_inputs(d, P, T, N, seed):
 
 # 32 / 64 / 128 = tensor-core paths (tcgen05): 2 / 4 / 8 CTAs per task; csrc/k3_tc.cuh (Walker2d, Hopper-v3 shapes),
 # csrc/k3_tcw.cuh (Humanoid: layer 1 streamed in 64-feature blocks)
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 32, 64, 128])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16, 32, 64, 128])
 @pytest.mark.parametrize("name,P,T,N,mb", [("walker", 2, 64, 4, 256), ("walker", 1, 30, 4, 100),
                                             ("hopper3", 2, 48, 2, 64), ("humanoid", 1, 32, 8, 96),
                                             ("humanoid", 2, 64, 8, 512), ("humanoid", 1, 40, 8, 300)])
@@ -149,6 +149,8 @@ def test_k3_gradient_matches_oracle(name, P, T, N, mb, cluster):
         pytest.skip("wide networks need cluster >= 2 (both halves do not fit one CTA's shared memory)")
     if name != "humanoid" and cluster == 128:
         pytest.skip("8 CTAs per task exist on the wide-observation tensor-core path only")
+    if name == "humanoid" and cluster == 16:
+        pytest.skip("16-CTA clusters are a plan of the small-network FFMA kernel only")
     cur, pk, perm = _ppo_inputs(d, P, T, N, seed=11)
     S = T * N
     idx = np.random.RandomState(0).permutation(S)[:mb]
@@ -167,7 +169,7 @@ def test_k3_gradient_matches_oracle(name, P, T, N, mb, cluster):
         assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 2e-5
 
 
-@pytest.mark.parametrize("cluster", [0, 1, 2, 4, 8, 32, 64])
+@pytest.mark.parametrize("cluster", [0, 1, 2, 4, 8, 16, 32, 64])
 @pytest.mark.parametrize("name,P,T,N,B", [("walker", 3, 64, 4, 4), ("hopper3", 2, 48, 2, 3), ("walker", 2, 160, 4, 2)])
 def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
     from pgmorl_b200 import kernels as K
@@ -199,6 +201,36 @@ def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
         assert rel_err(gm[p].cpu().numpy(), m) < 1e-4          # Adam first moment
         assert rel_err(gv[p].cpu().numpy(), v) < 1e-4          # Adam second moment
         assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 1e-4
+
+
+TAIL2 = 0x100     # flag OR-ed into `cluster`: the opt-in two-barrier step tail of the FFMA cluster kernel (csrc/k3_fast.cuh)
+
+
+@pytest.mark.parametrize("cluster", [4, 8, 16])
+@pytest.mark.parametrize("name,P,T,N,B", [("walker", 3, 64, 4, 4), ("hopper3", 2, 48, 2, 3), ("walker", 2, 512, 4, 8)])
+def test_k3_step_tails_bit_identical(name, P, T, N, B, cluster):
+    """The two-barrier step tail (tiles pushed to the slice owner, whole-half Adam in every CTA) performs the same
+    operations in the same order as the three-barrier sliced tail: parameters, moments and losses are equal bit for bit,
+    and so is the raw gradient."""
+    from pgmorl_b200 import kernels as K
+    d = DIMS[name]
+    cur, pk, perm = _ppo_inputs(d, P, T, N, seed=17)
+    hyper = K.PpoHyper(entropy_coef=0.01)
+    lr = dev(np.array([3e-4, 2.5e-4, 1e-4][:P]), torch.float64)
+    out = []
+    for cl in (cluster, cluster | TAIL2):
+        gp, gm, gv = dev(cur), torch.zeros(P, d.n_par, device="cuda"), torch.zeros(P, d.n_par, device="cuda")
+        gstep = torch.zeros(P, dtype=torch.int32, device="cuda")
+        losses = K.ppo_update(gp, gm, gv, gstep, lr, dev(pk["obs"]), dev(pk["action"]), dev(pk["logp"]), dev(pk["value"]),
+                              dev(pk["returns"]), dev(pk["adv"]), dev(perm[None], torch.int32), B, d, hyper=hyper, cluster=cl)
+        idx = np.random.RandomState(0).permutation(T * N)[:max(T * N // B, 1)]
+        g, gl = K.ppo_grad(dev(cur), dev(pk["obs"]), dev(pk["action"]), dev(pk["logp"]), dev(pk["value"]),
+                           dev(pk["returns"]), dev(pk["adv"]), dev(idx, torch.int32), d, hyper=hyper, cluster=cl)
+        torch.cuda.synchronize()
+        out.append((gp, gm, gv, gstep, losses, g, gl))
+    for x, y in zip(*out):
+        assert torch.equal(x, y)
+    assert int(out[0][3][0]) == perm.shape[0] * B
 
 
 @pytest.mark.parametrize("cluster", [0, 8, 32, 64, 128])

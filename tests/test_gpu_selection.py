@@ -209,7 +209,7 @@ def test_selection_at_full_population_size(M, n_pop, n_ep):
     candidate there). A sample of the fits is compared with scipy."""
     import torch
     from pgmorl_b200.scalarization_methods import WeightedSumScalarization
-    from pgmorl_b200.synthetic import make_selection_state
+    from synth_envs import make_selection_state
     torch.set_default_dtype(torch.float64)
     try:
         args, graph, pop, ep = make_selection_state(M, n_pop, n_ep, seed=3)

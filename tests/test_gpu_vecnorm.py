@@ -110,7 +110,7 @@ class _HostNormalised:
 
     def __init__(self, raw, dims, gamma):
         from oracle.vecnorm_oracle import VecNormalizeOracle
-        from pgmorl_b200.synthetic import _Box
+        from synth_envs import _Box
         self.raw, self.vn = raw, VecNormalizeOracle(raw.N, raw.O, ob=True, ret=True, obj_rms=True, gamma=gamma)
         self.observation_space, self.action_space, self.venv = _Box(dims.obs), _Box(dims.act), self
 
@@ -136,13 +136,14 @@ def test_fused_rollout_loop_equals_host_normalised_loop(tmp_path):
     """mopg_population_update with the normalisation on the device (raw simulator output -> K6 -> K1 per step) produces
     the SAME offspring -- parameters, Adam state and running moments bit for bit -- as the loop that normalises on the
     host the way the reference does"""
+    import synth_envs
     from pgmorl_b200 import mopg, synthetic, warm_up
     from pgmorl_b200.layout import NetDims
     from pgmorl_b200.sample import Task
     d = NetDims(17, 6, 2)
-    args = synthetic.run_args_2d(str(tmp_path), T=32, N=4)
+    args = synth_envs.run_args_2d(str(tmp_path), T=32, N=4)
     mopg.set_env_hooks(make_vec_envs=lambda **kw: _HostNormalised(_RawEnv(args.num_processes, d.obs, d.obj), d, args.gamma),
-                       gym_make=lambda name: synthetic.ToyEvalEnv(d), make_raw_vec_envs=False)
+                       gym_make=lambda name: synth_envs.ToyEvalEnv(d), make_raw_vec_envs=False)
     torch.manual_seed(0)
     elites, scals = warm_up.initialize_warm_up_batch(args, "cuda")
     tasks = [Task(e, s) for e, s in zip(elites[:3], scals[:3])]

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import synth_envs
 from pgmorl_b200 import synthetic
 from pgmorl_b200.prediction import GraphView, fit_inputs
 from tests.helpers import rebuild_selection_state
@@ -44,7 +45,7 @@ def test_population_update_matches_reference(name, M):
         args, graph, pop, ep = rebuild_selection_state(z, g - 1, M)
         n_prev_nodes = len(z[f"g{g - 1}_graph_objs"])
         O = z[f"g{g}_graph_objs"]
-        offspring = [synthetic.ObjSample(O[i].copy(), i) for i in range(n_prev_nodes, len(O))]   # one node per task
+        offspring = [synth_envs.ObjSample(O[i].copy(), i) for i in range(n_prev_nodes, len(O))]   # one node per task
         pop.update(offspring)
         assert [s.optgraph_id for s in pop.sample_batch] == z[f"g{g}_pop_ids"].tolist()
 
