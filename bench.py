@@ -158,6 +158,7 @@ class GenerationBoundary:
         self.gen = 0
         self.n_state = pdist.sample_state_len(d)
         self.picks = []
+        self._next_objs = None
         if cpu:   # CPU arm: the archive's dominance filter and the selection come from the oracle (no GPU visible)
             from oracle import selection_oracle as so
             from pgmorl_b200 import ep as ep_mod
@@ -189,7 +190,7 @@ class GenerationBoundary:
                 raise NotImplementedError("CPU boundary: 2-objective configs only")
             if len(tw) == 0:
                 continue
-            theta = [so.fit_scipy(x, y, w, ub)[0] for x, y, w, ub in fit_inputs(view, s.optgraph_id, M, False)]
+            theta = [so.fit_scipy(x, y, w, ub).x for x, y, w, ub in fit_inputs(view, s.optgraph_id, M, False)]
             t = np.array(tw, dtype=np.float64)
             t = t / t.sum(axis=1, keepdims=True)
             pred = view.objs[s.optgraph_id][None, :] + np.stack([model(t[:, m], *theta[m]) for m in range(M)], axis=1)
@@ -205,14 +206,22 @@ class GenerationBoundary:
             elites.append(cands[int(b)][0]); scals.append(sc)
         return elites, scals
 
+    def prepare(self):
+        """Stand-in for the evaluation episodes of the generation that is about to close (host work during the
+        iterations, outside this path's scope): the synthetic objective vectors of this rank's tasks. Not timed."""
+        self._next_objs = [self._objs(i) for i in self.mine]
+
     def run(self):
         """One generation boundary; returns the seconds spent in (exchange, bookkeeping, selection, migration)."""
         import synth_envs
         import torch
         pd, M, W, rank = self.pd, self.M, self.W, self.rank
+        if self._next_objs is None:
+            self.prepare()
         t0 = time.perf_counter()
         local = pd.pack_records(self.mine, [self.elites[i].optgraph_id for i in self.mine],
-                                [self.weights[i] for i in self.mine], [self._objs(i) for i in self.mine])
+                                [self.weights[i] for i in self.mine], self._next_objs)
+        self._next_objs = None
         table = pd.all_gather_records(local, self.n_tasks)
         t1 = time.perf_counter()
         all_samples, offspring = [], []
@@ -424,18 +433,27 @@ def api_leg(d, P, T, N, E, B, gamma, device, cluster):
         s = Sample({k: getattr(env, k) for k in ("ob_rms", "ret_rms", "obj_rms")}, ac, agent, objs=np.ones(d.obj), optgraph_id=0)
         tasks.append(Task(s, WeightedSumScalarization(num_objs=d.obj, weights=w[p % len(w)])))
     out = {}
-    times = []
-    for it in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        mopg.mopg_population_update(args, tasks, device, it, 1, cluster=cluster)
-        torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    ms = 1e3 * min(times[1:])
-    out["host_normalised"] = {"ms_per_iteration": ms, "env_steps_per_s": P * T * N / (ms * 1e-3),
-                              "us_per_env_time_step": 1e3 * ms / T}
-    out["note"] = ("wall clock of mopg_population_update(num_updates=1) incl. the replay environments' Python stepping, "
-                   "the per-iteration Sample snapshots and one toy evaluation episode per task; best of 2 after 1 warm-up")
+    for mode in ("host_normalised", "device_normalised"):
+        if mode == "device_normalised":       # raw simulator output, running normalisation on the device (K6)
+            mopg.set_env_hooks(make_raw_vec_envs=lambda **kw: synth_envs.RawReplayVecEnv(trajs[next(order) % P], d))
+        rows = []
+        for it in range(3):
+            stats = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mopg.mopg_population_update(args, tasks, device, it, 1, cluster=cluster, stats=stats)
+            torch.cuda.synchronize()
+            rows.append((time.perf_counter() - t0, stats["env_s"], stats["eval_s"]))
+        wall, env_s, eval_s = min(rows[1:])
+        ms = 1e3 * (wall - env_s - eval_s)
+        out[mode] = {"ms_per_iteration": 1e3 * wall, "ms_in_env_step_calls": 1e3 * env_s, "ms_in_evaluation": 1e3 * eval_s,
+                     "ms_excluding_env_and_evaluation": ms, "env_steps_per_s_excluding_env": P * T * N / (ms * 1e-3),
+                     "us_per_env_time_step_excluding_env": 1e3 * ms / T}
+    mopg.set_env_hooks(make_raw_vec_envs=False)
+    out["note"] = ("wall clock of mopg_population_update(num_updates=1): per environment step ONE CUDA-graph replay (H2D of the "
+                   "staged step, [K6,] K1 into the rollout slot, D2H of the actions) + stream synchronise for all tasks, then K2 / "
+                   "K3, the Sample snapshots and one toy evaluation episode per task; the Python time inside the replay "
+                   "environments' step() and the evaluation episodes is reported separately; best of 2 after 1 warm-up")
     return out
 
 
@@ -564,13 +582,21 @@ def main():
 
     def boundary(i):
         if gb is not None and (i + 1) % GEN_ITERS == 0:
+            # the boundary consumes the finished generation (the objectives come from evaluating the final policies):
+            # wait for the queued iterations first so that the host-side breakdown below is the boundary's own time
+            torch.cuda.synchronize()
             bnd_log.append(gb.run())
+
+    def prepare(i):
+        if gb is not None and (i + 1) % GEN_ITERS == 0:
+            gb.prepare()
 
     def run_device(steps):
         """-> (device ms per step incl. boundaries, device ms per step of the MOPG part alone)"""
         marks = []
         for i in range(steps):
             flush.fill_(i & 0xFF)                      # evict L2 between timed iterations (not timed)
+            prepare(i)
             s, m, e = ev(), ev(), ev()
             s.record()
             pop.step()
@@ -588,6 +614,7 @@ def main():
         tot = mopg = 0.0
         for i in range(steps):
             flush.fill_(i & 0xFF)
+            prepare(i)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             pop.step_from_staged(snapshot_slot=i)
@@ -621,7 +648,7 @@ def main():
     run_device(max(args.warmup, 3))
     run_e2e(3)
     if gb is not None:
-        gb.run()                       # one untimed boundary: K4 / K5 / NCCL warm-up
+        gb.run(); gb.run()             # two untimed boundaries: K4 / K5 / NCCL warm-up (lazy module loading, communicator)
     bnd_log.clear()
     clocks = ClockSampler(local_rank)
     barrier()
@@ -640,6 +667,7 @@ def main():
     gen = None
     if gb is not None:
         bnd_log.clear()
+        gb.prepare()
         barrier()
         tg0 = time.perf_counter()
         for i in range(GEN_ITERS):

@@ -72,6 +72,22 @@ int pgm_policy_forward_f32(const float *params, const float *obs, const float *e
                            float *action, float *value, float *logp, int mode, int P, int rows_v,
                            int rows_a, int O, int A, int M, void *stream);
 
+/* K1 in per-step mode for real environment loops (morl/mopg.py:103-135: one Policy.act per environment step): every
+ * task's N current observations -> value / sampled action / log-prob written STRAIGHT INTO time slot t of the rollout
+ * buffers (what RolloutStorage.insert does, a2c/storage.py:50-62), plus a dense copy of the actions for the host.
+ *   ctl      [2] int32 in DEVICE memory: {t, sample}. sample = 0: value only (the bootstrap get_value of mopg.py:132-135).
+ *            Read by the kernel, so ONE captured CUDA graph (H2D of the staged step -> this launch -> D2H of the
+ *            actions) serves every step of every iteration.
+ *   obs_stage [P,N,O] dense block of this step's observations, copied by the kernel into slot t of obs_buf; or NULL:
+ *            the observations are already in slot t of obs_buf (written there by K6, pgm_vecnorm_step_f64).
+ *   eps      [P or 1, N, A] N(0,1) draws of this step
+ *   obs_buf [P,(T+1)N,O], value_buf [P,(T+1)N,M], action_buf [P,TN,A], logp_buf [P,TN]: rollout buffers, row = t*N + n,
+ *            task strides in elements;  act_out [P,N,A] dense (may be NULL). */
+int pgm_policy_step_f32(const float *params, const int32_t *ctl, const float *obs_stage, const float *eps,
+                        int eps_shared, float *obs_buf, size_t obs_task_stride, float *value_buf,
+                        size_t value_task_stride, float *action_buf, size_t action_task_stride, float *logp_buf,
+                        size_t logp_task_stride, float *act_out, int P, int N, int O, int A, int M, void *stream);
+
 /* ---------------------------------------------------------------------------
  * K2  vector-reward GAE + scalarised, normalised advantage.
  * Replaces RolloutStorage.compute_returns, branch use_gae && use_proper_time_limits
@@ -207,28 +223,20 @@ int pgm_vecnorm_step_f64(const double *raw_obs, const double *raw_rew, const dou
                          float *mask_out, size_t mask_task_stride, double gamma, double clipob, double cliprew,
                          double epsilon, int update, int reset, int P, int N, int O, int M, void *stream);
 
-/* ---------------------------------------------------------------------------
- * Self-test of the tcgen05 (5th-generation tensor core) building blocks of the K3 tensor-core path
- * (csrc/tc.cuh): TF32 UMMA through every shared-memory operand view K3 uses, TMEM load/store, the 3-way
- * TF32 split. No reference counterpart (the reference runs torch-CPU GEMMs, algo/ppo.py:62-107).
- * out [n_out >= 16] device floats: [0..4] max |error| of five exact integer GEMMs (must be 0),
- * [5] 1xTF32 / [6] 3xTF32 / [7] FP32-FMA relative error vs FP64, [8] 0 = inputs truncated, 1 = rounded,
- * [9],[10] cycles for 1 / 24 MMAs issue->complete, [11] TMEM load cycles, [12] TMEM store/load error. */
-int pgm_tc_selftest(float *out, int n_out, void *stream);
-
-/* Layout-discovery aid for the same building blocks: ONE tf32 MMA (K = 8) with caller-chosen descriptor strides;
- * out [128 * N] receives the raw TMEM accumulator (lane-major). fill 0 = operand words hold their word index,
- * fill 1 = K-major identity image with R rows; ltA/ltB = descriptor layout type; a_tmem: A operand from TMEM; kind 0 = tf32, 1 = f16 (K = 16,
- * operands filled per halfword); offA/offB = byte offsets added to the operand start addresses. Used by profiles/tc_layout_probe.py only. */
-int pgm_tc_layout_probe(float *out, int M, int N, int a_mn, int b_mn, int fillA, int fillB, int RA, int RB,
-                        int lboA, int sboA, int lboB, int sboB, int d_lane_off, int ltA, int ltB, int a_tmem,
-                        int kind, int offA, int offB, void *stream);
-
-/* MMA pacing microbenchmark (profiles/tc_mma_bench.py): nmma kind::f16 MMAs (M x N x 16) from zero-filled
- * SWIZZLE_128B images, rotating over nacc accumulators, operand start addresses advancing by a_step / b_step bytes.
- * out [6] floats: per repetition {cycles issue..complete, cycles spent issuing}. */
-int pgm_tc_mma_bench(float *out, int M, int N, int a_mn, int b_mn, int nmma, int nacc, int a_step, int b_step,
-                     void *stream);
+/* K6 in rollout-slot mode (one captured CUDA graph per environment step, together with pgm_policy_step_f32): the staged
+ * block holds the simulators' answer to the actions of time slot t-1; with ctl = {t, flags} in DEVICE memory (flags bit 1
+ * set) the kernel writes the normalised next observation into slot t of obs_buf [P,(T+1)N,O], the normalised reward
+ * vector into slot t-1 of rewards_buf [P,T,N,M], 1 - done into slot t of masks_buf [P,(T+1),N] and bad_in [P,N] into slot t
+ * of bad_masks_buf (what RolloutStorage.insert stores, a2c/storage.py:50-62); flags bit 1 clear: no-op (t = 0).
+ * Moments and arithmetic exactly as pgm_vecnorm_step_f64. */
+int pgm_vecnorm_rollout_step_f64(const int32_t *ctl, const double *raw_obs, const double *raw_rew, const double *raw_obj,
+                                 const uint8_t *done, const float *bad_in, double *ob_mean, double *ob_var,
+                                 double *ob_count, double *ret_acc, double *ret_stat, double *obj_acc,
+                                 int32_t *obj_started, double *obj_mean, double *obj_var, double *obj_count,
+                                 float *obs_buf, size_t obs_task_stride, float *rewards_buf, size_t rewards_task_stride,
+                                 float *masks_buf, size_t masks_task_stride, float *bad_masks_buf,
+                                 size_t bad_masks_task_stride, double gamma, double clipob, double cliprew,
+                                 double epsilon, int update, int P, int N, int O, int M, void *stream);
 
 #ifdef __cplusplus
 }

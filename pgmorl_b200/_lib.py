@@ -37,6 +37,7 @@ SIGNATURES = {
     "pgm_last_error": (C.c_char_p, []),
     "pgm_n_par": (_I, [_I, _I, _I]),
     "pgm_policy_forward_f32": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "pgm_policy_step_f32": (_I, [_P, _P, _P, _P, _I, _P, _Z, _P, _Z, _P, _Z, _P, _Z, _P, _I, _I, _I, _I, _I, _P]),
     "pgm_gae_adv_f32": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _I, _P]),
     "pgm_ppo_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "pgm_ppo_update_f32": (_I, [_P, _P, _P, _P, _P, _P, _Z, _P, _P, _P, _Z, _P, _P, _P, _I, _I, _I,
@@ -47,12 +48,40 @@ SIGNATURES = {
     "pgm_select_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "pgm_select_greedy_f64": (_I, [_P, _I, _P, _I, _I, C.c_double, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "pgm_vecnorm_step_f64": (_I, [_P] * 14 + [_P, _Z, _P, _Z, _P, _Z] + [C.c_double] * 4 + [_I] * 6 + [_P]),
-    "pgm_tc_selftest": (_I, [_P, _I, _P]),
-    "pgm_tc_mma_bench": (_I, [_P] + [_I] * 8 + [_P]),
-    "pgm_tc_layout_probe": (_I, [_P] + [_I] * 19 + [_P]),
+    "pgm_vecnorm_rollout_step_f64": (_I, [_P] * 16 + [_P, _Z, _P, _Z, _P, _Z, _P, _Z] + [C.c_double] * 4 + [_I] * 5 + [_P]),
     "pgm_ppo_grad_f32": (_I, [_P, _P, _Z, _P, _P, _P, _Z, _P, _P, _P, _I, C.POINTER(PpoHyper), _P, _P, _P,
                               _Z, _I, _I, _I, _I, _I, _I, _P]),
 }
+
+
+# diagnostics library (include/pgmorl_b200_diag.h): tcgen05 self-test / layout probe / MMA pacing; tests and profiles only
+DIAG_LIB_PATH = os.environ.get("PGM_DIAG_LIB_PATH", os.path.join(HERE, "libpgmorl_b200_diag.so"))
+DIAG_SIGNATURES = {
+    "pgm_tc_selftest": (_I, [_P, _I, _P]),
+    "pgm_tc_mma_bench": (_I, [_P] + [_I] * 8 + [_P]),
+    "pgm_tc_layout_probe": (_I, [_P] + [_I] * 19 + [_P]),
+}
+_diag = None
+
+
+def diag_lib():
+    """Load (once) the diagnostics library. Not used by the product path."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise PgmError(f"{DIAG_LIB_PATH} is missing: build it with `python -m pgmorl_b200.build`")
+        l = C.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in DIAG_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        l.pgm_last_error.restype = C.c_char_p
+        _diag = l
+    return _diag
+
+
+def check_diag(rc):
+    if rc != 0:
+        raise PgmError(f"pgmorl_b200 (diag) error {rc}: {diag_lib().pgm_last_error().decode()}")
 
 
 def lib():

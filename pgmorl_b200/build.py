@@ -13,6 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpgmorl_b200.so")
+OUT_DIAG = os.path.join(HERE, "libpgmorl_b200_diag.so")      # csrc/diag/*.cu + capi.cu: tcgen05 self-test / probes
 OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -23,9 +24,15 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def diag_sources():
+    d = os.path.join(CSRC, "diag")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu"))
+
+
 def deps():
     hdr = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     hdr.append(os.path.join(HERE, "..", "include", "pgmorl_b200.h"))
+    hdr.append(os.path.join(HERE, "..", "include", "pgmorl_b200_diag.h"))
     return hdr
 
 
@@ -50,7 +57,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdr = deps()
     jobs = []
-    for src in sources():
+    for src in sources() + diag_sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if force or _stale(obj, [src] + hdr):
             jobs.append((src, obj))
@@ -77,6 +84,12 @@ def build(force=False, verbose=False):
         r = subprocess.run([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    # diagnostics library: the probes + the error helpers of capi.cu, nothing of the product kernels
+    dobjs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in diag_sources()] + [os.path.join(OBJ, "capi.o")]
+    if force or jobs or _stale(OUT_DIAG, dobjs):
+        r = subprocess.run([NVCC, "-shared", "-o", OUT_DIAG] + dobjs + ["-lcudart"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link (diag) failed:\n" + r.stdout + r.stderr)
     return OUT
 
 

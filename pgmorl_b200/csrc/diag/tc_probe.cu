@@ -1,11 +1,13 @@
 // Self-test of the tcgen05 building blocks in tc.cuh: one CTA runs small TF32 GEMMs through every operand
 // view the K3 tensor-core kernel relies on (chunk images as K-major and MN-major A / B, N = 16 / 32 / 64,
 // accumulate flag, 3-way TF32 split) and checks them on the device against plain FP32/FP64 loops.
-// Exposed as pgm_tc_selftest (include/pgmorl_b200.h); tests/test_gpu_tc.py asserts on the result vector.
+// Exposed as pgm_tc_selftest by the DIAGNOSTIC library libpgmorl_b200_diag.so (include/pgmorl_b200_diag.h), not by the
+// product library; tests/test_gpu_tc.py asserts on the result vector.
 #include <cuda_fp16.h>
 
-#include "common.cuh"
-#include "tc.cuh"
+#include "../../../include/pgmorl_b200_diag.h"
+#include "../common.cuh"
+#include "../tc.cuh"
 
 namespace pgm {
 

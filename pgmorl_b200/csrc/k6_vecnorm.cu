@@ -28,6 +28,12 @@ struct K6Args {
     size_t obs_ts, obj_ts, mask_ts;
     double gamma, clipob, cliprew, epsilon;
     int update, reset, P, N, O, M;
+    // rollout-slot mode (pgm_vecnorm_rollout_step_f64): outputs are whole rollout buffers and the time slot comes from
+    // the device control word {t, flags}; flags bit 1 clear = nothing to normalise this step (t = 0)
+    const int32_t *ctl;
+    const float *bad_in;
+    float *bad_out;
+    size_t bad_ts;
 };
 
 // update_mean_var_count_from_moments (running_mean_std.py:20-31), same operation order
@@ -66,9 +72,18 @@ __device__ __forceinline__ double np_pairwise(F at, int n) {
 template <typename F>
 __device__ __forceinline__ double np_sum1d(F at, int n) { return np_pairwise(at, n); }
 
-__global__ void __launch_bounds__(128) k6_vecnorm_kernel(const K6Args a) {
+__global__ void __launch_bounds__(128) k6_vecnorm_kernel(K6Args a) {
     const int p = blockIdx.x, tid = threadIdx.x, N = a.N, O = a.O, M = a.M;
     const double dN = (double)N;
+    if (a.ctl) {      // the staged block holds the simulators' answer to the actions of slot t-1
+        if (!(__ldg(a.ctl + 1) & 2)) return;
+        const int t = __ldg(a.ctl);
+        a.obs_out += (size_t)t * N * O;               // next observation          -> slot t   (storage.py:51)
+        a.obj_out += (size_t)(t - 1) * N * M;         // reward vector of the step -> slot t-1 (storage.py:57)
+        a.mask_out += (size_t)t * N;                  // masks / bad_masks         -> slot t   (storage.py:58-59)
+        if (a.bad_out)
+            for (int n = tid; n < N; n += blockDim.x) a.bad_out[(size_t)p * a.bad_ts + (size_t)t * N + n] = a.bad_in[(size_t)p * N + n];
+    }
 
     // ---- observations: _obfilt (a2c/envs.py:202-211) ----
     {
@@ -195,6 +210,37 @@ extern "C" int pgm_vecnorm_step_f64(const double *raw_obs, const double *raw_rew
     a.obs_ts = obs_task_stride; a.obj_ts = obj_task_stride; a.mask_ts = mask_task_stride;
     a.gamma = gamma; a.clipob = clipob; a.cliprew = cliprew; a.epsilon = epsilon;
     a.update = update; a.reset = reset; a.P = P; a.N = N; a.O = O; a.M = M;
+    a.ctl = nullptr; a.bad_in = nullptr; a.bad_out = nullptr; a.bad_ts = 0;
+    k6_vecnorm_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(a);
+    PGM_CUDA(cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_vecnorm_rollout_step_f64(const int32_t *ctl, const double *raw_obs, const double *raw_rew, const double *raw_obj,
+                                            const uint8_t *done, const float *bad_in, double *ob_mean, double *ob_var,
+                                            double *ob_count, double *ret_acc, double *ret_stat, double *obj_acc,
+                                            int32_t *obj_started, double *obj_mean, double *obj_var, double *obj_count,
+                                            float *obs_buf, size_t obs_task_stride, float *rewards_buf, size_t rewards_task_stride,
+                                            float *masks_buf, size_t masks_task_stride, float *bad_masks_buf,
+                                            size_t bad_masks_task_stride, double gamma, double clipob, double cliprew,
+                                            double epsilon, int update, int P, int N, int O, int M, void *stream) {
+    PGM_REQUIRE(P >= 1 && N >= 1 && N <= 128 && O >= 1 && M >= 1, "vecnorm: bad sizes P=%d N=%d O=%d M=%d (N <= 128)", P, N, O, M);
+    PGM_REQUIRE(ctl && raw_obs && raw_obj && done && obs_buf && rewards_buf && masks_buf && obj_acc && obj_started,
+                "vecnorm (rollout step): null pointer argument");
+    PGM_REQUIRE((bad_in == nullptr) == (bad_masks_buf == nullptr), "vecnorm (rollout step): bad_in / bad_masks_buf go together");
+    PGM_REQUIRE((ob_mean == nullptr) == (ob_var == nullptr) && (ob_mean == nullptr) == (ob_count == nullptr),
+                "vecnorm: ob_mean / ob_var / ob_count go together");
+    PGM_REQUIRE((obj_mean == nullptr) == (obj_var == nullptr) && (obj_mean == nullptr) == (obj_count == nullptr),
+                "vecnorm: obj_mean / obj_var / obj_count go together");
+    K6Args a;
+    a.raw_obs = raw_obs; a.raw_rew = raw_rew; a.raw_obj = raw_obj; a.done = done;
+    a.ob_mean = ob_mean; a.ob_var = ob_var; a.ob_count = ob_count; a.ret_acc = ret_acc; a.ret_stat = ret_stat;
+    a.obj_acc = obj_acc; a.obj_mean = obj_mean; a.obj_var = obj_var; a.obj_count = obj_count; a.obj_started = obj_started;
+    a.obs_out = obs_buf; a.obj_out = rewards_buf; a.mask_out = masks_buf;
+    a.obs_ts = obs_task_stride; a.obj_ts = rewards_task_stride; a.mask_ts = masks_task_stride;
+    a.gamma = gamma; a.clipob = clipob; a.cliprew = cliprew; a.epsilon = epsilon;
+    a.update = update; a.reset = 0; a.P = P; a.N = N; a.O = O; a.M = M;
+    a.ctl = ctl; a.bad_in = bad_in; a.bad_out = bad_masks_buf; a.bad_ts = bad_masks_task_stride;
     k6_vecnorm_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(a);
     PGM_CUDA(cudaGetLastError());
     return PGM_OK;

@@ -52,6 +52,21 @@ def policy_forward(params, obs, dims: NetDims, eps=None, action=None, mode=ACT_S
     return value, act_out, logp
 
 
+def policy_step(params, ctl, obs_stage, eps, obs_buf, value_buf, action_buf, logp_buf, act_out, N, dims: NetDims):
+    """K1 per-step mode (pgm_policy_step_f32): value / action / log-prob of every task's N current observations written
+    into time slot ctl[0] of the rollout buffers; ctl = int32 [2] on the device {t, sample flag}."""
+    P = params.shape[0]
+    assert ctl.is_cuda and ctl.dtype == torch.int32 and ctl.numel() >= 2
+    for n, t in (("params", params), ("obs_stage", obs_stage), ("eps", eps), ("obs_buf", obs_buf), ("value_buf", value_buf),
+                 ("action_buf", action_buf), ("logp_buf", logp_buf), ("act_out", act_out)):
+        _f32c(t, n)
+    assert eps.shape[-2:] == (N, dims.act) and eps.shape[0] in (1, P)
+    check(lib().pgm_policy_step_f32(ptr(params), ptr(ctl), ptr(obs_stage), ptr(eps), int(eps.shape[0] == 1 and P > 1),
+                                    ptr(obs_buf), obs_buf.stride(0), ptr(value_buf), value_buf.stride(0),
+                                    ptr(action_buf), action_buf.stride(0), ptr(logp_buf), logp_buf.stride(0), ptr(act_out),
+                                    P, N, dims.obs, dims.act, dims.obj, _stream()))
+
+
 def gae_adv(rewards, value, masks, bad_masks, gamma, lam, weights=None, obj_var=None, out=None):
     """K2. rewards [P,T,N,M]; value [P,T+1,N,M]; masks/bad_masks [P,T+1,N]; weights/obj_var [P,M].
     Returns (returns [P,T,N,M], adv [P,T,N] or None)."""

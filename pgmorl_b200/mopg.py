@@ -196,24 +196,68 @@ def MOPG_worker(args, task_id, task, device, iteration, num_updates, start_time,
     done_event.wait()
 
 
-def _population_update_raw(args, task_batch, pop, device, start_iter, final_iter, total_num_updates):
+_POP_CACHE = {}
+
+
+def _population(dims, P, args, hyper, dev, cluster):
+    """The device-resident population shard of this (shape, size, schedule): rollout buffers, K3 workspace, pinned staging
+    and the captured per-step graphs are allocated ONCE and reused by every generation."""
+    from .rollout import StepPipe
+    key = (dims, P, args.num_steps, args.num_processes, args.ppo_epoch, args.num_mini_batch, args.gamma, args.gae_lambda,
+           str(dev), cluster)
+    hit = _POP_CACHE.get(key)
+    if hit is None:
+        if len(_POP_CACHE) >= 4:                       # a run alternates between at most a few shard sizes
+            _POP_CACHE.pop(next(iter(_POP_CACHE)))
+        pop = PopulationMOPG(dims, P, args.num_steps, args.num_processes, ppo_epoch=args.ppo_epoch,
+                             num_mini_batch=args.num_mini_batch, gamma=args.gamma, gae_lambda=args.gae_lambda,
+                             hyper=hyper, device=dev, cluster=cluster)
+        hit = _POP_CACHE[key] = {"pop": pop, "pipe": StepPipe(pop), "raw": None}
+    hit["pop"].hyper = hyper
+    return hit
+
+
+def _snapshot_samples(task_batch, pop, lr, env_params_of):
+    """One Sample per task from the device state (mopg.py:146-149): the policy / Adam tensors are clones of the shard's
+    rows, everything else is copied from the task's sample."""
+    out = []
+    step = pop.adam_step.tolist()
+    for p, task in enumerate(task_batch):
+        ac, agent = deepcopy(task.sample.actor_critic), deepcopy(task.sample.agent)
+        ac.flat = pop.params[p].clone()
+        agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
+        agent.optimizer.step_count = int(step[p])
+        agent.optimizer.param_groups[0]['lr'] = lr
+        out.append(Sample(env_params_of(p), ac, agent))
+    return out
+
+
+def _population_update_raw(args, task_batch, cache, device, start_iter, final_iter, total_num_updates, stats):
     """The rollout loop of `mopg_population_update` with the normalisation on the device: the host only steps the raw
-    simulators; K6 turns their output into the normalised observation / reward / mask slots of the rollout buffers and
-    K1 reads the observation from there."""
+    simulators; per environment step ONE graph replay (rollout.StepPipe) uploads their answer, K6 turns it into the
+    normalised observation / reward / mask slots of the rollout buffers and K1 acts on the new observation."""
+    from .rollout import StepPipe
     from .vec_normalize import DeviceVecNormalize
+    pop = cache["pop"]
     P, T, N, M = len(task_batch), args.num_steps, args.num_processes, args.obj_num
     dims = pop.dims
     kw = dict(env_name=args.env_name, seed=args.seed, num_processes=N, gamma=args.gamma, log_dir=None, device=device,
               allow_early_resets=False, obj_rms=args.obj_rms, ob_rms=args.ob_rms)
     envs_all = [_HOOKS["make_raw_vec_envs"](**kw) for _ in task_batch]
     # a2c/envs.py:86-91: VecNormalize(ret=False) without a discount, else VecNormalize(gamma=...); ob / obj moments optional
-    vn = DeviceVecNormalize(P, N, dims.obs, M, ob=args.ob_rms, ret=args.gamma is not None, obj_rms=args.obj_rms,
-                            gamma=args.gamma if args.gamma is not None else 0.99, device=pop.device)
+    sig = (bool(args.ob_rms), args.gamma is not None, bool(args.obj_rms), args.gamma)
+    if cache["raw"] is None or cache["raw"]["sig"] != sig:
+        vn = DeviceVecNormalize(P, N, dims.obs, M, ob=args.ob_rms, ret=args.gamma is not None, obj_rms=args.obj_rms,
+                                gamma=args.gamma if args.gamma is not None else 0.99, device=pop.device)
+        cache["raw"] = {"sig": sig, "vn": vn, "pipe": StepPipe(pop, vn)}
+    vn, pipe = cache["raw"]["vn"], cache["raw"]["pipe"]
+    vn.reset_state()
     for p, task in enumerate(task_batch):
         vn.load_task(p, task.sample.env_params)
     vn.reset(np.stack([np.asarray(e.reset(), dtype=np.float64) for e in envs_all]), pop.obs[:, 0:N])
     offspring = [[] for _ in range(P)]
-    bad = torch.empty(P, N, pin_memory=True)
+    raw_obs, raw_rew, raw_obj = pipe.h_raw_obs.numpy(), pipe.h_raw_rew.numpy(), pipe.h_raw_obj.numpy()
+    done_h, bad_h = pipe.h_done.numpy(), pipe.h_bad.numpy()
     for j in range(start_iter, final_iter):
         torch.manual_seed(j)
         lr = args.lr - (args.lr * ((j * args.lr_decay_ratio) / float(total_num_updates))) if args.use_linear_lr_decay else args.lr
@@ -222,44 +266,47 @@ def _population_update_raw(args, task_batch, pop, device, start_iter, final_iter
         pop.bad_masks[:, 0] = 1.0 if j == start_iter else pop.bad_masks[:, T]
         if j > start_iter:
             pop.obs[:, 0:N].copy_(pop.obs[:, T * N:])                                               # after_update (storage.py:71-75)
-        for step in range(T):
-            eps_t = torch.empty(N, dims.act, dtype=torch.float64).normal_(0, 1)
-            act_host = pop.act_step_resident(step, eps_t).cpu()
-            raw = [envs.step(act_host[p]) for p, envs in enumerate(envs_all)]
-            for p, (_, _, _, infos) in enumerate(raw):
+        for step in range(T + 1):
+            # slot `step`: normalise the simulators' answer to the previous actions (none at step 0), then act on it
+            eps_t = torch.empty(N, dims.act, dtype=torch.float64).normal_(0, 1) if step < T else None
+            act_host = pipe.step(step, eps_t, sample=step < T, normalise=step > 0)
+            if step == T:
+                break
+            t0 = time.perf_counter()
+            for p, envs in enumerate(envs_all):
+                ob, rew, done, infos = envs.step(act_host[p])
+                raw_obs[p] = ob
+                raw_rew[p] = np.asarray(rew, dtype=np.float64).reshape(N)
+                done_h[p] = done
                 for n, info in enumerate(infos):
-                    bad[p, n] = 0.0 if 'bad_transition' in info.keys() else 1.0
-            vn.step(np.stack([np.asarray(r[0], dtype=np.float64) for r in raw]),
-                    np.stack([np.asarray(r[1], dtype=np.float64).reshape(N) for r in raw]),
-                    np.stack([np.stack([np.asarray(i['obj'], dtype=np.float64) for i in r[3]]) for r in raw]),
-                    np.stack([np.asarray(r[2], dtype=bool) for r in raw]),
-                    pop.obs[:, (step + 1) * N:(step + 2) * N], pop.rewards[:, step], pop.masks[:, step + 1])
-            pop.bad_masks[:, step + 1].copy_(bad)
-        pop.finish_rollout_resident()
+                    raw_obj[p, n] = info['obj']
+                    bad_h[p, n] = 0.0 if 'bad_transition' in info.keys() else 1.0
+            stats["env_s"] += time.perf_counter() - t0
+        vn.mark_stepped()
         if vn.has_obj:
             pop.obj_var.copy_(vn.obj_var.to(torch.float32))
         else:
             pop.obj_var.fill_(1.0 - 1e-8)
         pop.perm.copy_(torch.stack([torch.randperm(T * N) for _ in range(args.ppo_epoch)]).to(torch.int32)[None])
         pop.update_only()
-        for p, task in enumerate(task_batch):
-            ac, agent = deepcopy(task.sample.actor_critic), deepcopy(task.sample.agent)
-            ac.flat = pop.params[p].clone()
-            agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
-            agent.optimizer.step_count = int(pop.adam_step[p])
-            agent.optimizer.param_groups[0]['lr'] = lr
-            offspring[p].append(Sample(vn.snapshot(p), ac, agent))
-        for p, objs in enumerate(evaluation_batch(args, [off[-1] for off in offspring])):
-            offspring[p][-1].objs = objs
+        new = _snapshot_samples(task_batch, pop, lr, vn.snapshot)
+        t0 = time.perf_counter()
+        for p, objs in enumerate(evaluation_batch(args, new)):
+            new[p].objs = objs
+            offspring[p].append(new[p])
+        stats["eval_s"] += time.perf_counter() - t0
     for envs in envs_all:
         envs.close()
     return offspring
 
 
-def mopg_population_update(args, task_batch, device, iteration, num_updates, start_time=None, cluster=0):
+def mopg_population_update(args, task_batch, device, iteration, num_updates, start_time=None, cluster=0, stats=None):
     """All tasks of this shard advance together; returns offspring[task_id] = list of Samples (one per iteration),
-    the content the reference's workers put on the queue (morl/morl.py:93-99)."""
+    the content the reference's workers put on the queue (morl/morl.py:93-99). `stats` (optional dict) receives the
+    seconds spent inside the environments' step() calls (`env_s`) and in the evaluation episodes (`eval_s`)."""
     P = len(task_batch)
+    stats = stats if stats is not None else {}
+    stats.setdefault("env_s", 0.0); stats.setdefault("eval_s", 0.0)
     first = task_batch[0].sample.actor_critic
     dims, dev = first.dims, first.flat.device
     total_num_updates = int(args.num_env_steps) // args.num_steps // args.num_processes
@@ -267,9 +314,8 @@ def mopg_population_update(args, task_batch, device, iteration, num_updates, sta
     g0 = ag0.optimizer.param_groups[0]
     hyper = PpoHyper(ag0.clip_param, ag0.value_loss_coef, ag0.entropy_coef, ag0.max_grad_norm, g0["betas"][0],
                      g0["betas"][1], g0["eps"])
-    pop = PopulationMOPG(dims, P, args.num_steps, args.num_processes, ppo_epoch=args.ppo_epoch,
-                         num_mini_batch=args.num_mini_batch, gamma=args.gamma, gae_lambda=args.gae_lambda,
-                         hyper=hyper, device=dev, cluster=cluster)
+    cache = _population(dims, P, args, hyper, dev, cluster)
+    pop, pipe = cache["pop"], cache["pipe"]
     envs_all = []
     raw_mode = _HOOKS["make_raw_vec_envs"] is not None
     for p, task in enumerate(task_batch):
@@ -285,43 +331,49 @@ def mopg_population_update(args, task_batch, device, iteration, num_updates, sta
         envs_all.append(envs)
     T, N, M = args.num_steps, args.num_processes, args.obj_num
     if raw_mode:
-        return _population_update_raw(args, task_batch, pop, device, iteration, min(iteration + num_updates, total_num_updates),
-                                      total_num_updates)
-    obs_now = torch.stack([torch.as_tensor(e.reset()).to(torch.float32) for e in envs_all])       # [P,N,O] host
+        return _population_update_raw(args, task_batch, cache, device, iteration, min(iteration + num_updates, total_num_updates),
+                                      total_num_updates, stats)
+    obs_h = pipe.h_obs.numpy()                                            # pinned [P,N,O]: this step's observations
+    rew_h, mask_h, bad_h = (pop.staging()[k].numpy() for k in ("rewards", "masks", "bad_masks"))   # pinned, whole rollout
+    for p, e in enumerate(envs_all):
+        obs_h[p] = np.asarray(e.reset(), dtype=np.float32)
     offspring = [[] for _ in range(P)]
     start_iter, final_iter = iteration, min(iteration + num_updates, total_num_updates)
     for j in range(start_iter, final_iter):
-        eps, perm = None, None
         torch.manual_seed(j)              # every task of a generation sees the same streams (mopg.py:96)
         lr = args.lr - (args.lr * ((j * args.lr_decay_ratio) / float(total_num_updates))) if args.use_linear_lr_decay else args.lr
         pop.set_lr(lr)
-        pop.masks[:, 0] = 1.0 if j == start_iter else pop.masks[:, T]
-        pop.bad_masks[:, 0] = 1.0 if j == start_iter else pop.bad_masks[:, T]
+        if j == start_iter:
+            mask_h[:, 0] = 1.0; bad_h[:, 0] = 1.0
+        else:                                                             # after_update (storage.py:71-75)
+            mask_h[:, 0] = mask_h[:, T]; bad_h[:, 0] = bad_h[:, T]
         for step in range(T):
             eps_t = torch.empty(N, dims.act, dtype=torch.float64).normal_(0, 1)
-            action = pop.act_step(step, obs_now, eps_t)                                             # K1, per-step mode
-            act_host = action.cpu()
+            act_host = pipe.step(step, eps_t)                             # one graph replay: H2D, K1 into slot `step`, D2H
+            t0 = time.perf_counter()
             for p, envs in enumerate(envs_all):
                 obs, _, done, infos = envs.step(act_host[p])
-                obs_now[p] = torch.as_tensor(obs).to(torch.float32)
-                pop.store_transition(p, step, np.stack([np.asarray(i['obj'], dtype=np.float64) for i in infos]),
-                                     [0.0 if d else 1.0 for d in done],
-                                     [0.0 if 'bad_transition' in i.keys() else 1.0 for i in infos])
-        pop.finish_rollout(obs_now)                                                                 # value of the last obs
+                obs_h[p] = np.asarray(obs, dtype=np.float32)
+                for n, info in enumerate(infos):
+                    rew_h[p, step, n] = info['obj']
+                    mask_h[p, step + 1, n] = 0.0 if done[n] else 1.0
+                    bad_h[p, step + 1, n] = 0.0 if 'bad_transition' in info.keys() else 1.0
+            stats["env_s"] += time.perf_counter() - t0
+        pipe.step(T, None, sample=False)                                  # value of the last obs (mopg.py:132-135)
+        # reward vectors / masks were only collected on the host during the rollout: one upload each before K2
+        for k in ("rewards", "masks", "bad_masks"):
+            getattr(pop, k).copy_(pop.staging()[k], non_blocking=True)
         for p, envs in enumerate(envs_all):
             var = envs.obj_rms.var if envs.obj_rms is not None else np.ones(M) - 1e-8
             pop.obj_var[p].copy_(torch.as_tensor(np.asarray(var, dtype=np.float64) * np.ones(M), dtype=torch.float32))
         pop.perm.copy_(torch.stack([torch.randperm(T * N) for _ in range(args.ppo_epoch)]).to(torch.int32)[None])
         pop.update_only()                                                                           # K2 + K3
-        for p, (task, envs) in enumerate(zip(task_batch, envs_all)):
-            ac, agent = deepcopy(task.sample.actor_critic), deepcopy(task.sample.agent)
-            ac.flat = pop.params[p].clone()
-            agent.optimizer.exp_avg, agent.optimizer.exp_avg_sq = pop.adam_m[p].clone(), pop.adam_v[p].clone()
-            agent.optimizer.step_count = int(pop.adam_step[p])
-            agent.optimizer.param_groups[0]['lr'] = lr
-            offspring[p].append(Sample(_snapshot_rms(envs), ac, agent))
-        for p, objs in enumerate(evaluation_batch(args, [off[-1] for off in offspring])):
-            offspring[p][-1].objs = objs
+        new = _snapshot_samples(task_batch, pop, lr, lambda p: _snapshot_rms(envs_all[p]))
+        t0 = time.perf_counter()
+        for p, objs in enumerate(evaluation_batch(args, new)):
+            new[p].objs = objs
+            offspring[p].append(new[p])
+        stats["eval_s"] += time.perf_counter() - t0
     for envs in envs_all:
         envs.close()
     return offspring

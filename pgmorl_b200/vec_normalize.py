@@ -22,6 +22,17 @@ class RunningMeanStd:
         self.mean, self.var, self.count = np.zeros(shape, 'float64'), np.ones(shape, 'float64'), epsilon
 
 
+def _rms_class():
+    """The class snapshots are made of: the reference's own `baselines.common.running_mean_std.RunningMeanStd` when that
+    package is importable, so that final/EP_env_params_*.pkl (morl/morl.py:228) resolves for the reference's tooling
+    without this package; the local stand-in (same attributes) otherwise."""
+    try:
+        from baselines.common.running_mean_std import RunningMeanStd as Ref
+        return Ref
+    except Exception:
+        return RunningMeanStd
+
+
 class DeviceVecNormalize:
     def __init__(self, P, N, obs_dim, obj_num, ob=True, ret=True, obj_rms=False, clipob=10., cliprew=10., gamma=0.99,
                  epsilon=1e-8, device="cuda"):
@@ -43,6 +54,21 @@ class DeviceVecNormalize:
         pin = lambda *s, dtype=torch.float64: torch.empty(*s, dtype=dtype, pin_memory=True)
         self._h = {"obs": pin(P, N, obs_dim), "rew": pin(P, N), "obj": pin(P, N, obj_num), "done": pin(P, N, dtype=torch.uint8)}
         self._d = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in self._h.items()}
+
+    def reset_state(self):
+        """Back to the state of a freshly constructed object (the shard's normaliser is reused by every generation)."""
+        self.ob_mean.zero_(); self.ob_var.fill_(1.0); self.ob_count.fill_(1e-4)
+        self.ret_acc.zero_()
+        self.ret_stat.copy_(torch.tensor([[0.0, 1.0, 1e-4]] * self.P, dtype=torch.float64))
+        self.obj_acc.zero_(); self.obj_started.zero_()
+        self.obj_mean.zero_(); self.obj_var.fill_(1.0); self.obj_count.fill_(1e-4)
+        self._obj_scalar = [True] * self.P
+        self.training = True
+
+    def mark_stepped(self):
+        """Steps were run through the rollout-slot entry point (rollout.StepPipe): obj_rms now has its vector shape."""
+        if self.has_obj:
+            self._obj_scalar = [False] * self.P
 
     def train(self):
         self.training = True
@@ -70,6 +96,7 @@ class DeviceVecNormalize:
     def snapshot(self, p):
         """-> {'ob_rms', 'ret_rms', 'obj_rms'} host copies for Sample.env_params (mopg.py:146-149)."""
         out = {'ob_rms': None, 'ret_rms': None, 'obj_rms': None}
+        RunningMeanStd = _rms_class()
         if self.has_ob:
             r = RunningMeanStd(shape=(self.O,))
             r.mean, r.var, r.count = self.ob_mean[p].cpu().numpy(), self.ob_var[p].cpu().numpy(), float(self.ob_count[p])

@@ -13,7 +13,7 @@ from pgmorl_b200 import _lib  # noqa: E402
 
 def run(M, N, a_mn, b_mn, fillA, fillB, RA, RB, lboA, sboA, lboB, sboB, lane_off=0, ltA=0, ltB=0, a_tmem=0):
     out = torch.zeros(128 * N, dtype=torch.float32, device="cuda")
-    _lib.check(_lib.lib().pgm_tc_layout_probe(_lib.ptr(out), M, N, a_mn, b_mn, fillA, fillB, RA, RB,
+    _lib.check_diag(_lib.diag_lib().pgm_tc_layout_probe(_lib.ptr(out), M, N, a_mn, b_mn, fillA, fillB, RA, RB,
                                               lboA, sboA, lboB, sboB, lane_off, ltA, ltB, a_tmem, None))
     torch.cuda.synchronize()
     return out.cpu().numpy().reshape(128, N)

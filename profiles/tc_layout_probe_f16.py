@@ -12,7 +12,7 @@ from pgmorl_b200 import _lib  # noqa: E402
 
 def run(M, N, a_mn, b_mn, fillA, fillB, RA, RB, lboA, sboA, lboB, sboB, ltA=0, ltB=0, offA=0, offB=0):
     out = torch.zeros(128 * N, dtype=torch.float32, device="cuda")
-    _lib.check(_lib.lib().pgm_tc_layout_probe(_lib.ptr(out), M, N, a_mn, b_mn, fillA, fillB, RA, RB,
+    _lib.check_diag(_lib.diag_lib().pgm_tc_layout_probe(_lib.ptr(out), M, N, a_mn, b_mn, fillA, fillB, RA, RB,
                                               lboA, sboA, lboB, sboB, 0, ltA, ltB, 0, 1, offA, offB, None))
     torch.cuda.synchronize()
     return out.cpu().numpy().reshape(128, N)

@@ -11,7 +11,7 @@ from pgmorl_b200 import _lib  # noqa: E402
 
 def run(M, N, a_mn, b_mn, nmma, nacc, a_step=0, b_step=0):
     out = torch.zeros(8, dtype=torch.float32, device="cuda")
-    _lib.check(_lib.lib().pgm_tc_mma_bench(_lib.ptr(out), M, N, a_mn, b_mn, nmma, nacc, a_step, b_step, None))
+    _lib.check_diag(_lib.diag_lib().pgm_tc_mma_bench(_lib.ptr(out), M, N, a_mn, b_mn, nmma, nacc, a_step, b_step, None))
     torch.cuda.synchronize()
     o = out.cpu().tolist()
     return o[4], o[5]

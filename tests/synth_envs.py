@@ -177,6 +177,33 @@ class ReplayVecEnv:
         pass
 
 
+class RawReplayVecEnv:
+    """Raw-simulator stand-in (no VecNormalize wrapper): un-normalised float64 observations, scalar rewards,
+    raw objective vectors and termination flags replayed from make_trajectories() output of one task, scaled away from
+    zero mean / unit variance so the running moments have something to do. Independent of the actions."""
+
+    def __init__(self, traj_task, dims):
+        self.traj, self.t, self.dims = traj_task, 0, dims
+        self.obs = np.asarray(traj_task["obs"], dtype=np.float64) * 3.0 + 1.0
+        self.obj = np.asarray(traj_task["rewards"], dtype=np.float64) * np.array([1.0, 30.0, 5.0][:dims.obj])
+        self.done = np.asarray(traj_task["masks"]) == 0
+        self.bad = np.asarray(traj_task["bad_masks"]) == 0
+        self.N = self.obs.shape[1]
+
+    def reset(self):
+        self.t = 0
+        return self.obs[0]
+
+    def step(self, action):
+        t = self.t
+        self.t += 1
+        infos = [dict(obj=self.obj[t, n], **({"bad_transition": True} if self.bad[t + 1, n] else {})) for n in range(self.N)]
+        return self.obs[t + 1], self.obj[t].sum(axis=1), self.done[t + 1], infos
+
+    def close(self):
+        pass
+
+
 class SeededReplayVecEnv:
     """Replay environment for whole runs (driver-loop tests): the trajectory of MOPG iteration j is
     make_trajectories(seed = base_seed + j), where j is read from torch's global seed -- both the reference's worker

@@ -17,8 +17,8 @@ def library():
     return _lib.lib()
 
 
-def header_symbols():
-    src = open(os.path.join(ROOT, "include", "pgmorl_b200.h")).read()
+def header_symbols(name="pgmorl_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(pgm_[a-z0-9_]+)\s*\(", src)))
 
@@ -31,6 +31,17 @@ def test_header_symbols_all_exported_and_bound(library):
         assert hasattr(library, s), f"{s} declared in include/pgmorl_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in pgmorl_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_diagnostics_live_in_their_own_library(library):
+    """The tcgen05 probes are exported by libpgmorl_b200_diag.so only (include/pgmorl_b200_diag.h)."""
+    from pgmorl_b200 import _lib
+    diag = _lib.diag_lib()
+    syms = [s for s in header_symbols("pgmorl_b200_diag.h") if s.startswith("pgm_tc_")]
+    assert sorted(syms) == sorted(_lib.DIAG_SIGNATURES) and len(syms) == 3
+    for s in syms:
+        assert hasattr(diag, s)
+        assert not hasattr(library, s), f"{s} must not be exported by the product library"
 
 
 def test_n_par_matches_python_layout(library):

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 def test_tc_selftest():
     out = torch.zeros(16, dtype=torch.float32, device="cuda")
-    _lib.check(_lib.lib().pgm_tc_selftest(_lib.ptr(out), 16, None))
+    _lib.check_diag(_lib.diag_lib().pgm_tc_selftest(_lib.ptr(out), 16, None))
     torch.cuda.synchronize()
     o = out.cpu().tolist()
     print("tc selftest:", o)

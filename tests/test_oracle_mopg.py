@@ -70,3 +70,31 @@ def test_torch_port_matches_reference():
         assert rel_err(out["adv"], z[pre + "adv"]) < 1e-12
         assert rel_err(out["losses"], z[pre + "losses"]) < 1e-9
         assert rel_err(pol.flat(), z[pre + "params"]) < 1e-9
+
+
+def test_reference_runner_reproduces_golden():
+    """oracle/ref_mopg_runner.py (bench.py's `kind: "reference"` CPU arm: the UNMODIFIED reference imported in place) gives
+    the golden's first iteration. Runs only where /root/reference exists (the build container)."""
+    import os
+    if not os.path.isdir("/root/reference/morl"):
+        pytest.skip("/root/reference is not present on this machine")
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle import ref_mopg_runner as rr
+from pgmorl_b200 import synthetic
+from tests.helpers import load_mopg_case, task_traj, rel_err
+z, meta = load_mopg_case("mopg_walker_small.npz")
+d = meta["dims"]; task = 1; j = int(meta["iters"][0])
+lr = synthetic.linear_lr(3e-4, j, 1.0, meta["total_num_updates"])
+dt, flat, losses = rr._iteration(z[f"t{task}_init"], (d.obs, d.act, d.obj), task_traj(meta, j, task), j, lr,
+                                 z[f"t{task}_weights"], z[f"t{task}_obj_var"], meta["gamma"], meta["lam"], meta["E"], meta["B"])
+assert rel_err(flat, z[f"t{task}_i0_params"]) < 1e-12, rel_err(flat, z[f"t{task}_i0_params"])
+assert rel_err(losses, z[f"t{task}_i0_losses"]) < 1e-12
+print("ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # separate process: importing the reference switches torch's default dtype to float64 for the whole interpreter
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
