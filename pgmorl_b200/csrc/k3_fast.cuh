@@ -102,13 +102,30 @@ __device__ __forceinline__ void layer_fwd_fast(const float *__restrict__ in, int
     }
 }
 
-// RA = false: sliced Adam, three cluster barriers per step (partials pulled from the peers' images, new parameters pushed).
-// RA = true : partial gradient tiles go straight from registers into the slice OWNER's per-source slots, the owner adds its
+// Step tails (all bit-identical):
+// TAIL = 0  : sliced Adam, three cluster barriers per step (partials pulled from the peers' images, new parameters pushed).
+// TAIL = 1  : (RA) partial gradient tiles go straight from registers into the slice OWNER's per-source slots, the owner adds its
 //             G slots in fixed order and pushes the reduced slice to every CTA of the half, and every CTA runs Adam on the whole
 //             half redundantly (moments of the whole half resident) -- two cluster barriers per step, nothing is pulled.
 //             Same operations in the same order as RA = false: results are bit-identical.
-template <int C, int TM, bool RA>
+// TAIL = 2  : as TAIL = 0, but the parameter broadcast goes through the TMA: every CTA stores its updated slice to an
+//             L2-resident staging row and issues ONE bulk copy with cluster multicast (cp.async.bulk ... .multicast::cluster)
+//             that lands the slice in the resident image of every CTA of the half; an mbarrier per CTA counts the bytes of
+//             the G slices, so the third cluster barrier disappears. Bit-identical results.
+// TAIL = 3  : as TAIL = 2, and the gradient exchange goes through L2 instead of distributed shared memory: every CTA stores
+//             its partial gradient image to its scratch slot in global memory, and after barrier (1) the slice owners read the
+//             G partials with ld.global.cg (L2 bandwidth per SM is several times the SM-to-SM network's ~17 B/clk).
+// TAIL = 4  : as TAIL = 2, and the gradient reduce-scatter is PUSHED by the bulk-copy engine: every CTA writes its partial
+//             image to its own shared memory as before, then 8 threads issue one cp.async.bulk shared::cta -> shared::cluster
+//             per slice owner into that owner's per-source slot; the owner's mbarrier counts the bytes of its G incoming
+//             slices, so barrier (1) disappears as well and nothing is pulled through ld.shared::cluster. The owner adds
+//             its G local slots in the same fixed order. One cluster barrier per step is left (the norm exchange).
+// TAIL = 5  : as TAIL = 4, and the squared-norm partials travel with st.async ... mbarrier::complete_tx into every CTA's
+//             mbarrier: NO cluster barrier is left inside the step, the optimiser step is pure dataflow over three mbarriers
+//             (gradient slices in, norm partials in, parameter slices in). Ordering argument in DESIGN.md section 4.
+template <int C, int TM, int TAIL>
 __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a) {
+    constexpr bool RA = TAIL == 1, MC = TAIL >= 2, GL = TAIL == 3, BP = TAIL >= 4, NB = TAIL == 5;
     constexpr int RC = 16 * TM;
     constexpr int G = C / 2;
     constexpr int NU = 4;                 // gather items per thread (RC * RSG/4 <= NU * 256, checked on host)
@@ -117,6 +134,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
     __shared__ float red[34];
     __shared__ double sh_d[4];
     __shared__ float ssqS[16];            // squared-norm partials of all C CTAs (same offset in every CTA)
+    __shared__ __align__(8) unsigned long long mbarS;   // TAIL >= 2: counts the bytes of the G multicast parameter slices
+    __shared__ __align__(8) unsigned long long mbarR;   // TAIL >= 4: counts the bytes of the G incoming gradient slices
+    __shared__ __align__(8) unsigned long long mbarN;   // TAIL = 5: counts the bytes of the C incoming squared-norm partials
 
     const NetLayout &L = a.L;
     const int tid = threadIdx.x, tr = tid & 15, tc = tid >> 4;
@@ -150,16 +170,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
     // RA = false: gP = this CTA's partial gradient (image layout), read by peers; moments + reduced gradient of my slice
     // RA = true : gP = G per-source slots of my slice (written by the peers), gS = reduced gradient of the whole half
     //             (written by the slice owners), mS / vS = moments of the whole half
-    float *gP = p; p += RA ? G * 4 * per4 : a.NHP;
+    float *gP = p; p += RA ? G * 4 * per4 : (GL ? 0 : a.NHP);
+    float *gPg = a.gpart + ((size_t)(task * 2 + half) * G + g) * a.NHP;      // TAIL = 3: my partial image in global memory
+    float *slotB = p; p += BP ? G * 4 * per4 : 0;                            // TAIL = 4: G per-source slots of my slice
     float *gS = p; p += RA ? G * 4 * per4 : 4 * per4;
     const int nmom = RA ? NIMG : 4 * per4;
     float *mS = p, *vS = p + nmom;
     const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)per4 - 1) / (unsigned)per4);   // i4 / per4 == umulhi(i4, magic)
 
+    if (MC && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbarS)));
+        if (BP) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbarR)));
+        if (NB) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbarN)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");     // visible to the peers' multicasts: barrier (1)
+    }                                                                          // and (2) of step 0 come before the first one
+    if (BP) sync_group<C>();     // no barrier precedes the first remote signal in these tails: publish the mbarrier inits now
     float *gparams = a.params + (size_t)task * L.n_par;
     halfnet_load<false>(n, gparams, L, half);
     for (int i = tid; i < nmom; i += NTHREADS) { mS[i] = 0.f; vS[i] = 0.f; }
-    for (int i = tid; i < (RA ? G * 4 * per4 : a.NHP); i += NTHREADS) gP[i] = 0.f;   // padding entries stay zero for the whole launch
+    for (int i = tid; i < (RA ? G * 4 * per4 : (GL ? 0 : a.NHP)); i += NTHREADS) gP[i] = 0.f;   // padding entries stay zero for the whole launch
     if (RA) for (int i = tid; i < G * 4 * per4; i += NTHREADS) gS[i] = 0.f;
     for (int i = tid; i < RC; i += NTHREADS) dlpS[i] = 1.f;       // the critic never rewrites it
     __syncthreads();
@@ -477,6 +506,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                     const uint32_t i4 = (uint32_t)io >> 2, ow = __umulhi(i4, magic);
                     const uint32_t loc = gP_u + 16u * ((uint32_t)g * (uint32_t)per4 + (i4 - ow * (uint32_t)per4));
                     st_dsmem2x64(mapa_u32(loc, (uint32_t)(half * G) + ow), v);
+                } else if (GL) {
+                    *reinterpret_cast<ulonglong2 *>(gPg + io) = v;
                 } else {
                     *reinterpret_cast<ulonglong2 *>(gP + io) = v;
                 }
@@ -486,6 +517,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                     const uint32_t ow = __umulhi((uint32_t)io >> 2, magic);
                     const uint32_t loc = gP_u + 4u * ((uint32_t)g * 4u * (uint32_t)per4 + ((uint32_t)io - 4u * ow * (uint32_t)per4));
                     st_dsmem1(mapa_u32(loc, (uint32_t)(half * G) + ow), v);
+                } else if (GL) {
+                    gPg[io] = v;
                 } else {
                     gP[io] = v;
                 }
@@ -521,7 +554,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             loss_ent += ent;
         }
         PGM_TR(7)
-        sync_group<C>();   // (1) every CTA's partial gradient image is complete
+        if (BP) {
+            // my partial image -> the per-source slot of every slice owner, by the bulk-copy engine; no barrier (1)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // my st.shared, before the async proxy reads them
+            __syncthreads();
+            if (tid == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"(smem_u32(&mbarR)), "r"(G * 16 * (sl1 - sl0)) : "memory");
+            if (tid < G) {
+                const int o0 = tid * per4, o1 = min(n4, o0 + per4);
+                if (o1 > o0) {
+                    const uint32_t dst = mapa_u32(smem_u32(slotB) + 16u * (uint32_t)(g * per4), (uint32_t)(half * G + tid));
+                    const uint32_t mb = mapa_u32(smem_u32(&mbarR), (uint32_t)(half * G + tid));
+                    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "r"(smem_u32(gP) + 16u * (uint32_t)o0), "r"(16 * (o1 - o0)), "r"(mb) : "memory");
+                }
+            }
+            uint32_t done = 0;      // the G partial slices of my slice have landed in my slots
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(smem_u32(&mbarR)), "r"(s & 1) : "memory");
+        } else {
+            sync_group<C>();   // (1) every CTA's partial gradient image is complete
+        }
         PGM_TR(8)
 
         // ---- reduce my slice over the G CTAs of my half (fixed order), squared-norm partial ----
@@ -537,7 +592,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg) {
                     // RA: slot gg of my slice (local, filled by CTA gg of my half); else CTA gg's image through DSMEM
-                    const float4 t = RA ? lds4(gP + 4 * (gg * per4 + (i4 - sl0))) : ld_dsmem4(peer[gg] + 16u * (uint32_t)i4);
+                    const float4 t = RA ? lds4(gP + 4 * (gg * per4 + (i4 - sl0)))
+                                   : BP ? lds4(slotB + 4 * (gg * per4 + (i4 - sl0)))
+                                   : (GL ? __ldcg(reinterpret_cast<const float4 *>(a.gpart + ((size_t)(task * 2 + half) * G + gg) * a.NHP) + i4)
+                                         : ld_dsmem4(peer[gg] + 16u * (uint32_t)i4));
                     acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
                 }
                 if (ecoef != 0.f && half == 0 && i4 >= ls4) {   // d(-ecoef * entropy)/d logstd
@@ -558,9 +616,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             }
             sq = block_sum(sq, red);
             PGM_TR(9)
-            if (tid < C) st_dsmem1(mapa_u32(smem_u32(ssqS + rank), (uint32_t)tid), sq);   // my partial -> every CTA
+            if (NB) {       // my partial -> every CTA's slot, signalling that CTA's mbarrier (4 bytes each)
+                if (tid == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbarN)), "r"(4 * C) : "memory");
+                if (tid < C)
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                                 ::"r"(mapa_u32(smem_u32(ssqS + rank), (uint32_t)tid)), "r"(__float_as_uint(sq)),
+                                   "r"(mapa_u32(smem_u32(&mbarN), (uint32_t)tid)) : "memory");
+            } else if (tid < C) {
+                st_dsmem1(mapa_u32(smem_u32(ssqS + rank), (uint32_t)tid), sq);   // my partial -> every CTA
+            }
         }
         if (a.grad_only) {
+            if (NB) {               // every st.async aimed at this CTA must have landed before it may exit
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(smem_u32(&mbarN)), "r"(s & 1) : "memory");
+            }
             sync_group<C>();
             const int nH = L.half_size(half);
             for (int e = tid; e < nH; e += NTHREADS) {
@@ -575,7 +648,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             sh_d[0] = lr / (1.0 - b1pow);            // step_size
             sh_d[1] = 1.0 / sqrt(1.0 - b2pow);       // 1 / bias_correction2_sqrt
         }
-        sync_group<C>();   // (2) all squared-norm partials have landed in ssqS
+        if (NB) {
+            __syncthreads();        // sh_d (Adam scalars) written by thread 0
+            uint32_t done = 0;      // all C squared-norm partials have landed in ssqS
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(smem_u32(&mbarN)), "r"(s & 1) : "memory");
+        } else {
+            sync_group<C>();   // (2) all squared-norm partials have landed in ssqS
+        }
         PGM_TR(10)
         {
             float tot = 0.f;
@@ -605,19 +686,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                 uint32_t peer[G];
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg) peer[gg] = mapa_u32(pimg_u, (uint32_t)(half * G + gg));
+                float *pst = a.pstage + (size_t)(task * 2 + half) * a.NHP;      // TAIL >= 2: L2-resident staging row of the half
                 for (int i4 = sl0 + tid; i4 < sl1; i4 += NTHREADS) {
                     const int j4 = i4 - sl0;
                     const float4 g4 = lds4(gS + 4 * j4);
                     float4 m4 = lds4(mS + 4 * j4), v4 = lds4(vS + 4 * j4), p4 = lds4(pimg + 4 * i4);
                     PGM_ADAM1(x) PGM_ADAM1(y) PGM_ADAM1(z) PGM_ADAM1(w)
                     sts4(mS + 4 * j4, m4); sts4(vS + 4 * j4, v4);
+                    if (MC) {
+                        *reinterpret_cast<float4 *>(pst + 4 * i4) = p4;
+                    } else {
 #pragma unroll
-                    for (int gg = 0; gg < G; ++gg) st_dsmem4(peer[gg] + 16u * (uint32_t)i4, p4);   // incl. my own image
+                        for (int gg = 0; gg < G; ++gg) st_dsmem4(peer[gg] + 16u * (uint32_t)i4, p4);   // incl. my own image
+                    }
+                }
+                if (MC) {
+                    asm volatile("fence.proxy.async.global;" ::: "memory");     // my stores, before the async proxy reads them
+                    __syncthreads();
+                    if (tid == 0) {
+                        const uint32_t mb = smem_u32(&mbarS);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(16 * n4) : "memory");
+                        if (sl1 > sl0) {
+                            const unsigned short mask = (unsigned short)(((1u << G) - 1u) << (half * G));
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                                         "[%0], [%1], %2, [%3], %4;"
+                                         ::"r"(pimg_u + 16u * (uint32_t)sl0), "l"(pst + 4 * sl0), "r"(16 * (sl1 - sl0)), "r"(mb), "h"(mask)
+                                         : "memory");
+                        }
+                    }
+                    uint32_t done = 0;      // all G slices of my half have landed in my resident image
+                    while (!done)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(done) : "r"(smem_u32(&mbarS)), "r"(s & 1) : "memory");
                 }
             }
 #undef PGM_ADAM1
         }
-        if (!RA) sync_group<C>();   // (3) every resident image holds the new parameters
+        if (!RA && !MC) sync_group<C>();   // (3) every resident image holds the new parameters
         PGM_TR(11)
     }
 
@@ -658,14 +763,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
     }
 }
 
-__host__ inline size_t k3_fast_smem_bytes(const NetLayout &L, int TM, int RSS, int NHP, int stage_floats, int G, bool ra) {
+__host__ inline size_t k3_fast_smem_bytes(const NetLayout &L, int TM, int RSS, int NHP, int stage_floats, int G, bool ra, bool gl = false,
+                                          bool bp = false) {
     const int RC = 16 * TM;
     const int ldo = ((L.A > L.M ? L.A : L.M) | 1);
     const int img = halfnet_smem_floats(L, 0) > halfnet_smem_floats(L, 1) ? halfnet_smem_floats(L, 0) : halfnet_smem_floats(L, 1);
     // image + activations + loss arrays + staging + records + partial-gradient image + slice buffers (G >= 1)
     const size_t per = 4 * (size_t)((img / 4 + G - 1) / G);
     size_t f = img + 4 * (size_t)RC * LDH + 3 * (size_t)round_up(RC * ldo, 4) + RC + round_up(stage_floats, 4) +
-               2 * (size_t)RC * RSS + (ra ? 2 * G * per + 2 * (size_t)img : (size_t)NHP + 3 * per);
+               2 * (size_t)RC * RSS + (ra ? 2 * G * per + 2 * (size_t)img : (gl ? 0 : (size_t)NHP) + 3 * per + (bp ? G * per : 0));
     return f * sizeof(float);
 }
 

@@ -33,6 +33,7 @@ struct K3Args {
     const int32_t *perm;    // [P or 1][E][S]  (update)  or  [mb] (grad mode)
     float *losses;          // [P][3]
     float *gpart;           // scratch: partial / reduced gradients [P][2][G][NHP]
+    float *pstage;          // scratch: updated parameters on their way to the TMA multicast [P][2][NHP] (fast path, TAIL >= 2)
     float *ssq;             // scratch: squared-norm partials       [P][16]
     float *lpart;           // scratch: loss partial sums           [P][16][4]
     float *grad_out;        // grad mode only: [P][n_par]
@@ -551,7 +552,7 @@ namespace pgm {
 struct K3Plan {
     int C, G, TM, KG1, NA, RC, Rg, RSG, RSS, NHP;
     bool DB, fast, tc, tcw;
-    bool ra;      // fast path: redundant-Adam step tail (two cluster barriers per step, k3_fast.cuh)
+    int tail;     // fast path step tail (k3_fast.cuh): 0 three cluster barriers, 1 redundant Adam, 2 TMA multicast broadcast
     int rs;
     int stage_floats;
     size_t smem;
@@ -611,16 +612,33 @@ static int k3_tcw_resident_clusters(int rs) {
     return cache[rs] = n;
 }
 
-// flag OR-ed into `cluster`: the two-barrier step tail of the FFMA cluster kernel (tiles pushed to the slice owner, whole-half
-// Adam in every CTA; k3_fast.cuh, RA = true). Bit-identical results; measured SLOWER than the default three-barrier sliced
-// tail at the headline configuration (4.04 vs 3.86 ms, profiles/r02/ab_k3_tail.md), so it is opt-in (A/B, tests) only.
-constexpr int K3_CLUSTER_TAIL2 = 0x100;
+// Step tails of the FFMA cluster kernel (k3_fast.cuh, template parameter TAIL); every variant performs the same arithmetic
+// in the same order, so results are bit-identical (tests/test_gpu_kernels.py::test_k3_step_tails_bit_identical). Same-box
+// A/B at the headline configuration (6 tasks x 16 CTAs, profiles/r02/README.md), ms per MOPG iteration:
+//   tail 0  3.876  three cluster barriers: partial images pulled through ld.shared::cluster, parameters pushed (round 1)
+//   tail 1  4.04   two barriers: register tiles pushed to the slice owner, whole-half Adam in every CTA
+//   tail 2  3.734  parameter broadcast by TMA bulk copy with cluster multicast, third barrier gone
+//   tail 3  3.839  tail 2 + gradient exchange through L2 scratch slots
+//   tail 4  3.712  tail 2 + gradient reduce-scatter pushed by cp.async.bulk shared::cta -> shared::cluster, first barrier gone
+//   tail 5  3.575  tail 4 + norm partials by st.async with mbarrier completion: no cluster barrier left in the step (default)
+// A tail can be forced per call by OR-ing a flag into `cluster` (tests, A/B) or per process with PGM_K3_TAIL=0..5.
+constexpr int K3_DEFAULT_TAIL = 5;
+constexpr int K3_CLUSTER_TAIL2 = 0x100;    // tail 1
+constexpr int K3_CLUSTER_TAILMC = 0x200;   // tail 2
+constexpr int K3_CLUSTER_TAILGL = 0x400;   // tail 3
+constexpr int K3_CLUSTER_TAIL0 = 0x800;    // tail 0
+constexpr int K3_CLUSTER_TAILBP = 0x1000;  // tail 4
+constexpr int K3_CLUSTER_TAILNB = 0x2000;  // tail 5
+constexpr int K3_CLUSTER_FLAGS = K3_CLUSTER_TAIL2 | K3_CLUSTER_TAILMC | K3_CLUSTER_TAILGL | K3_CLUSTER_TAIL0 | K3_CLUSTER_TAILBP |
+                                 K3_CLUSTER_TAILNB;
 
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
-    const bool tail2 = (cluster & K3_CLUSTER_TAIL2) != 0;
-    cluster &= ~K3_CLUSTER_TAIL2;
-    pl.tc = false; pl.tcw = false; pl.ra = false; pl.off_mv = 0;
+    const bool tail2 = (cluster & K3_CLUSTER_TAIL2) != 0, tailmc = (cluster & K3_CLUSTER_TAILMC) != 0;
+    const bool tailgl = (cluster & K3_CLUSTER_TAILGL) != 0, tail0 = (cluster & K3_CLUSTER_TAIL0) != 0;
+    const bool tailbp = (cluster & K3_CLUSTER_TAILBP) != 0, tailnb = (cluster & K3_CLUSTER_TAILNB) != 0;
+    cluster &= ~K3_CLUSTER_FLAGS;
+    pl.tc = false; pl.tcw = false; pl.tail = 0; pl.off_mv = 0;
     // wide observations (Humanoid): the streamed tensor-core kernel; row split over as many CTAs per half as fill the SMs
     if (k3_tcw_dims(O, A, M) && (cluster == 0 || cluster == K3_CLUSTER_TC || cluster == K3_CLUSTER_TC2 || cluster == K3_CLUSTER_TC4)) {
         const int tiles = (mb + 127) / 128;
@@ -713,11 +731,16 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     if (pl.fast) {
         const int s0 = k3_fast_stage_floats(L.OP, A), s1 = k3_fast_stage_floats(L.OP, M);
         pl.stage_floats = s0 > s1 ? s0 : s1;
-        // step tail: three-barrier sliced variant by default; the two-barrier variant on request (cluster flag, or
-        // PGM_K3_TAIL=2 in the environment for whole-program A/B runs) when its buffers fit
-        static const bool env_ra = [] { const char *e = getenv("PGM_K3_TAIL"); return e && e[0] == '2'; }();
-        pl.ra = (env_ra || tail2) && pl.G >= 2 && k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, true) <= 227 * 1024;
-        pl.smem = k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, pl.ra);
+        // step tail: default from K3_DEFAULT_TAIL; others on request (cluster flags, or PGM_K3_TAIL=0|1|2 in the
+        // environment for whole-program A/B runs)
+        static const int env_tail = [] { const char *e = getenv("PGM_K3_TAIL"); return (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : -1; }();
+        pl.tail = tail0 ? 0 : (tail2 ? 1 : (tailmc ? 2 : (tailgl ? 3 : (tailbp ? 4 : (tailnb ? 5 : (env_tail >= 0 ? env_tail : K3_DEFAULT_TAIL))))));
+        if (pl.tail == 1 && !(pl.G >= 2 && k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, true) <= 227 * 1024))
+            pl.tail = 0;
+        if (pl.tail >= 2 && pl.G < 2) pl.tail = 0;
+        if (pl.tail >= 4 && k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, false, false, true) > 227 * 1024)
+            pl.tail = 2;
+        pl.smem = k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, pl.tail == 1, pl.tail == 3, pl.tail >= 4);
     } else {
         pl.smem = k3_smem_bytes(L, C, pl.TM, pl.DB, pl.RSS);
     }
@@ -725,7 +748,7 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
     size_t off = 0;
     auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     pl.off_rec = seg((size_t)P * S * pl.RSG * sizeof(float));
-    pl.off_gpart = seg((size_t)P * 2 * pl.G * pl.NHP * sizeof(float));
+    pl.off_gpart = seg((size_t)P * 2 * (pl.G + 1) * pl.NHP * sizeof(float));      // + one staging row per half (pstage)
     pl.off_ssq = seg((size_t)P * 16 * sizeof(float));
     pl.off_lpart = seg((size_t)P * 16 * 4 * sizeof(float));
 #ifdef PGM_K3_TRACE
@@ -755,11 +778,24 @@ template <int C>
 static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st) {
     if constexpr (C > 1) {
         if (pl.fast) {
-            if (pl.ra)
-                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, true>, C, a, pl, P, st)
-                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, true>, C, a, pl, P, st);
-            return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, false>, C, a, pl, P, st)
-                              : k3_launch_k(k3_ppo_fast_kernel<C, 4, false>, C, a, pl, P, st);
+            if (pl.tail == 1)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 1>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, 1>, C, a, pl, P, st);
+            if (pl.tail == 2)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 2>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, 2>, C, a, pl, P, st);
+            if (pl.tail == 3)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 3>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, 3>, C, a, pl, P, st);
+            if (pl.tail == 4)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 4>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, 4>, C, a, pl, P, st);
+            if (pl.tail == 5)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 5>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, 5>, C, a, pl, P, st);
+
+            return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 0>, C, a, pl, P, st)
+                              : k3_launch_k(k3_ppo_fast_kernel<C, 4, 0>, C, a, pl, P, st);
         }
         if (pl.KG1 == 6) return k3_launch_k(k3_ppo_kernel<C, 2, 6, 2, false>, C, a, pl, P, st);
         return pl.TM == 2 ? k3_launch_k(k3_ppo_kernel<C, 2, 1, 1, true>, C, a, pl, P, st)
@@ -822,14 +858,14 @@ extern "C" size_t pgm_ppo_last_trace_offset() { return g_last_trace_offset; }
 extern "C" size_t pgm_ppo_workspace_bytes(int P, int S, int O, int A, int M, int cluster) {
     // upper bound over every plan the launcher may choose for these dims (cluster 0 = auto)
     NetLayout L(O, A, M);
-    cluster &= ~K3_CLUSTER_TAIL2;
+    cluster &= ~K3_CLUSTER_FLAGS;
     const int G = cluster == 0 ? 8 : (cluster == 1 ? 1 : cluster / 2);
     const int i0 = halfnet_smem_floats(L, 0), i1 = halfnet_smem_floats(L, 1);
     const int NHP = round_up(i0 > i1 ? i0 : i1, 64);
     size_t t = 0;
     auto seg = [&](size_t b) { t += (b + 255) / 256 * 256; };
     seg((size_t)P * S * rec_stride(L) * sizeof(float));
-    seg((size_t)P * 2 * G * NHP * sizeof(float));
+    seg((size_t)P * 2 * (G + 1) * NHP * sizeof(float));
     seg((size_t)P * 16 * sizeof(float));
     seg((size_t)P * 64 * sizeof(float));
     if (k3_tc_dims(O, A, M)) seg(k3_tc_mv_bytes(P));
@@ -862,7 +898,7 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
     K3Args a;
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_step = adam_step; a.lr = lr;
     a.rec = (const float *)(ws + pl.off_rec); a.perm = perm; a.losses = losses;
-    a.gpart = (float *)(ws + pl.off_gpart); a.ssq = (float *)(ws + pl.off_ssq); a.lpart = (float *)(ws + pl.off_lpart);
+    a.gpart = (float *)(ws + pl.off_gpart); a.pstage = a.gpart + (size_t)P * 2 * pl.G * pl.NHP; a.ssq = (float *)(ws + pl.off_ssq); a.lpart = (float *)(ws + pl.off_lpart);
 #ifdef PGM_K3_TRACE
     a.trace = (long long *)(ws + pl.off_trace);
     g_last_trace_offset = pl.off_trace;
@@ -898,7 +934,7 @@ static int ppo_common(float *params, float *adam_m, float *adam_v, int32_t *adam
         PGM_CUDA(cudaGetLastError());
     }
     // padding entries of the gradient slots are never written by the kernel: keep them zero
-    PGM_CUDA(cudaMemsetAsync(ws + pl.off_gpart, 0, (size_t)P * 2 * pl.G * pl.NHP * sizeof(float), st));
+    PGM_CUDA(cudaMemsetAsync(ws + pl.off_gpart, 0, (size_t)P * 2 * (pl.G + 1) * pl.NHP * sizeof(float), st));
     return k3_launch(a, pl, P, st);
 }
 

@@ -203,22 +203,28 @@ def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
         assert rel_err(losses[p].cpu().numpy(), np.array(lref)) < 1e-4
 
 
-TAIL2 = 0x100     # flag OR-ed into `cluster`: the opt-in two-barrier step tail of the FFMA cluster kernel (csrc/k3_fast.cuh)
+# flags OR-ed into `cluster`: alternative step tails of the FFMA cluster kernel (csrc/k3_fast.cuh)
+TAIL2 = 0x100     # two-barrier tail: tiles pushed to the slice owner, whole-half Adam in every CTA
+TAILMC = 0x200    # parameter broadcast through the TMA (cp.async.bulk with cluster multicast) instead of DSMEM stores
+TAILGL = 0x400    # TAILMC + gradient exchange through L2 scratch slots instead of distributed shared memory
+TAIL0 = 0x800     # the plain three-barrier DSMEM tail
+TAILBP = 0x1000   # TAILMC + gradient reduce-scatter pushed by cp.async.bulk (shared::cta -> shared::cluster), one barrier left
+TAILNB = 0x2000   # TAILBP + norm partials by st.async with mbarrier completion: no cluster barrier inside the step
 
 
 @pytest.mark.parametrize("cluster", [4, 8, 16])
 @pytest.mark.parametrize("name,P,T,N,B", [("walker", 3, 64, 4, 4), ("hopper3", 2, 48, 2, 3), ("walker", 2, 512, 4, 8)])
 def test_k3_step_tails_bit_identical(name, P, T, N, B, cluster):
-    """The two-barrier step tail (tiles pushed to the slice owner, whole-half Adam in every CTA) performs the same
-    operations in the same order as the three-barrier sliced tail: parameters, moments and losses are equal bit for bit,
-    and so is the raw gradient."""
+    """The alternative step tails (two-barrier tail with whole-half Adam in every CTA; TMA multicast parameter broadcast)
+    perform the same operations in the same order as the three-barrier sliced tail: parameters, moments and losses are
+    equal bit for bit, and so is the raw gradient."""
     from pgmorl_b200 import kernels as K
     d = DIMS[name]
     cur, pk, perm = _ppo_inputs(d, P, T, N, seed=17)
     hyper = K.PpoHyper(entropy_coef=0.01)
     lr = dev(np.array([3e-4, 2.5e-4, 1e-4][:P]), torch.float64)
     out = []
-    for cl in (cluster, cluster | TAIL2):
+    for cl in (cluster, cluster | TAIL0, cluster | TAIL2, cluster | TAILMC, cluster | TAILGL, cluster | TAILBP, cluster | TAILNB):
         gp, gm, gv = dev(cur), torch.zeros(P, d.n_par, device="cuda"), torch.zeros(P, d.n_par, device="cuda")
         gstep = torch.zeros(P, dtype=torch.int32, device="cuda")
         losses = K.ppo_update(gp, gm, gv, gstep, lr, dev(pk["obs"]), dev(pk["action"]), dev(pk["logp"]), dev(pk["value"]),
@@ -228,8 +234,9 @@ def test_k3_step_tails_bit_identical(name, P, T, N, B, cluster):
                            dev(pk["returns"]), dev(pk["adv"]), dev(idx, torch.int32), d, hyper=hyper, cluster=cl)
         torch.cuda.synchronize()
         out.append((gp, gm, gv, gstep, losses, g, gl))
-    for x, y in zip(*out):
-        assert torch.equal(x, y)
+    for other in out[1:]:
+        for x, y in zip(out[0], other):
+            assert torch.equal(x, y)
     assert int(out[0][3][0]) == perm.shape[0] * B
 
 
