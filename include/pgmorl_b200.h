@@ -52,6 +52,10 @@ const char *pgm_last_error(void);
 
 /* number of parameters of one policy (actor 64-64 + critic 64-64 + heads + logstd) */
 int pgm_n_par(int obs_dim, int act_dim, int obj_num);
+/* offsets (in elements) of the 13 parameter tensors of one policy inside its flat vector, in the reference's
+ * named_parameters() order: base.actor.0.{weight,bias}, base.actor.2.{weight,bias}, base.critic.0.{...}, base.critic.2.{...},
+ * base.critic_linear.{weight,bias}, dist.fc_mean.{weight,bias}, dist.logstd._bias (a2c/model.py:201-256) */
+int pgm_param_offsets(int obs_dim, int act_dim, int obj_num, int *out13);
 
 /* ---------------------------------------------------------------------------
  * K1  population-batched actor-critic forward.

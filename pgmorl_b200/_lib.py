@@ -36,6 +36,7 @@ SIGNATURES = {
     "pgm_abi_version": (_I, []),
     "pgm_last_error": (C.c_char_p, []),
     "pgm_n_par": (_I, [_I, _I, _I]),
+    "pgm_param_offsets": (_I, [_I, _I, _I, _P]),
     "pgm_policy_forward_f32": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pgm_policy_step_f32": (_I, [_P, _P, _P, _P, _I, _P, _Z, _P, _Z, _P, _Z, _P, _Z, _P, _I, _I, _I, _I, _I, _P]),
     "pgm_gae_adv_f32": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _I, _P]),

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1_tc_kernel(const K1Args a) {
                 xv[e] = f < O ? stage[i * 128 * O + row * O + f] : ((f == O && ok) ? 1.f : 0.f);
             }
             unsigned char *xr = smem_raw + sl.tile[i] + 65536 + row * 128;
-            store_pair8(xr, (uint32_t)c, xr, (uint32_t)c + 4u, (uint32_t)(row & 7), xv);
+            store_pair8_ovf(xr, (uint32_t)c, xr, (uint32_t)c + 4u, (uint32_t)(row & 7), xv);
         }
         sync_all();
         if (warp == 0 && tc::elect_one()) {

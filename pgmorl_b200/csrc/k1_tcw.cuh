@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1_tcw_kernel(const K1Args a) 
             const float4 v = xin[k];
             const float h0 = round11(v.x), h1 = round11(v.y), h2 = round11(v.z), h3 = round11(v.w);
             unsigned char *d = img + row * 128 + ((uint32_t)((pc >> 1) ^ (row & 7)) << 4) + (pc & 1) * 8;
-            *reinterpret_cast<uint2 *>(d) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-            *reinterpret_cast<uint2 *>(d + 16384) = make_uint2(pack_h2(v.x - h0, v.y - h1), pack_h2(v.z - h2, v.w - h3));
+            *reinterpret_cast<uint2 *>(d) = make_uint2(pack_h2_ovf(h0, h1), pack_h2_ovf(h2, h3));
+            *reinterpret_cast<uint2 *>(d + 16384) = make_uint2(pack_h2_ovf(v.x - h0, v.y - h1), pack_h2_ovf(v.z - h2, v.w - h3));
         }
     };
     load_x(t0, 0);

@@ -947,6 +947,10 @@ extern "C" int pgm_ppo_update_f32(float *params, float *adam_m, float *adam_v, i
                                   void *stream) {
     PGM_REQUIRE(adam_m && adam_v && adam_step && lr, "pgm_ppo_update_f32: null optimizer state");
     PGM_REQUIRE(E > 0 && B > 0 && S / B > 0, "pgm_ppo_update_f32: bad E=%d B=%d for S=%d", E, B, S);
+    // the reference's BatchSampler(drop_last=True) yields S // (S // B) minibatches per epoch (a2c/storage.py:133-137), which
+    // is B only when the remainder S % B is smaller than one minibatch; otherwise it would take more than E*B steps
+    PGM_REQUIRE(S / (S / B) == B, "pgm_ppo_update_f32: S=%d samples in B=%d minibatches of %d leave a remainder of %d >= one "
+                "minibatch: the reference would run %d minibatches per epoch; choose S, B with S %% B < S / B", S, B, S / B, S % B, S / (S / B));
     return ppo_common(params, adam_m, adam_v, adam_step, lr, obs, obs_task_stride, action, logp_old, value_old,
                       value_task_stride, returns, adv, perm, perm_shared, E, B, S / B, hyper_host, losses, nullptr,
                       workspace, workspace_bytes, cluster, P, S, O, A, M, (cudaStream_t)stream);

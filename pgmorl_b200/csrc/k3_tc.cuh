@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                             const float h0 = round11(xv[0]), h1 = round11(xv[1]), h2 = round11(xv[2]), h3 = round11(xv[3]);
                             unsigned char *xr = smem_raw + sl.grp[i] + 65536 + row * 128 + (pc & 1) * 8;
                             const uint32_t c = (uint32_t)(pc >> 1), sw = (uint32_t)(row & 7);
-                            *reinterpret_cast<uint2 *>(xr + ((c ^ sw) << 4)) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                            *reinterpret_cast<uint2 *>(xr + ((c ^ sw) << 4)) = make_uint2(pack_h2_ovf(h0, h1), pack_h2_ovf(h2, h3));
                             *reinterpret_cast<uint2 *>(xr + (((c + 4u) ^ sw) << 4)) =
-                                make_uint2(pack_h2(xv[0] - h0, xv[1] - h1), pack_h2(xv[2] - h2, xv[3] - h3));
+                                make_uint2(pack_h2_ovf(xv[0] - h0, xv[1] - h1), pack_h2_ovf(xv[2] - h2, xv[3] - h3));
                         } else {
                             *reinterpret_cast<float4 *>(SC + (i * 128 + row) * 12 + 4 * (pc - NPX)) = v;
                         }
@@ -724,8 +724,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
                     const float w0 = p4.x * TC_SW, w1 = p4.y * TC_SW, w2 = p4.z * TC_SW, w3 = p4.w * TC_SW;
                     const float h0 = round11(w0), h1 = round11(w1), h2 = round11(w2), h3 = round11(w3);
                     const int hw = sw128_hw(j, k0);
-                    *reinterpret_cast<uint2 *>(W2a + hw) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-                    *reinterpret_cast<uint2 *>(W2b + hw) = make_uint2(pack_h2(w0 - h0, w1 - h1), pack_h2(w2 - h2, w3 - h3));
+                    *reinterpret_cast<uint2 *>(W2a + hw) = make_uint2(pack_h2_ovf(h0, h1), pack_h2_ovf(h2, h3));
+                    *reinterpret_cast<uint2 *>(W2b + hw) = make_uint2(pack_h2_ovf(w0 - h0, w1 - h1), pack_h2_ovf(w2 - h2, w3 - h3));
                 } else {
                     put_param(e0, p4.x);
                     if (e0 + 1 < nH) put_param(e0 + 1, p4.y);

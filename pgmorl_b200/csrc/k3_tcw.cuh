@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
         if (inW1 || inW2 || inWh) {
             const float w0 = p.x * TC_SW, w1 = p.y * TC_SW, w2 = p.z * TC_SW, w3 = p.w * TC_SW;
             const float h0 = round11(w0), h1 = round11(w1), h2 = round11(w2), h3 = round11(w3);
-            const uint2 v1 = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-            const uint2 v2 = make_uint2(pack_h2(w0 - h0, w1 - h1), pack_h2(w2 - h2, w3 - h3));
+            const uint2 v1 = make_uint2(pack_h2_ovf(h0, h1), pack_h2_ovf(h2, h3));
+            const uint2 v2 = make_uint2(pack_h2_ovf(w0 - h0, w1 - h1), pack_h2_ovf(w2 - h2, w3 - h3));
             if (inW1) {
                 const int j = e0 / O, c = e0 - j * O;
                 __half *img = w1g + (c >> 6) * 8192;

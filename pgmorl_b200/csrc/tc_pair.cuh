@@ -31,6 +31,13 @@ __device__ __forceinline__ int ld_nc_s32(const int32_t *p) {
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {   // two floats -> fp16x2 (a in the low half), saturating
     uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
 }
+// Same without saturation, for the operands that come from OUTSIDE the kernel (observations, parameters): a value beyond
+// fp16's range (|x| >= 65 520 for an observation; |w| >= 255.9 for a parameter, which is stored x 2^8) becomes inf and turns
+// the outputs of that task into inf / NaN -- a loud failure instead of a silently clamped operand. Activations (|h| <= 1,
+// stored x 2^8) and the backward signals (x 2^12) keep the saturating form.
+__device__ __forceinline__ uint32_t pack_h2_ovf(float a, float b) {
+    uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
 // a1 = v rounded to 11 significant bits (round half away: integer add + mask, no conversion-pipe instruction);
 // exactly representable in fp16 whenever v is in fp16's normal range
 __device__ __forceinline__ float round11(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
@@ -44,6 +51,18 @@ __device__ __forceinline__ void store_pair8(unsigned char *rowa, uint32_t ca, un
     p1.x = pack_h2(h[0], h[1]); p1.y = pack_h2(h[2], h[3]); p1.z = pack_h2(h[4], h[5]); p1.w = pack_h2(h[6], h[7]);
     p2.x = pack_h2(v[0] - h[0], v[1] - h[1]); p2.y = pack_h2(v[2] - h[2], v[3] - h[3]);
     p2.z = pack_h2(v[4] - h[4], v[5] - h[5]); p2.w = pack_h2(v[6] - h[6], v[7] - h[7]);
+    *reinterpret_cast<uint4 *>(rowa + ((ca ^ swz8) << 4)) = p1;
+    *reinterpret_cast<uint4 *>(rowb + ((cb ^ swz8) << 4)) = p2;
+}
+// store_pair8 for externally supplied values (observations): overflow becomes inf, see pack_h2_ovf
+__device__ __forceinline__ void store_pair8_ovf(unsigned char *rowa, uint32_t ca, unsigned char *rowb, uint32_t cb, uint32_t swz8, const float *v) {
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = round11(v[i]);
+    uint4 p1, p2;
+    p1.x = pack_h2_ovf(h[0], h[1]); p1.y = pack_h2_ovf(h[2], h[3]); p1.z = pack_h2_ovf(h[4], h[5]); p1.w = pack_h2_ovf(h[6], h[7]);
+    p2.x = pack_h2_ovf(v[0] - h[0], v[1] - h[1]); p2.y = pack_h2_ovf(v[2] - h[2], v[3] - h[3]);
+    p2.z = pack_h2_ovf(v[4] - h[4], v[5] - h[5]); p2.w = pack_h2_ovf(v[6] - h[6], v[7] - h[7]);
     *reinterpret_cast<uint4 *>(rowa + ((ca ^ swz8) << 4)) = p1;
     *reinterpret_cast<uint4 *>(rowb + ((cb ^ swz8) << 4)) = p2;
 }

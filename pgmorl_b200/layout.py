@@ -10,8 +10,9 @@ vector converts to / from a reference ``state_dict`` by plain slicing:
     base.critic_linear.{weight[M,H],bias[M]},
     dist.fc_mean.{weight[A,H],bias[A]}, dist.logstd._bias[A,1]
 
-The same offsets are compiled into the CUDA side (csrc/mopg_common.cuh,
-``struct NetLayout``); tests/test_layout.py checks both agree.
+The same offsets are compiled into the CUDA side (csrc/common.cuh,
+``struct NetLayout``, exported as ``pgm_param_offsets``); tests/test_cabi.py checks
+that both agree for every named environment shape.
 """
 from collections import OrderedDict
 from dataclasses import dataclass

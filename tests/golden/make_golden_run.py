@@ -29,7 +29,10 @@ METHODS = ("prediction-guided", "moead", "ra", "pfa", "random")     # morl/morl.
 
 
 def run_args(save_dir, method="prediction-guided"):
-    """The configuration of the golden run; tests/test_gpu_run.py builds the same namespace."""
+    """The configuration of the golden run; tests/test_gpu_run.py builds the same namespace. The pseudo-method "long" is
+    the longer prediction-guided cut (synth_envs.run_args_2d_long: warm-up 16 + 2 generations of 4, T = 512)."""
+    if method == "long":
+        return synth_envs.run_args_2d_long(save_dir)
     args = synth_envs.run_args_2d(save_dir)
     args.selection_method = method
     return args

@@ -281,3 +281,13 @@ def run_args_2d(save_dir, T=64, N=4):
         eval_num=1, raw=True, use_linear_lr_decay=True, lr_decay_ratio=1.0, use_gae=True, gae_lambda=0.95,
         use_proper_time_limits=True, rl_log_interval=0, pbuffer_num=100, pbuffer_size=2, num_tasks=6,
         num_weight_candidates=7, sparsity=1.0)
+
+
+def run_args_2d_long(save_dir):
+    """A longer cut of BASELINE.json configs[0] (C1): 6 tasks, T = 512 x 4 envs, minibatches of 256 rows, warm-up of 16
+    iterations + 2 generations of 4 iterations (24 MOPG iterations = 768 Adam steps per task), prediction-guided selection."""
+    args = run_args_2d(save_dir, T=512, N=4)
+    args.warmup_iter, args.update_iter = 16, 4
+    args.num_env_steps = (16 + 2 * 4) * 512 * 4
+    args.ppo_epoch, args.num_mini_batch = 4, 8
+    return args

@@ -51,10 +51,34 @@ def test_n_par_matches_python_layout(library):
     assert library.pgm_n_par(17, 6, 2) == 11150 and library.pgm_n_par(376, 17, 2) == 57828
 
 
+def test_tensor_offsets_match_python_layout(library):
+    """The offsets state_dict / checkpoint slicing uses (pgmorl_b200/layout.py) are the ones compiled into the kernels."""
+    import ctypes
+    from pgmorl_b200.layout import ENV_SHAPES, param_layout
+    for d in ENV_SHAPES.values():
+        out = (ctypes.c_int * 13)()
+        assert library.pgm_param_offsets(d.obs, d.act, d.obj, out) == 0
+        layout, n = param_layout(d)
+        assert [off for off, _ in layout.values()] == list(out) and n == library.pgm_n_par(d.obs, d.act, d.obj)
+
+
 def test_argument_errors_are_reported_without_a_gpu(library):
     # argument validation happens before any CUDA call
     rc = library.pgm_gae_adv_f32(None, None, None, None, None, None, 0.99, 0.95, None, None, 1, 1, 1, 1, None)
     assert rc == 1 and b"null" in library.pgm_last_error()
+
+
+def test_minibatch_split_the_reference_would_run_differently_is_rejected(library):
+    """S = 100 samples in B = 32 minibatches: the reference's BatchSampler(drop_last=True) yields 33 minibatches of 3 per
+    epoch (a2c/storage.py:133-137), not 32 -- refused with a clear message instead of silently taking fewer steps."""
+    import ctypes
+    from pgmorl_b200._lib import PpoHyper
+    buf = (ctypes.c_double * 8)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    hy = PpoHyper()
+    rc = library.pgm_ppo_update_f32(p, p, p, p, p, p, 0, p, p, p, 0, p, p, p, 1, 2, 32, ctypes.byref(hy), p, p, 1024, 0,
+                                    1, 100, 17, 6, 2, None)
+    assert rc == 1 and b"33 minibatches" in library.pgm_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -95,6 +95,49 @@ def test_k1_modes(name, T):
     assert torch.equal(v3, value)
 
 
+@pytest.mark.parametrize("name", ["walker", "humanoid"])
+def test_tensor_core_paths_with_unnormalised_observations(name):
+    """The tensor-core kernels hold observations as UNSCALED fp16 pairs (range +-65 504, 22 significant bits) and parameters
+    as pairs scaled by 2^8 (|w| < 255.9). Observations far outside VecNormalize's +-10 (ob_rms off, raw simulator output)
+    still meet the FP32 tolerances on the tensor-core forward and update; a value BEYOND fp16's range does not get clamped
+    silently: it turns that task's outputs into inf / NaN (csrc/tc_pair.cuh, pack_h2_ovf) and leaves other tasks alone."""
+    from pgmorl_b200 import kernels as K
+    d = DIMS[name]
+    P, T, N = 2, 300 if name == "walker" else 150, 4 if name == "walker" else 8      # >= 1024 rows: tensor-core forward
+    params, traj, eps, perm, _, _, _ = make_case(d, P, T, N, seed=23)
+    params = params * 0.05                                      # small weights: tanh not saturated by inputs of size 300
+    big = traj["obs"].astype(np.float64) * 300.0 + 40.0
+    obs = dev(big).reshape(P, (T + 1) * N, d.obs)
+    value, action, logp = K.policy_forward(dev(params), obs, d, mode=K.ACT_DETERMINISTIC)
+    torch.cuda.synchronize()
+    for p in range(P):
+        net = orc.Net(dev(params[p]).cpu().numpy().astype(np.float64), d.obs, d.act, d.obj)
+        v, mean, _ = orc.forward(net, obs[p].cpu().numpy().astype(np.float64))
+        assert rel_err(value[p].cpu().numpy(), v) < 2e-5 and rel_err(action[p].cpu().numpy(), mean) < 2e-5
+    # one PPO gradient on the tensor-core update kernel (cluster 32) with the same large observations
+    S = T * N
+    rng = np.random.RandomState(3)
+    act = rng.randn(P, S, d.act); lp = rng.randn(P, S) * 0.1 - 5.0
+    vold = value.cpu().numpy().astype(np.float64) + rng.randn(P, (T + 1) * N, d.obj) * 0.05
+    ret = rng.randn(P, S, d.obj); adv = rng.randn(P, S)
+    idx = rng.permutation(S)[:256 if name == "walker" else 512]
+    g, _ = K.ppo_grad(dev(params), obs, dev(act), dev(lp), dev(vold), dev(ret), dev(adv), dev(idx, torch.int32), d, cluster=32)
+    torch.cuda.synchronize()
+    for p in range(P):
+        net = orc.Net(dev(params[p]).cpu().numpy().astype(np.float64), d.obs, d.act, d.obj)
+        f64 = lambda t: dev(t).cpu().numpy().astype(np.float64)
+        gref, _ = orc.ppo_grad(net, obs[p].cpu().numpy().astype(np.float64)[:S][idx], f64(act[p])[idx], f64(lp[p])[idx],
+                               f64(vold[p])[:S][idx], f64(ret[p])[idx], f64(adv[p])[idx])
+        assert rel_err(g[p].cpu().numpy(), gref) < 5e-5
+    # beyond fp16's range: loud, and confined to the task that holds the value
+    bad = obs.clone()
+    bad[1, 5, 3] = 1.0e5
+    value, action, logp = K.policy_forward(dev(params), bad, d, mode=K.ACT_DETERMINISTIC)
+    torch.cuda.synchronize()
+    assert not torch.isfinite(value[1, 5]).all() or not torch.isfinite(action[1, 5]).all()
+    assert torch.isfinite(value[0]).all() and torch.isfinite(action[0]).all()
+
+
 @pytest.mark.parametrize("name,P,T,N", [("walker", 3, 64, 4), ("hopper3", 2, 45, 2), ("walker", 2, 2048, 4),
                                          ("walker", 1, 7, 1), ("humanoid", 2, 100, 8)])
 def test_k2_gae_adv_matches_oracle(name, P, T, N):
@@ -204,6 +247,42 @@ def test_k3_update_matches_oracle(name, P, T, N, B, cluster):
 
 
 # flags OR-ed into `cluster`: alternative step tails of the FFMA cluster kernel (csrc/k3_fast.cuh)
+@pytest.mark.parametrize("P,expect_waves", [(160, True), (74, False), (37, False), (75, True)])
+def test_k3_update_large_populations_auto_plan(P, expect_waves):
+    """Populations larger than one wave of clusters (the auto plan's tensor-core kernel with 2 CTAs per task: 148 SMs hold
+    74 tasks at once; P = 160 runs three waves) and the plan boundaries P = 37 (last size with 4 CTAs per task... first with
+    2) and 74 / 75 (last single wave / first with a second wave): parameters, moments and step of tasks at the wave
+    boundaries against the float64 oracle, same tolerances as the small-population tests."""
+    from pgmorl_b200 import kernels as K
+    d = DIMS["walker"]
+    T, N, B = 32, 4, 1                                     # one minibatch of 128 rows (one row tile), E epochs
+    cur1, pk1, perm = _ppo_inputs(d, 4, T, N, seed=19)     # 4 distinct tasks, tiled to P with per-task parameter offsets
+    rng = np.random.RandomState(5)
+    reps = (P + 3) // 4
+    cur = np.tile(cur1, (reps, 1))[:P] + rng.randn(P, d.n_par) * 1e-3
+    pk = {k: np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:P] for k, v in pk1.items()}
+    S = T * N
+    lr = np.full(P, 3e-4)
+    gp, gm, gv = dev(cur), torch.zeros(P, d.n_par, device="cuda"), torch.zeros(P, d.n_par, device="cuda")
+    gstep = torch.zeros(P, dtype=torch.int32, device="cuda")
+    K.ppo_update(gp, gm, gv, gstep, dev(lr, torch.float64), dev(pk["obs"]), dev(pk["action"]), dev(pk["logp"]),
+                 dev(pk["value"]), dev(pk["returns"]), dev(pk["adv"]), dev(perm[None], torch.int32), B, d, cluster=0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(gp).all()
+    check = sorted({0, 1, 36, 37, 73, 74, 75, 147, 148, P - 1} & set(range(P)))
+    for p in check:
+        flat = dev(cur[p]).cpu().numpy().astype(np.float64)
+        m, v = np.zeros_like(flat), np.zeros_like(flat)
+        obs3 = pk["obs"][p].reshape(T + 1, N, d.obs).astype(np.float64)
+        step, _ = orc.ppo_update(flat, m, v, 0, lr[p], (d.obs, d.act, d.obj), obs3, pk["action"][p].reshape(T, N, -1),
+                                 pk["logp"][p].reshape(T, N), pk["value"][p].reshape(T + 1, N, -1),
+                                 pk["returns"][p].reshape(T, N, -1), pk["adv"][p].reshape(T, N), perm, B)
+        assert int(gstep[p]) == step
+        assert rel_err(gp[p].cpu().numpy(), flat) < 1e-5, p
+        assert rel_err(gm[p].cpu().numpy(), m) < 1e-4, p
+        assert rel_err(gv[p].cpu().numpy(), v) < 1e-4, p
+
+
 TAIL2 = 0x100     # two-barrier tail: tiles pushed to the slice owner, whole-half Adam in every CTA
 TAILMC = 0x200    # parameter broadcast through the TMA (cp.async.bulk with cluster multicast) instead of DSMEM stores
 TAILGL = 0x400    # TAILMC + gradient exchange through L2 scratch slots instead of distributed shared memory

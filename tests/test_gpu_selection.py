@@ -8,8 +8,14 @@ import pytest
 
 from oracle import selection_oracle as so
 
+import json
+
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# The recorded fits K4 does not reproduce to rtol 1e-6, pinned by index, next to the fits on which scipy ITSELF moves by more
+# than that under a 1e-13 relative perturbation of x0 (tests/golden/make_k4_allowlist.py, run on a B200; SURVEY.md section 7,
+# protocol (ii)): 18 / 32 / 5 fits of 474 / 996 / 300, of which 18 / 31 / 4 are among scipy's own 19 / 38 / 6 chaotic fits.
+K4_PINNED = json.load(open(os.path.join(GOLDEN, "k4_disagreeing_fits.json")))
 
 
 def test_ep_filter_and_metrics_known_answers():
@@ -92,12 +98,14 @@ def test_greedy_edge_cases():
         assert np.array_equal(hv[r], ohv[r]) and np.array_equal(sp[r], osp[r])
 
 
-@pytest.mark.parametrize("name", ["selection_2d.npz", "selection_3d.npz"])
+@pytest.mark.parametrize("name", ["selection_2d.npz", "selection_3d.npz", "selection_2d_fork.npz"])
 def test_k4_fits_match_scipy(name):
     """K4 follows scipy's TRF step for step; the only substitution is the SVD algorithm, and ~2-4 % of these
-    fits are chaotic even against scipy itself (hard part 3). Gate: theta within rtol 1e-6
-    for >= 93 % of the fits, every fit finite and inside its bounds, and the disagreeing fits are not better
-    or worse than scipy's by more than the solver tolerance in cost ... reported, not hidden."""
+    fits are chaotic even against scipy itself (hard part 3). Gate: the set of fits whose theta is
+    NOT within rtol 1e-6 of scipy's is exactly the pinned allow-list (tests/golden/k4_disagreeing_fits.json: 3.8 % / 3.2 % /
+    1.7 % of the fits, all but 0 / 1 / 1 of them fits on which scipy itself is sensitive to a 1e-13 perturbation of x0);
+    every fit finite and inside its bounds, and the disagreeing fits are not worse than scipy's by more than the solver
+    tolerance in cost ... reported, not hidden."""
     from pgmorl_b200 import kernels as K
     z = np.load(os.path.join(GOLDEN, name))
     xs, ys, ws, ubs, ref, ref_cost, ref_status = [], [], [], [], [], [], []
@@ -111,9 +119,15 @@ def test_k4_fits_match_scipy(name):
     assert np.isfinite(theta).all() and (theta >= so.LB - 1e-12).all() and (theta <= ubs + 1e-12).all()
     close = np.isclose(theta, ref, rtol=1e-6, atol=1e-9).all(axis=1)
     frac = close.mean()
+    pin = K4_PINNED[name]
+    dis = np.nonzero(~close)[0].tolist()
     print(f"{name}: {len(ref)} fits, theta within 1e-6 of scipy: {100 * frac:.1f} %, status equal: "
-          f"{100 * (status == np.array(ref_status)).mean():.1f} %")
-    assert frac >= 0.93
+          f"{100 * (status == np.array(ref_status)).mean():.1f} %; disagreeing fits {dis}; scipy's own sensitivity to a "
+          f"1e-13 perturbation of x0: {len(pin['sensitive'])} fits, {len(set(dis) & set(pin['sensitive']))} of the "
+          f"{len(dis)} disagreeing ones among them")
+    assert len(ref) == pin["n_fits"]
+    assert set(dis) <= set(pin["disagree"]), f"new disagreeing fits: {sorted(set(dis) - set(pin['disagree']))}"
+    assert len(dis) >= len(pin["disagree"]) - 1 or len(dis) == 0      # the list is the measurement, not slack
     # where theta agrees the bookkeeping agrees too
     assert (status[close] == np.array(ref_status)[close]).mean() > 0.98
     assert np.allclose(cost[close], ref_cost[close], rtol=1e-8, atol=1e-12)
@@ -197,7 +211,7 @@ def _run_generations(z, gens, M, name):
         print(f"{name} gen {g}: picks {'identical' if same else 'DIFFER'}; fits matching scipy "
               f"{int(fits_ok.sum())}/{len(fits_ok)}")
     print(f"{name}: {exact}/{gens} generations bit-exact, {explained} explained by chaotic fits")
-    assert exact >= gens - 2
+    assert exact == gens            # measured on a B200: 7/7 (2 objectives) and 5/5 (3 objectives) generations identical
 
 
 @pytest.mark.parametrize("M,n_pop,n_ep", [(2, 200, 300), (3, 420, 500)])
@@ -283,4 +297,4 @@ def test_fork_scoring_variant_matches_the_fork_reference():
             print(f"fork gen {g}: picks {'identical' if same else 'DIFFER'}; fits matching scipy {int(fits_ok.sum())}/{len(fits_ok)}")
     finally:
         torch.set_default_dtype(torch.float32)
-    assert exact >= gens - 1
+    assert exact == gens            # measured on a B200: 5/5 generations identical
