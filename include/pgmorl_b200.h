@@ -123,7 +123,12 @@ int pgm_gae_adv_f32(const float *rewards, const float *value, const float *masks
  *   workspace: >= pgm_ppo_workspace_bytes(...) bytes, 256-byte aligned
  *   cluster: 1,2,4,8,16 = CTAs per task of the FP32 FFMA kernels; 32 / 64 = the tensor-core kernel (tcgen05 UMMA on FP16
  *            operand pairs, FP32 accumulate, FP32-level accuracy) with 2 / 4 CTAs per task, built for the (O,A,M)
- *            shapes (17,6,2) and (11,3,3); 0 = choose from P, the shape and the SM count (tensor cores from 8 tasks on)
+ *            shapes (17,6,2) and (11,3,3); 0 = choose from P, the shape and the SM count (tensor cores from 8 tasks on).
+ *            Tensor-core operand ranges: |obs| < 65 504 (unscaled fp16 pairs), |parameter| < 255.9, |backward signal| < 16;
+ *            beyond them the task's outputs become inf / NaN (non-saturating conversions), never a silently clamped result.
+ *            OR-able flags 0x100 / 0x200 / 0x400 / 0x800 / 0x1000 / 0x2000 select the step tail of the FFMA cluster kernel
+ *            (A/B and tests; bit-identical results; default = 0x2000, csrc/k3_ppo.cu).
+ *   S and B must satisfy S % B < S / B (the reference's BatchSampler(drop_last=True) then yields exactly B minibatches).
  */
 typedef struct {
     double clip_param;      /* 0.2  a2c/algo/ppo.py:83-84  */

@@ -139,7 +139,11 @@ def test_tensor_core_paths_with_unnormalised_observations(name):
 
 
 @pytest.mark.parametrize("name,P,T,N", [("walker", 3, 64, 4), ("hopper3", 2, 45, 2), ("walker", 2, 2048, 4),
-                                         ("walker", 1, 7, 1), ("humanoid", 2, 100, 8)])
+                                         ("walker", 1, 7, 1), ("humanoid", 2, 100, 8),
+                                         # long rollouts of small populations: the segmented kernel (32 / N segments of the
+                                         # time axis per env column), incl. a ragged last segment and N that does not divide 32
+                                         ("humanoid", 2, 2048, 8), ("hopper3", 2, 1030, 3), ("walker", 6, 2048, 4),
+                                         ("walker", 70, 700, 4)])      # > 64 tasks: one warp per column again
 def test_k2_gae_adv_matches_oracle(name, P, T, N):
     from pgmorl_b200 import kernels as K
     d = DIMS[name]
