@@ -559,6 +559,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from pgmorl_b200 import dist as pdist
+        pdist.warm_up_p2p(dev)          # every rank pair's NCCL channel is opened once at start-up, as morl.run does
     pop = PopulationMOPG(d, P, T, N, ppo_epoch=E, num_mini_batch=B, gamma=gamma, device=dev, cluster=args.cluster)
     pop.alloc_snapshots(GEN_ITERS)
     # rank r owns the global tasks {r, r + W, ...} (dist.shard_tasks); inputs seeded per rank

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     double *sh_d = (double *)(smem_raw + sl.misc + 1024);
     uint64_t *mbars = (uint64_t *)(smem_raw + sl.misc + 1024 + 32);     // [0..1] chain (A), [2..3] weight grads (B)
     uint32_t *tmem_ptr_s = (uint32_t *)(smem_raw + sl.misc + 1024 + 64);
+    uint64_t *mbarN = (uint64_t *)(smem_raw + sl.misc + 1024 + 72);     // counts the bytes of the peer's 8 squared-norm partials
     const float *b2s = PM + ob2, *bhs = PM + obh, *lss = PM + ols;
 
     // ---------------- one-time setup ----------------
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
     if (warp == 0) tc::tmem_alloc(tmem_ptr_s, 512);
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) tc::mbar_init(mbars + i, 1);
+        tc::mbar_init(mbarN, 1);
         tc::fence_mbar_init();
     }
     const float *gpar = a.params + (size_t)task * L.n_par;
@@ -688,12 +690,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tc_kernel(const K3Args a) {
         // only synchronisation, every thread then adds the 16 partials in one fixed order
         sq = warp_sum(sq);
         float *ssq2 = ssqS + 16 * (s & 1);    // slots alternate by step parity: the peer may still be reading the last ones
+        // (round 2) no cluster barrier: the partials travel with st.async and complete the PEER's mbarrier (8 x 4 bytes per
+        // step); slots alternate by step parity, and a CTA cannot run more than one step ahead of its peer because it needs
+        // the peer's partials of every step -- so a slot is never rewritten while it is still being read
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbarN)), "r"(32) : "memory");
         if (lane == 0) {                      // my half's partials -> me and the CTA of the other half with my row-split index
             ssq2[half * 8 + warp] = sq;
-            st_dsmem1(mapa_u32(smem_u32(ssq2 + half * 8 + warp), (uint32_t)((1 - half) * RS + rs)), sq);
+            const uint32_t peer = (uint32_t)((1 - half) * RS + rs);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                         ::"r"(mapa_u32(smem_u32(ssq2 + half * 8 + warp), peer)), "r"(__float_as_uint(sq)),
+                           "r"(mapa_u32(smem_u32(mbarN), peer)) : "memory");
         }
         TCT(35)
-        sync_group<2>();
+        __syncthreads();                      // my own 8 partials
+        tc::mbar_wait(mbarN, (uint32_t)(s & 1));   // the peer's 8 partials
         TCT(36)
         float tot = 0.f;
 #pragma unroll

@@ -16,6 +16,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._nvtx import rng as _nvtx
+
 
 def world():
     return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
@@ -60,7 +62,8 @@ def all_gather_records(local, n_tasks, device=None):
     send = torch.full((per, R), -1.0, dtype=torch.float64, device=dev)       # task id -1 marks padding
     send[:len(local)] = torch.from_numpy(local).to(dev)
     recv = torch.empty(W * per, R, dtype=torch.float64, device=dev)
-    dist.all_gather_into_tensor(recv, send)
+    with _nvtx("dist.all_gather_records"):
+        dist.all_gather_into_tensor(recv, send)
     table = recv.cpu().numpy()
     table = table[table[:, 0] >= 0]
     assert len(table) == n_tasks, (len(table), n_tasks)
@@ -163,11 +166,51 @@ def migrate_states(plan, get_state, put_state, n_state, device=None, dtype=torch
             t = torch.empty(n_state, dtype=dtype, device=dev)
             ops.append(dist.P2POp(dist.irecv, t, src, tag=task)); bufs.append((task, t))
     if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        with _nvtx("dist.migrate_states"):
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
     for task, t in bufs:
         if task is not None:
             put_state(task, t)
+
+
+def warm_up_p2p(device=None):
+    """Establish the point-to-point connection of every rank pair once (NCCL opens a pair's channel lazily at its first
+    send / recv, ~20-50 ms each: without this the first generations of an 8-GPU run spend up to 1.5 s in `migrate_states`
+    while new pairs keep appearing). One batched exchange of a single element with every peer."""
+    rank, W = world()
+    if W == 1:
+        return
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+    send = torch.full((1,), float(rank), dtype=torch.float64, device=dev)
+    recv = [torch.empty(1, dtype=torch.float64, device=dev) for _ in range(W)]
+    ops = []
+    for peer in range(W):
+        if peer != rank:
+            ops.append(dist.P2POp(dist.isend, send, peer))
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    assert all(int(recv[p].item()) == p for p in range(W) if p != rank)
+
+
+def all_gather_rows(local, n_total, device=None):
+    """All-gather a float64 table whose row i lives on rank i % W (position i // W there): `local` = this rank's rows in
+    that order; returns the [n_total, R] table in global row order, bit-identical on every rank."""
+    rank, W = world()
+    local = np.asarray(local, dtype=np.float64)
+    if W == 1:
+        return local
+    R = local.shape[1]
+    per = (n_total + W - 1) // W
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+    send = torch.zeros(per, R, dtype=torch.float64, device=dev)
+    send[:len(local)] = torch.from_numpy(local).to(dev)
+    recv = torch.empty(W * per, R, dtype=torch.float64, device=dev)
+    with _nvtx("dist.all_gather_rows"):
+        dist.all_gather_into_tensor(recv, send)
+    table = recv.cpu().numpy().reshape(W, per, R)
+    return np.stack([table[i % W, i // W] for i in range(n_total)]) if n_total else np.zeros((0, R))
 
 
 def all_reduce_rows(rows, device=None):

@@ -1,9 +1,22 @@
 """External Pareto archive (mirror of morl/ep.py:10-31): all policies on the current front."""
-from copy import deepcopy
+from copy import copy, deepcopy
 
 import numpy as np
 
 from .utils import get_ep_indices
+
+
+def _copy_sample(s):
+    """Deep copy of a sample (ep.py:24 of the reference deep-copies every incoming sample). A metadata-only sample -- the stub
+    of a policy whose state lives on another rank (sharded runs: all but 1/W of the offspring), or an objective-only
+    stand-in -- holds nothing but its objective vector and ids, so a shallow copy plus a copy of the vector IS its deep
+    copy, at a tenth of the cost of walking it with copy.deepcopy (1 000 offspring per generation at 48 tasks)."""
+    if getattr(s, "actor_critic", 1) is None and getattr(s, "agent", 1) is None and getattr(s, "env_params", 1) is None:
+        c = copy(s)
+        if s.objs is not None:
+            c.objs = np.array(s.objs, copy=True)
+        return c
+    return deepcopy(s)
 
 
 class EP:
@@ -23,7 +36,7 @@ class EP:
         (ep.py:23-31); the dominance filter runs on the GPU (K5 ep_filter)."""
         new = np.empty(len(sample_batch), dtype=object)
         for i, s in enumerate(sample_batch):
-            new[i] = deepcopy(s)
+            new[i] = _copy_sample(s)
         self.sample_batch = np.append(self.sample_batch, new)
         objs = [np.asarray(s.objs, dtype=np.float64) for s in sample_batch]
         if objs:

@@ -9,7 +9,7 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import finish_predictions, launch_fits
+from .prediction import predict_candidates
 from .utils import get_ep_indices, norm2
 
 
@@ -116,11 +116,11 @@ class Population:
         # ---- prediction: candidates = (sample, weight) pairs with their predicted objectives
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
         fork = bool(getattr(args, 'fork_scoring', False))     # the WorkingMorl/ copy's variant of this routine
-        pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=fork)
-        all_tests = [self._test_weights(opt_graph, sample, args.num_weight_candidates) for sample in self.sample_batch]
+        all_tests, preds, self.last_fits = predict_candidates(
+            opt_graph, self.sample_batch, lambda sample: self._test_weights(opt_graph, sample, args.num_weight_candidates),
+            args.obj_num, cap_threshold=fork, max_tests=args.num_weight_candidates, zero_if_degenerate=fork)
         samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
         tests = [tw for tw in all_tests if len(tw) > 0]
-        preds, self.last_fits = finish_predictions(pending, all_tests, zero_if_degenerate=fork)
         candidates = []
         for sample, tw, pr in zip(samples, tests, preds):
             for w, p in zip(tw, pr):

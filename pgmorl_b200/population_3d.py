@@ -9,7 +9,7 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import finish_predictions, launch_fits
+from .prediction import predict_candidates
 from .utils import generate_weights_batch_dfs, norm2
 
 
@@ -141,13 +141,13 @@ class Population:
         grid = []
         generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
-        pending = launch_fits(opt_graph, [s.optgraph_id for s in self.sample_batch], args.obj_num, cap_threshold=True)
         grid_arr = np.array(grid, dtype=np.float64)
         grid_norm = [norm2(w) for w in grid]
-        all_tests = [self._test_weights(args, opt_graph, sample, grid, grid_arr, grid_norm) for sample in self.sample_batch]
+        all_tests, preds, self.last_fits = predict_candidates(
+            opt_graph, self.sample_batch, lambda sample: self._test_weights(args, opt_graph, sample, grid, grid_arr, grid_norm),
+            args.obj_num, cap_threshold=True, max_tests=args.num_weight_candidates + 1, tests_in_lockstep=True)
         samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
         tests = [tw for tw in all_tests if len(tw) > 0]
-        preds, self.last_fits = finish_predictions(pending, all_tests)
         candidates = []
         for sample, tw, pr in zip(samples, tests, preds):
             for w, p in zip(tw, pr):

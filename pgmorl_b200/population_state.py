@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import kernels as K
+from ._nvtx import rng as _nvtx
 from ._lib import PpoHyper
 from .layout import NetDims
 
@@ -83,14 +84,17 @@ class PopulationMOPG:
         """One MOPG iteration for all P tasks on data already resident in HBM
         (rollout inference -> vector GAE + advantage -> PPO update). Asynchronous."""
         T, N, P, d = self.T, self.N, self.P, self.dims
-        K.policy_forward(self.params, self.obs, d, eps=self.eps, rows_a=self.S,
-                         out=(self.value, self.action, self.logp))
-        K.gae_adv(self.rewards, self.value.view(P, T + 1, N, d.obj), self.masks, self.bad_masks, self.gamma,
-                  self.lam, weights=self.weights, obj_var=self.obj_var, out=(self.returns, self.adv))
-        K.ppo_update(self.params, self.adam_m, self.adam_v, self.adam_step, self.lr, self.obs, self.action,
-                     self.logp, self.value, self.returns.view(P, self.S, d.obj), self.adv.view(P, self.S),
-                     self.perm, self.B, d, hyper=self.hyper, workspace=self.workspace, cluster=self.cluster,
-                     losses=self.losses)
+        with _nvtx("mopg.k1_forward"):
+            K.policy_forward(self.params, self.obs, d, eps=self.eps, rows_a=self.S,
+                             out=(self.value, self.action, self.logp))
+        with _nvtx("mopg.k2_gae_adv"):
+            K.gae_adv(self.rewards, self.value.view(P, T + 1, N, d.obj), self.masks, self.bad_masks, self.gamma,
+                      self.lam, weights=self.weights, obj_var=self.obj_var, out=(self.returns, self.adv))
+        with _nvtx("mopg.k3_ppo_update"):
+            K.ppo_update(self.params, self.adam_m, self.adam_v, self.adam_step, self.lr, self.obs, self.action,
+                         self.logp, self.value, self.returns.view(P, self.S, d.obj), self.adv.view(P, self.S),
+                         self.perm, self.B, d, hyper=self.hyper, workspace=self.workspace, cluster=self.cluster,
+                         losses=self.losses)
         return self.losses
 
     GPU_LAUNCHES_PER_STEP = 4   # K1 forward, K2 GAE/adv, K3 record pack, K3 PPO

@@ -8,6 +8,7 @@ launch of K4 (csrc/k4_fit.cu). Predictions are then objs + f(test weight)."""
 import numpy as np
 
 from . import kernels as K
+from ._nvtx import rng as _nvtx
 from .utils import norm2
 
 
@@ -112,13 +113,15 @@ def model(x, A, a, b, c):
 def launch_fits(opt_graph, node_ids, obj_num, cap_threshold):
     """Build the training data of every node's model and launch all n x M fits (K4) without waiting for them.
     Returns a handle for `finish_predictions`; the caller may do host work that does not need the fits meanwhile."""
-    view = GraphView(opt_graph)
-    xs, ys, ws, ubs = [], [], [], []
-    for k in node_ids:
-        for x, y, w, ub in fit_inputs(view, k, obj_num, cap_threshold):
-            xs.append(x); ys.append(y); ws.append(w); ubs.append(ub)
-    return dict(view=view, node_ids=list(node_ids), obj_num=obj_num, x=xs, y=ys, w=ws, ub=ubs,
-                fits=K.fit_hyperbolic_launch(xs, ys, ws, ubs))                    # all fits in one launch
+    with _nvtx("selection.fit_inputs"):
+        view = GraphView(opt_graph)
+        xs, ys, ws, ubs = [], [], [], []
+        for k in node_ids:
+            for x, y, w, ub in fit_inputs(view, k, obj_num, cap_threshold):
+                xs.append(x); ys.append(y); ws.append(w); ubs.append(ub)
+    with _nvtx("selection.k4_fits"):
+        fits = K.fit_hyperbolic_launch(xs, ys, ws, ubs)                    # all fits in one launch
+    return dict(view=view, node_ids=list(node_ids), obj_num=obj_num, x=xs, y=ys, w=ws, ub=ubs, fits=fits)
 
 
 def finish_predictions(handle, test_weights_per_node, zero_if_degenerate=False):
@@ -147,6 +150,55 @@ def finish_predictions(handle, test_weights_per_node, zero_if_degenerate=False):
     pick = lambda seq: [seq[j] for j in keep]
     return preds, dict(x=pick(handle["x"]), y=pick(handle["y"]), w=pick(handle["w"]), ub=pick(handle["ub"]),
                        theta=theta[keep], status=status[keep], nfev=nfev[keep], cost=cost[keep])
+
+
+def predict_candidates(opt_graph, samples, make_tests, obj_num, cap_threshold, max_tests, zero_if_degenerate=False,
+                       tests_in_lockstep=False):
+    """Test weights and predicted objectives of every population member: -> (all_tests: one [n_i, M] list per member,
+    preds: one [n_i, M] array per member WITH test weights, fit record).
+
+    Single process: all fits in one K4 launch, issued before the host enumerates the test weights so that it runs under
+    that work. Under torch.distributed (sharded runs) the members are split over the ranks
+    (member i on rank i % W): each rank builds the fit inputs, runs K4 and evaluates the models for ITS members only, then
+    one all-gather of a padded float64 table (count, test weights, predictions per member) gives every rank the identical
+    candidate set -- the per-rank cost of the selection front-end stays flat as tasks and GPUs grow together.
+    `tests_in_lockstep`: the test weights consume numpy's global RNG (3 objectives), so every rank enumerates them for
+    every member to keep the streams identical; only fits and predictions are split."""
+    from . import dist as pdist
+    rank, W = pdist.world()
+    n = len(samples)
+    if W == 1 or n < W:
+        pending = launch_fits(opt_graph, [s.optgraph_id for s in samples], obj_num, cap_threshold)
+        all_tests = [make_tests(s) for s in samples]
+        preds, fits = finish_predictions(pending, all_tests, zero_if_degenerate=zero_if_degenerate)
+        return all_tests, preds, fits
+    mine = list(range(rank, n, W))
+    pending = launch_fits(opt_graph, [samples[i].optgraph_id for i in mine], obj_num, cap_threshold)
+    if tests_in_lockstep:
+        everyone = [make_tests(s) for s in samples]
+        my_tests = [everyone[i] for i in mine]
+    else:
+        my_tests = [make_tests(samples[i]) for i in mine]
+    my_preds, fits = finish_predictions(pending, my_tests, zero_if_degenerate=zero_if_degenerate)
+    M = obj_num
+    rows = np.zeros((len(mine), 1 + 2 * max_tests * M))
+    it = iter(my_preds)
+    for j, tw in enumerate(my_tests):
+        k = len(tw)
+        assert k <= max_tests
+        rows[j, 0] = k
+        if k:
+            rows[j, 1:1 + k * M] = np.asarray(tw, dtype=np.float64).reshape(-1)
+            rows[j, 1 + max_tests * M:1 + max_tests * M + k * M] = np.asarray(next(it), dtype=np.float64).reshape(-1)
+    table = pdist.all_gather_rows(rows, n)
+    all_tests, preds = [], []
+    for i in range(n):
+        k = int(table[i, 0])
+        tw = table[i, 1:1 + k * M].reshape(k, M)
+        all_tests.append([tw[j].copy() for j in range(k)])
+        if k:
+            preds.append(table[i, 1 + max_tests * M:1 + max_tests * M + k * M].reshape(k, M).copy())
+    return all_tests, preds, fits
 
 
 def predict_population(opt_graph, node_ids, test_weights_per_node, obj_num, cap_threshold):

@@ -19,6 +19,7 @@ import torch
 
 from . import kernels as K
 from ._lib import check, lib, ptr
+from ._nvtx import rng as _nvtx
 
 
 def _carve(nbytes_by_name):
@@ -126,6 +127,7 @@ class StepPipe:
             self.np_eps[0] = eps_t.numpy() if hasattr(eps_t, "numpy") else eps_t
         if self.graph is None:
             self._capture()
-        self.graph.replay()
-        torch.cuda.current_stream().synchronize()
+        with _nvtx("rollout.step"):
+            self.graph.replay()
+            torch.cuda.current_stream().synchronize()
         return self.h_act
