@@ -85,6 +85,8 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if self.index is None:          # ranks other than 0: one sampler per job (eight concurrent nvidia-smi pollers stall launches)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -560,7 +562,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from pgmorl_b200 import dist as pdist
-        pdist.warm_up_p2p(dev)          # every rank pair's NCCL channel is opened once at start-up, as morl.run does
+        # every rank pair's NCCL channels are opened once at start-up, at the size of one migrated state, as morl.run does
+        pdist.warm_up_p2p(dev, n_elems=pdist.sample_state_len(d))
     pop = PopulationMOPG(d, P, T, N, ppo_epoch=E, num_mini_batch=B, gamma=gamma, device=dev, cluster=args.cluster)
     pop.alloc_snapshots(GEN_ITERS)
     # rank r owns the global tasks {r, r + W, ...} (dist.shard_tasks); inputs seeded per rank
@@ -652,9 +655,9 @@ def main():
     if gb is not None:
         gb.run(); gb.run()             # two untimed boundaries: K4 / K5 / NCCL warm-up (lazy module loading, communicator)
     bnd_log.clear()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank if rank == 0 else None)     # rank 0 samples its GPU; started BEFORE the barrier so that
+    clocks.start()                                                 # the fork of the sampler does not skew the ranks
     barrier()
-    clocks.start()
     t0 = time.perf_counter()
     ms, ms_mopg = run_device(args.steps)
     n_bnd_device = len(bnd_log)
@@ -685,6 +688,12 @@ def main():
         ms, ms_e2e, ms_mopg, ms_e2e_mopg, gw = t.tolist()
         if gen:
             gen["wall_ms"] = gw
+    bnd_max = None
+    if gb is not None and bnd_timed:          # slowest rank's time in each timed boundary (rank 0's breakdown is in per_boundary)
+        tot = torch.tensor([sum(v for k, v in b.items() if k.endswith("_s")) for b in bnd_timed], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        bnd_max = [1e3 * x for x in tot.tolist()]
     picks_equal = None
     if gb is not None and world > 1:      # every rank must have picked the same (elite, weight) pairs in every generation
         hsh = int(hashlib.sha256(repr(gb.picks).encode()).hexdigest()[:15], 16)
@@ -757,7 +766,8 @@ def main():
             gen["unit"] = "env-steps/s over one generation (GEN_ITERS x [H2D + K1-K3 + D2H] + record exchange + selection + migration), wall clock"
             line["generation"] = gen
             line["boundaries_in_timed_region"] = {"device_loop": n_bnd_device, "e2e_loop": len(bnd_timed) - n_bnd_device,
-                                                  "per_boundary": bnd_timed, "picks_identical_on_all_ranks": picks_equal}
+                                                  "per_boundary": bnd_timed, "boundary_ms_max_over_ranks": bnd_max,
+                                                  "picks_identical_on_all_ranks": picks_equal}
         if world == 1 and not args.no_selection:
             try:
                 line["selection"] = selection_leg(cpu=not args.no_cpu_baseline)

@@ -174,24 +174,26 @@ def migrate_states(plan, get_state, put_state, n_state, device=None, dtype=torch
             put_state(task, t)
 
 
-def warm_up_p2p(device=None):
-    """Establish the point-to-point connection of every rank pair once (NCCL opens a pair's channel lazily at its first
-    send / recv, ~20-50 ms each: without this the first generations of an 8-GPU run spend up to 1.5 s in `migrate_states`
-    while new pairs keep appearing). One batched exchange of a single element with every peer."""
+def warm_up_p2p(device=None, n_elems=1, rounds=2):
+    """Establish the point-to-point connection of every rank pair once (NCCL opens a pair's channels lazily at first use,
+    ~20-50 ms each: without this the first generations of an 8-GPU run spend up to 1.5 s in `migrate_states` while new
+    pairs keep appearing). `rounds` batched exchanges of `n_elems` float64 with every peer -- pass the size of one migrated
+    state (`sample_state_len`) so that the channels a message of that size uses are all open."""
     rank, W = world()
     if W == 1:
         return
     dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
-    send = torch.full((1,), float(rank), dtype=torch.float64, device=dev)
-    recv = [torch.empty(1, dtype=torch.float64, device=dev) for _ in range(W)]
-    ops = []
-    for peer in range(W):
-        if peer != rank:
-            ops.append(dist.P2POp(dist.isend, send, peer))
-            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
-    assert all(int(recv[p].item()) == p for p in range(W) if p != rank)
+    send = torch.full((max(int(n_elems), 1),), float(rank), dtype=torch.float64, device=dev)
+    recv = [torch.empty_like(send) for _ in range(W)]
+    for _ in range(rounds):
+        ops = []
+        for peer in range(W):
+            if peer != rank:
+                ops.append(dist.P2POp(dist.isend, send, peer))
+                ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    assert all(int(recv[p][0].item()) == p for p in range(W) if p != rank)
 
 
 def all_gather_rows(local, n_total, device=None):

@@ -32,15 +32,18 @@ class EP:
             return deepcopy(self.obj_batch[idx]), deepcopy(self.sample_batch[idx])
 
     def update(self, sample_batch):
-        """Append deep copies of `sample_batch`, keep the non-dominated set sorted by objective 0
-        (ep.py:23-31); the dominance filter runs on the GPU (K5 ep_filter)."""
-        new = np.empty(len(sample_batch), dtype=object)
-        for i, s in enumerate(sample_batch):
-            new[i] = _copy_sample(s)
-        self.sample_batch = np.append(self.sample_batch, new)
+        """Append `sample_batch`, keep the non-dominated set sorted by objective 0 (ep.py:23-31); the dominance filter
+        runs on the GPU (K5 ep_filter). The reference deep-copies every incoming sample and then drops the dominated
+        ones; here the filter runs first on the objective vectors and only the SURVIVING newcomers are copied -- the same
+        archive (same members, same order, independent copies), without 100+ discarded policy copies per generation."""
+        n_old = len(self.sample_batch)
         objs = [np.asarray(s.objs, dtype=np.float64) for s in sample_batch]
         if objs:
             self.obj_batch = np.vstack([self.obj_batch] + objs) if len(self.obj_batch) > 0 else np.vstack(objs)
         if len(self.obj_batch) == 0:
             return
-        self.index(get_ep_indices(self.obj_batch))
+        idx = np.array(get_ep_indices(self.obj_batch), dtype=int)
+        kept = np.empty(len(idx), dtype=object)
+        for j, i in enumerate(idx.tolist()):
+            kept[j] = self.sample_batch[i] if i < n_old else _copy_sample(sample_batch[i - n_old])
+        self.obj_batch, self.sample_batch = self.obj_batch[idx], kept

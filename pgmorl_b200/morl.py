@@ -181,8 +181,10 @@ def run(args, device="cuda", cluster=0, save=True):
         sample.optgraph_id = opt_graph.insert(deepcopy(scalarization.weights), deepcopy(sample.objs), -1)
     state_template = None
     if W > 1:
-        pdist.warm_up_p2p(device if device.type == "cuda" else None)     # open every rank pair's channel once, up front
         state_template = Sample.copy_from(elite_batch[0])
+        # open every rank pair's channels once, up front, at the size of one migrated state
+        pdist.warm_up_p2p(device if device.type == "cuda" else None,
+                          n_elems=pdist.sample_state_len(state_template.actor_critic.dims))
         for i, sample in enumerate(elite_batch):
             owner = pdist.owner_of(i, W)
             elite_batch[i] = sample if owner == rank else Sample.stub(sample.objs, sample.optgraph_id)
