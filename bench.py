@@ -459,11 +459,17 @@ def api_leg(d, P, T, N, E, B, gamma, device, cluster):
     return out
 
 
-def k3_source_hash():
+K3_SOURCES = {      # the files a kernel family is compiled from (pgmorl_b200/csrc/)
+    "k3_ppo_fast_kernel": ("k3_fast.cuh", "k3_ppo.cu", "net.cuh", "common.cuh"),
+    "k3_tc_kernel": ("k3_tc.cuh", "tc.cuh", "tc_pair.cuh", "k3_ppo.cu", "net.cuh", "common.cuh"),
+    "k3_tcw_kernel": ("k3_tcw.cuh", "tc.cuh", "tc_pair.cuh", "k3_ppo.cu", "net.cuh", "common.cuh"),
+}
+
+
+def k3_source_hash(kernel="k3_ppo_fast_kernel"):
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "pgmorl_b200", "csrc", "*"))):
-        if os.path.basename(f).startswith(("k3_", "net.", "common.", "tc.", "tc_pair.")):
-            h.update(open(f, "rb").read())
+    for f in K3_SOURCES[kernel.split(":")[0]]:
+        h.update(open(os.path.join(ROOT, "pgmorl_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -478,7 +484,7 @@ def measured_traffic(kernel):
     e = t.get(kernel)
     if not e:
         return None, None
-    if e.get("source_sha") != k3_source_hash():
+    if e.get("source_sha") != k3_source_hash(kernel):
         return None, f"stale: {e.get('csv')} was captured at source hash {e.get('source_sha')}"
     return e["dram_bytes"], e.get("csv")
 
@@ -754,7 +760,9 @@ def main():
             "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_e2e,
                     "mopg_only_ms_per_step": ms_e2e_mopg, "timer": "host wall clock, blocking H2D -> K1-K3 -> D2H per step",
                     "h2d_bytes_per_step": pop.h2d_bytes, "d2h_bytes_per_step": pop.d2h_bytes},
-            "gpu_launches": launches_per_step * args.steps * 2,
+            # K1, K2, pack, K3 per step in both timed loops; per generation boundary the archive filter (2), K4 (1), K5 init /
+            # finish (2) and one scoring + one pick launch per selected task
+            "gpu_launches": launches_per_step * args.steps * 2 + len(bnd_timed) * (5 + 2 * n_tasks),
             "roofline": roofline,
             "stages_ms": {"k1_forward": float(stages[0]), "k2_gae_adv": float(stages[1]), "k3_pack_ppo": k3_ms},
             "stage_hbm_gbs": {"k1_forward": P * (S + N) * k1b / (stages[0] * 1e-3) / 1e9,

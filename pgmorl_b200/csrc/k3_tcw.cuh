@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     double *sh_d = (double *)(smem_raw + sl.misc + 2304);
     uint64_t *mbars = (uint64_t *)(smem_raw + sl.misc + 2304 + 32);     // 0 chain, 1-3 forward stages, 4 weight grads, 5-6 G1X pairs, 7 tile done
     uint32_t *tmem_ptr_s = (uint32_t *)(smem_raw + sl.misc + 2304 + 96);
+    uint64_t *mbarN = (uint64_t *)(smem_raw + sl.misc + 2304 + 104);    // counts the bytes of the cluster's squared-norm partials
     const float *b2s = FP, *bhs = FP + 64, *lss = FP + 96;
 
     // global state of my half
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
     if (warp == 0) tc::tmem_alloc(tmem_ptr_s, 512);
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) tc::mbar_init(mbars + i, 1);
+        tc::mbar_init(mbarN, 1);
         tc::fence_mbar_init();
     }
     // publish one parameter / four consecutive parameters (half-local index) to wherever the kernels read them:
@@ -784,13 +786,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k3_tcw_kernel(const K3Args a, c
         // squared norm: per-warp partials straight into every CTA of the cluster; the barrier is the only synchronisation
         sq = warp_sum(sq);
         float *ssq2 = ssqS + 64 * (s & 1);                  // slots alternate by step parity
+        // (round 2) the norm exchange needs no cluster barrier: every partial travels with st.async and completes the
+        // RECEIVER's mbarrier (8 warps x C CTAs x 4 bytes per step, the CTA's own partials included); what barrier (2) also
+        // separated -- reading the peers' GR slices before, publishing new weights after -- is ordered by barriers (1) and (3)
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbarN)), "r"(32 * C) : "memory");
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < C; ++k)
-                st_dsmem1(mapa_u32(smem_u32(ssq2 + (int)rank * 8 + warp), (uint32_t)k), sq);
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                             ::"r"(mapa_u32(smem_u32(ssq2 + (int)rank * 8 + warp), (uint32_t)k)), "r"(__float_as_uint(sq)),
+                               "r"(mapa_u32(smem_u32(mbarN), (uint32_t)k)) : "memory");
         }
         TWT(31)
-        sync_group<2>();
+        __syncthreads();                                    // sh_d (Adam scalars) written by thread 0
+        tc::mbar_wait(mbarN, (uint32_t)(s & 1));
         TWT(32)
         float tot = 0.f;
 #pragma unroll

@@ -6,7 +6,7 @@
 Reads `dram__bytes_read.sum + dram__bytes_write.sum` of the (single) kernel in an `ncu --set full` report, writes the raw
 metric page to the CSV given (committed next to this file) and records {KEY: {dram_bytes, csv, source_sha, kernel}} in
 profiles/traffic.json. KEY = "<kernel family>:<bench config>", e.g. "k3_ppo_fast_kernel:c2". `source_sha` is the hash of the
-K3 sources at capture time (bench.k3_source_hash): bench.py reports `traffic: null` with the reason when the sources have
+sources of that kernel family at capture time (bench.k3_source_hash): bench.py reports `traffic: null` with the reason when the sources have
 changed since, instead of a stale constant.
 """
 import csv
@@ -38,7 +38,7 @@ def main(rep, key, csv_out):
     table[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": vals[col["Kernel Name"]],
                   "duration": float(vals[col["gpu__time_duration.sum"]].replace(",", "")),
                   "duration_unit": units[col["gpu__time_duration.sum"]] + " (under ncu, cold cache)",
-                  "csv": os.path.relpath(csv_out, ROOT), "source_sha": k3_source_hash()}
+                  "csv": os.path.relpath(csv_out, ROOT), "source_sha": k3_source_hash(key)}
     json.dump(table, open(path, "w"), indent=1)
     print(key, table[key])
 
