@@ -31,6 +31,11 @@ int pgm_tc_layout_probe(float *out, int M, int N, int a_mn, int b_mn, int fillA,
 int pgm_tc_mma_bench(float *out, int M, int N, int a_mn, int b_mn, int nmma, int nacc, int a_step, int b_step,
                      void *stream);
 
+/* FP32 FMA peak probe (csrc/diag/ffma_peak.cu): `ctas` CTAs x 512 threads, each thread `iters` x 64 packed FFMA2 on 16
+ * independent accumulators; out [ctas * 512] floats. FLOPs of one launch = ctas * 512 * iters * 64 * 2 lanes * 2. bench.py
+ * times it with CUDA events (2 CTAs per SM) and uses the result as the denominator of the FP32-FFMA roofline. */
+int pgm_ffma2_burn(float *out, int ctas, int iters, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,7 @@ DIAG_SIGNATURES = {
     "pgm_tc_selftest": (_I, [_P, _I, _P]),
     "pgm_tc_mma_bench": (_I, [_P] + [_I] * 8 + [_P]),
     "pgm_tc_layout_probe": (_I, [_P] + [_I] * 19 + [_P]),
+    "pgm_ffma2_burn": (_I, [_P, _I, _I, _P]),
 }
 _diag = None
 

@@ -37,8 +37,8 @@ def test_diagnostics_live_in_their_own_library(library):
     """The tcgen05 probes are exported by libpgmorl_b200_diag.so only (include/pgmorl_b200_diag.h)."""
     from pgmorl_b200 import _lib
     diag = _lib.diag_lib()
-    syms = [s for s in header_symbols("pgmorl_b200_diag.h") if s.startswith("pgm_tc_")]
-    assert sorted(syms) == sorted(_lib.DIAG_SIGNATURES) and len(syms) == 3
+    syms = [s for s in header_symbols("pgmorl_b200_diag.h") if s.startswith(("pgm_tc_", "pgm_ffma2_"))]
+    assert sorted(syms) == sorted(_lib.DIAG_SIGNATURES) and len(syms) == 4
     for s in syms:
         assert hasattr(diag, s)
         assert not hasattr(library, s), f"{s} must not be exported by the product library"
