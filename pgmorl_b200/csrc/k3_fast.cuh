@@ -123,9 +123,12 @@ __device__ __forceinline__ void layer_fwd_fast(const float *__restrict__ in, int
 // TAIL = 5  : as TAIL = 4, and the squared-norm partials travel with st.async ... mbarrier::complete_tx into every CTA's
 //             mbarrier: NO cluster barrier is left inside the step, the optimiser step is pure dataflow over three mbarriers
 //             (gradient slices in, norm partials in, parameter slices in). Ordering argument in DESIGN.md section 4.
+// TAIL = 6  : as TAIL = 5, and the slices that hold only dW2 (5 of 8 at Walker2d dims, 70 % of the bytes) leave EARLY: dW2 is
+//             final after the {dW2, dz1} phase of the step's last chunk, so its tiles are written to the image there and the
+//             bulk copies of the W2-only slices fly under phase C, the row-split combine and the rest of the image write.
 template <int C, int TM, int TAIL>
 __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a) {
-    constexpr bool RA = TAIL == 1, MC = TAIL >= 2, GL = TAIL == 3, BP = TAIL >= 4, NB = TAIL == 5;
+    constexpr bool RA = TAIL == 1, MC = TAIL >= 2, GL = TAIL == 3, BP = TAIL >= 4, NB = TAIL >= 5, EP = TAIL == 6;
     constexpr int RC = 16 * TM;
     constexpr int G = C / 2;
     constexpr int NU = 4;                 // gather items per thread (RC * RSG/4 <= NU * 256, checked on host)
@@ -392,6 +395,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                     gW2[3][0] = ffma2_s(dv.w, hv.x, gW2[3][0]); gW2[3][1] = ffma2_s(dv.w, hv.y, gW2[3][1]);
                     if (tk == 0) { gb2[0] += dv.x; gb2[1] += dv.y; gb2[2] += dv.z; gb2[3] += dv.w; }
                 }
+                if (EP && c == nchunk - 1) {      // dW2 of this step is complete: its tiles go to the image now
+                    const int oW2e = (int)(n.W2 - n.W1);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        *reinterpret_cast<ulonglong2 *>(gP + oW2e + (4 * tj + jj) * LDH + 4 * tk) = make_ulonglong2(gW2[jj][0], gW2[jj][1]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
                 u64 acc[TM][2];
 #pragma unroll
                 for (int i = 0; i < TM; ++i) acc[i][0] = acc[i][1] = 0ull;
@@ -421,6 +431,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
                 }
             }
             __syncthreads();
+            if (EP && c == nchunk - 1) {          // W2-only slices -> their owners' slots, under phase C and the image write
+                if (tid == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                 ::"r"(smem_u32(&mbarR)), "r"(G * 16 * (sl1 - sl0)) : "memory");
+                if (tid < G) {
+                    const int o0 = tid * per4, o1 = min(n4, o0 + per4);
+                    const int w0 = (int)(n.W2 - n.W1) >> 2, w1 = (int)(n.b2 - n.W1) >> 2;
+                    if (o1 > o0 && o0 >= w0 && o1 <= w1) {
+                        const uint32_t dst = mapa_u32(smem_u32(slotB) + 16u * (uint32_t)(g * per4), (uint32_t)(half * G + tid));
+                        const uint32_t mb = mapa_u32(smem_u32(&mbarR), (uint32_t)(half * G + tid));
+                        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst), "r"(smem_u32(gP) + 16u * (uint32_t)o0), "r"(16 * (o1 - o0)), "r"(mb) : "memory");
+                    }
+                }
+            }
             PGM_TR(5)
 
             // ---------------- phase C: dW1/db1 on slots [0, nW1), dWh/dbh/dls on the rest ----------------
@@ -526,9 +551,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             const int tj = tid & 15, tk = tid >> 4;
             const int ob1 = (int)(n.b1 - n.W1), oW2 = (int)(n.W2 - n.W1), ob2 = (int)(n.b2 - n.W1);
             const int oWh = (int)(n.Wh - n.W1), obh = (int)(n.bh - n.W1), ols = (int)(n.ls - n.W1);
+            if (!EP) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                emit16(oW2 + (4 * tj + jj) * LDH + 4 * tk, make_ulonglong2(gW2[jj][0], gW2[jj][1]));
+                for (int jj = 0; jj < 4; ++jj)
+                    emit16(oW2 + (4 * tj + jj) * LDH + 4 * tk, make_ulonglong2(gW2[jj][0], gW2[jj][1]));
+            }
             if (tk == 0) emit16(ob2 + 4 * tj, make_ulonglong2(pack2(gb2[0], gb2[1]), pack2(gb2[2], gb2[3])));
             if (isW1 && rs1 == 0) {
 #pragma unroll
@@ -558,12 +585,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k3_ppo_fast_kernel(const K3Args a
             // my partial image -> the per-source slot of every slice owner, by the bulk-copy engine; no barrier (1)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // my st.shared, before the async proxy reads them
             __syncthreads();
-            if (tid == 0)
+            if (!EP && tid == 0)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                              ::"r"(smem_u32(&mbarR)), "r"(G * 16 * (sl1 - sl0)) : "memory");
             if (tid < G) {
                 const int o0 = tid * per4, o1 = min(n4, o0 + per4);
-                if (o1 > o0) {
+                const int w0 = (int)(n.W2 - n.W1) >> 2, w1 = (int)(n.b2 - n.W1) >> 2;
+                if (o1 > o0 && !(EP && o0 >= w0 && o1 <= w1)) {      // (TAIL = 6: the W2-only slices left after phase B)
                     const uint32_t dst = mapa_u32(smem_u32(slotB) + 16u * (uint32_t)(g * per4), (uint32_t)(half * G + tid));
                     const uint32_t mb = mapa_u32(smem_u32(&mbarR), (uint32_t)(half * G + tid));
                     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -621,6 +621,8 @@ static int k3_tcw_resident_clusters(int rs) {
 //   tail 3  3.839  tail 2 + gradient exchange through L2 scratch slots
 //   tail 4  3.712  tail 2 + gradient reduce-scatter pushed by cp.async.bulk shared::cta -> shared::cluster, first barrier gone
 //   tail 5  3.575  tail 4 + norm partials by st.async with mbarrier completion: no cluster barrier left in the step (default)
+//   tail 6  3.557* tail 5 + the W2-only gradient slices pushed right after the {dW2, dz1} phase (*same box: tail 5 3.525;
+//                  the mid-phase proxy fence costs more than the early transfer saves)
 // A tail can be forced per call by OR-ing a flag into `cluster` (tests, A/B) or per process with PGM_K3_TAIL=0..5.
 constexpr int K3_DEFAULT_TAIL = 5;
 constexpr int K3_CLUSTER_TAIL2 = 0x100;    // tail 1
@@ -629,14 +631,16 @@ constexpr int K3_CLUSTER_TAILGL = 0x400;   // tail 3
 constexpr int K3_CLUSTER_TAIL0 = 0x800;    // tail 0
 constexpr int K3_CLUSTER_TAILBP = 0x1000;  // tail 4
 constexpr int K3_CLUSTER_TAILNB = 0x2000;  // tail 5
+constexpr int K3_CLUSTER_TAILEP = 0x4000;  // tail 6
 constexpr int K3_CLUSTER_FLAGS = K3_CLUSTER_TAIL2 | K3_CLUSTER_TAILMC | K3_CLUSTER_TAILGL | K3_CLUSTER_TAIL0 | K3_CLUSTER_TAILBP |
-                                 K3_CLUSTER_TAILNB;
+                                 K3_CLUSTER_TAILNB | K3_CLUSTER_TAILEP;
 
 static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cluster, int sms) {
     NetLayout L(O, A, M);
     const bool tail2 = (cluster & K3_CLUSTER_TAIL2) != 0, tailmc = (cluster & K3_CLUSTER_TAILMC) != 0;
     const bool tailgl = (cluster & K3_CLUSTER_TAILGL) != 0, tail0 = (cluster & K3_CLUSTER_TAIL0) != 0;
     const bool tailbp = (cluster & K3_CLUSTER_TAILBP) != 0, tailnb = (cluster & K3_CLUSTER_TAILNB) != 0;
+    const bool tailep = (cluster & K3_CLUSTER_TAILEP) != 0;
     cluster &= ~K3_CLUSTER_FLAGS;
     pl.tc = false; pl.tcw = false; pl.tail = 0; pl.off_mv = 0;
     // wide observations (Humanoid): the streamed tensor-core kernel; row split over as many CTAs per half as fill the SMs
@@ -733,8 +737,8 @@ static int k3_plan(K3Plan &pl, int P, int S, int mb, int O, int A, int M, int cl
         pl.stage_floats = s0 > s1 ? s0 : s1;
         // step tail: default from K3_DEFAULT_TAIL; others on request (cluster flags, or PGM_K3_TAIL=0|1|2 in the
         // environment for whole-program A/B runs)
-        static const int env_tail = [] { const char *e = getenv("PGM_K3_TAIL"); return (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : -1; }();
-        pl.tail = tail0 ? 0 : (tail2 ? 1 : (tailmc ? 2 : (tailgl ? 3 : (tailbp ? 4 : (tailnb ? 5 : (env_tail >= 0 ? env_tail : K3_DEFAULT_TAIL))))));
+        static const int env_tail = [] { const char *e = getenv("PGM_K3_TAIL"); return (e && e[0] >= '0' && e[0] <= '6') ? e[0] - '0' : -1; }();
+        pl.tail = tail0 ? 0 : (tail2 ? 1 : (tailmc ? 2 : (tailgl ? 3 : (tailbp ? 4 : (tailnb ? 5 : (tailep ? 6 : (env_tail >= 0 ? env_tail : K3_DEFAULT_TAIL)))))));
         if (pl.tail == 1 && !(pl.G >= 2 && k3_fast_smem_bytes(L, pl.TM, pl.RSS, pl.NHP, pl.stage_floats, pl.G, true) <= 227 * 1024))
             pl.tail = 0;
         if (pl.tail >= 2 && pl.G < 2) pl.tail = 0;
@@ -793,6 +797,9 @@ static int k3_launch_c(const K3Args &a, const K3Plan &pl, int P, cudaStream_t st
             if (pl.tail == 5)
                 return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 5>, C, a, pl, P, st)
                                   : k3_launch_k(k3_ppo_fast_kernel<C, 4, 5>, C, a, pl, P, st);
+            if (pl.tail == 6)
+                return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 6>, C, a, pl, P, st)
+                                  : k3_launch_k(k3_ppo_fast_kernel<C, 4, 6>, C, a, pl, P, st);
 
             return pl.TM == 2 ? k3_launch_k(k3_ppo_fast_kernel<C, 2, 0>, C, a, pl, P, st)
                               : k3_launch_k(k3_ppo_fast_kernel<C, 4, 0>, C, a, pl, P, st);

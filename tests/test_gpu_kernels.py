@@ -293,6 +293,7 @@ TAILGL = 0x400    # TAILMC + gradient exchange through L2 scratch slots instead 
 TAIL0 = 0x800     # the plain three-barrier DSMEM tail
 TAILBP = 0x1000   # TAILMC + gradient reduce-scatter pushed by cp.async.bulk (shared::cta -> shared::cluster), one barrier left
 TAILNB = 0x2000   # TAILBP + norm partials by st.async with mbarrier completion: no cluster barrier inside the step
+TAILEP = 0x4000   # TAILNB + the W2-only gradient slices are pushed right after the {dW2, dz1} phase
 
 
 @pytest.mark.parametrize("cluster", [4, 8, 16])
@@ -307,7 +308,7 @@ def test_k3_step_tails_bit_identical(name, P, T, N, B, cluster):
     hyper = K.PpoHyper(entropy_coef=0.01)
     lr = dev(np.array([3e-4, 2.5e-4, 1e-4][:P]), torch.float64)
     out = []
-    for cl in (cluster, cluster | TAIL0, cluster | TAIL2, cluster | TAILMC, cluster | TAILGL, cluster | TAILBP, cluster | TAILNB):
+    for cl in (cluster, cluster | TAIL0, cluster | TAIL2, cluster | TAILMC, cluster | TAILGL, cluster | TAILBP, cluster | TAILNB, cluster | TAILEP):
         gp, gm, gv = dev(cur), torch.zeros(P, d.n_par, device="cuda"), torch.zeros(P, d.n_par, device="cuda")
         gstep = torch.zeros(P, dtype=torch.int32, device="cuda")
         losses = K.ppo_update(gp, gm, gv, gstep, lr, dev(pk["obs"]), dev(pk["action"]), dev(pk["logp"]), dev(pk["value"]),
