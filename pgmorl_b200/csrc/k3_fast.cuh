@@ -6,11 +6,15 @@
 // Chunk pipeline (each arrow is one __syncthreads):
 //   records landed -> L1 fwd -> [issue next gather] L2 fwd -> head + per-element loss terms
 //   -> per-row loss (actor) -> dz2 -> dW2, db2, dz1 -> {dW1 | dWh} on disjoint thread groups
-// Step tail, all through distributed shared memory (no global traffic, three cluster barriers):
-//   combine row-split partials -> partial gradient image in OWN smem -> barrier -> each CTA reduces
-//   a 1/G slice over its G peers (ld.shared::cluster), pushes its squared-norm partial to every CTA
-//   -> barrier -> clip + Adam on the slice (moments of the slice live in smem for the whole launch),
-//   updated parameters pushed into every peer's resident image (st.shared::cluster) -> barrier.
+// Step tail = all-reduce of the half's gradient + Adam, template parameter TAIL (all variants bit-identical; A/B table in
+// k3_ppo.cu). Default (TAIL = 5), no cluster barrier inside the step:
+//   combine row-split partials -> partial gradient image in OWN smem -> 8 threads issue one cp.async.bulk per slice owner
+//   (smem -> the owner's per-source slot, completing the owner's mbarrier R) -> owner adds its G slots in fixed order,
+//   sends its squared-norm partial to every CTA with st.async (mbarrier N) -> clip + Adam on the slice (moments of the slice
+//   live in smem for the whole launch) -> updated slice to an L2 staging row, ONE TMA bulk copy with cluster multicast lands
+//   it in every resident image of the half (mbarrier S).
+// TAIL = 0 is the round-1 form: three barrier.cluster, partials pulled with ld.shared::cluster, parameters pushed with
+// st.shared::cluster.
 #pragma once
 
 namespace pgm {

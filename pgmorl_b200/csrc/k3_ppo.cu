@@ -13,9 +13,13 @@
 //              runs mb/G rows                                            (small populations)
 // Per step every CTA: gathers its rows' packed records (cp.async, double buffered), runs
 // forward + hand-derived backward on 16*TM-row chunks with weights resident in shared memory,
-// writes its partial gradient to an L2-resident scratch slot, and after a cluster barrier
-// reduces + Adam-updates a 1/G slice of its half (fixed summation order -> deterministic).
-// Three cluster barriers per step: partial grads -> squared-norm partials -> new parameters.
+// and takes part in an all-reduce of the half's gradient: reduce-scatter to the G slice owners
+// (fixed summation order -> deterministic), norm exchange over all C CTAs, clip + Adam on the
+// slice, all-gather of the new parameters. The generic kernel in this file does it through
+// L2 scratch slots and three cluster barriers per step (any dims, incl. C == 1); the fast
+// kernel for small networks (k3_fast.cuh) keeps everything in (distributed) shared memory and
+// runs the exchange as barrier-free dataflow (bulk copies + st.async into mbarriers, TMA
+// multicast for the parameters).
 //
 // FP32 FFMA throughout; Adam bias corrections in double.
 #include <cooperative_groups.h>
