@@ -182,9 +182,8 @@ class GenerationBoundary:
         """prediction_guided_selection with the CPU oracle: scipy least_squares for every fit, python greedy scoring."""
         from copy import deepcopy
         from oracle import selection_oracle as so
-        from pgmorl_b200.prediction import GraphView, fit_inputs, model
         pop, graph, args, M = self.population, self.graph, self.args, self.M
-        view = GraphView(graph)
+        view = so.GraphArrays(graph)
         cands = []
         for s in pop.sample_batch:
             tw = pop._test_weights(graph, s, args.num_weight_candidates) if M == 2 else None
@@ -192,10 +191,10 @@ class GenerationBoundary:
                 raise NotImplementedError("CPU boundary: 2-objective configs only")
             if len(tw) == 0:
                 continue
-            theta = [so.fit_scipy(x, y, w, ub).x for x, y, w, ub in fit_inputs(view, s.optgraph_id, M, False)]
+            theta = [so.fit_scipy(x, y, w, ub).x for x, y, w, ub in so.fit_inputs(view, s.optgraph_id, M, False)]
             t = np.array(tw, dtype=np.float64)
             t = t / t.sum(axis=1, keepdims=True)
-            pred = view.objs[s.optgraph_id][None, :] + np.stack([model(t[:, m], *theta[m]) for m in range(M)], axis=1)
+            pred = view.objs[s.optgraph_id][None, :] + np.stack([so.model(t[:, m], *theta[m]) for m in range(M)], axis=1)
             cands += [(s, w, p) for w, p in zip(tw, pred)]
         best = so.greedy_select_2d(np.asarray(self.ep.obj_batch), np.array([c[2] for c in cands]), args.sparsity,
                                    args.num_tasks)[0]

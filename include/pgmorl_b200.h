@@ -175,6 +175,34 @@ int pgm_fit_hyperbolic_f64(const double *x, const double *y, const double *w, co
                            int F, int Kmax, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * K4 front-end  training data of the prediction models (FLOAT64 compares, bit-identical to numpy).
+ * Replaces the neighbourhood search and the widening loop of collect_nearest_data / predict_hyperbolic
+ * (morl/population_2d.py:12-21,37-54, morl/population_3d.py:13-21,33-49) for a whole population in one launch.
+ * Opt-graph as flat arrays: objs [n_nodes,M]; the E edges (source -> successor) ordered by source node, then by
+ * successor (the order the reference walks opt_graph.succ): parent [E] = source node, edge_w [E,M] = successor weight
+ * divided by its sum, edge_dy [E,M] = delta_objs of the successor.
+ *
+ * pgm_fit_neighbours_f64: per member b (opt-graph node node_ids[b]) the edges whose source node i satisfies
+ *   |objs_k - objs_i| < |objs_k| * threshold in every objective, threshold doubled from 0.1 until those edges carry
+ *   more than 3 successor weights that are pairwise >= 1e-5 apart (first-occurrence scan), or -- cap_threshold != 0, the
+ *   3-objective variant -- until threshold >= 1, or until the threshold has overflowed to +inf (where the reference
+ *   would loop forever). klen [n] = number of edges, steps [n] = doublings done (threshold = 0.1 * 2^steps, sigma =
+ *   0.03 * 2^steps), edge_idx [n,E] = the edges in order (first klen[b] entries of row b).
+ * pgm_fit_gather_f64: the K4 inputs of the n*M fits (fit f = b*M + objective): x, y [n*M,Kmax] = edge_w / edge_dy
+ *   columns, ub [n*M,4] = (clip(max y - min y, 1, 500), 20, 5, 500) (population_2d.py:100-104), klen_f [n*M], and
+ *   source [n,Kmax] = source node of every listed edge. Kmax >= max(klen). The Gaussian point weights
+ *   exp(-(dist / sigma)^2 / 2) (population_2d.py:90-96) need numpy's exp bit for bit and are formed by the host from
+ *   `source`.
+ * M in 2..4; the opt-graph must fit one CTA's shared memory (E*(8M+4) + 2*n_nodes <= 200 KB).
+ */
+int pgm_fit_neighbours_f64(const double *objs, int n_nodes, int M, const int32_t *parent, int E, const double *edge_w,
+                           const int32_t *node_ids, int n, int cap_threshold, int32_t *klen, int32_t *steps,
+                           int32_t *edge_idx, void *stream);
+int pgm_fit_gather_f64(const int32_t *edge_idx, const int32_t *klen, int n, int E, int M, const int32_t *parent,
+                       const double *edge_w, const double *edge_dy, int Kmax, double *x, double *y, double *ub,
+                       int32_t *klen_f, int32_t *source, void *stream);
+
+/* ---------------------------------------------------------------------------
  * K5  Pareto filtering, exact hypervolume / sparsity, greedy candidate pick (all FLOAT64, and
  * bit-exact with the reference: same summation order, separate multiply / add, no FMA contraction).
  */

@@ -607,3 +607,88 @@ def qr_jacobi_svd(A, sweeps=60):
     s = s[order]; B = B[:, order]; V = V[:, order]
     UR = np.where(s > 0, B / np.where(s > 0, s, 1.0), 0.0)
     return Q[:, :n] @ UR, s, V.T
+
+
+# ------------------------------------------------------------------------------------------------
+# training data of the prediction models: collect_nearest_data + the widening loop
+# (population_2d.py:12-21,37-54,90-104; population_3d.py:13-21,33-49), one population member at a
+# time with the reference's scalar numpy expressions. Pinned bit for bit by the recorded fit inputs
+# of tests/golden/selection_{2d,3d}.npz (tests/test_host_selection.py); the product computes the same
+# data for the whole population at once (csrc/k4_inputs.cu + pgmorl_b200/prediction.py).
+# ------------------------------------------------------------------------------------------------
+def _norm2(v):
+    """np.linalg.norm of a real 1-D vector: sqrt of the BLAS dot product (numpy/linalg/_linalg.py, ord=None)."""
+    v = np.asarray(v)
+    return float(np.sqrt(v.dot(v)))
+
+
+class GraphArrays:
+    """Flat arrays over an opt-graph (lists `objs`, `weights`, `delta_objs`, `succ` as morl/opt_graph.py keeps them),
+    edges in the order collect_nearest_data walks them: by node, then by successor."""
+
+    def __init__(self, opt_graph):
+        self.objs = np.array([np.asarray(o, dtype=np.float64) for o in opt_graph.objs])
+        parents, children = [], []
+        for i, succ in enumerate(opt_graph.succ):
+            for s in succ:
+                parents.append(i); children.append(s)
+        self.parent = np.array(parents, dtype=np.int64)
+        self.child = np.array(children, dtype=np.int64)
+        # successor weights normalised to sum 1 (population_2d.py:19) and their objective gains
+        self.edge_w = np.array([np.asarray(opt_graph.weights[s], dtype=np.float64) / np.sum(np.asarray(opt_graph.weights[s], dtype=np.float64))
+                                for s in children]).reshape(len(children), -1)
+        self.edge_dy = np.array([np.asarray(opt_graph.delta_objs[s], dtype=np.float64) for s in children]).reshape(len(children), -1)
+
+
+def _enough_distinct(weights):
+    """More than 3 pairwise-distinct weights (L2 distance >= 1e-5), first-occurrence scan (population_2d.py:39-49)."""
+    cnt = 0
+    for i in range(len(weights)):
+        distinct = True
+        for j in range(i):
+            if _norm2(weights[i] - weights[j]) < 1e-5:
+                distinct = False
+                break
+        if distinct:
+            cnt += 1
+            if cnt > 3:
+                return True
+    return False
+
+
+def fit_inputs(view, k, obj_num, cap_threshold, with_steps=False):
+    """Training data of the model of node k: per objective (x, y, w, ub). `cap_threshold` reproduces the
+    3-objective variant's stop at threshold >= 1 (population_3d.py:46); the 2-objective one widens until
+    more than 3 distinct weights are found (population_2d.py:50). Where the reference would widen forever
+    (fewer than 4 distinct weights in the whole graph) the loop stops once the threshold has overflowed."""
+    threshold, sigma = 0.1, 0.03
+    ok = view.objs[k]
+    aok = np.abs(ok)
+    rel = np.abs(ok - view.objs)
+    steps = 0
+    with np.errstate(all="ignore"):
+        while True:
+            near = np.all(rel < aok * threshold, axis=1)
+            e = np.nonzero(near[view.parent])[0] if len(view.parent) else np.zeros(0, dtype=np.int64)
+            wd = view.edge_w[e]
+            if _enough_distinct(wd) or (cap_threshold and threshold >= 1.0):
+                break
+            if not np.isfinite(threshold):
+                break
+            threshold *= 2.0
+            sigma *= 2.0
+            steps += 1
+        q = rel / aok                                             # same element-wise operations as population_2d.py:92-93
+        coef = np.empty(len(e))
+        for r, i in enumerate(view.parent[e].tolist()):
+            dist = _norm2(q[i])
+            coef[r] = np.exp(-((dist / sigma) ** 2) / 2.0)
+    out = []
+    dy = view.edge_dy[e]
+    for dim in range(obj_num):
+        x = wd[:, dim].copy()
+        y = dy[:, dim].copy()
+        span = (y.max() - y.min()) if len(y) else 1.0            # np.clip(max - min, 1, 500) of population_2d.py:100
+        ub = np.array([min(max(span, 1.0), 500.0), 20.0, 5.0, 500.0])
+        out.append((x, y, coef.copy(), ub))
+    return (out, steps, e) if with_steps else out

@@ -214,6 +214,14 @@ def select_greedy(ep, cand, alpha, num_tasks):
 # ---------------------------------------------------------------------------------------------
 # K4: batched hyperbolic-model fits (float64)
 # ---------------------------------------------------------------------------------------------
+def _fit_result_buffers(F, dev):
+    """One float64 buffer for all K4 outputs (a single device -> host copy collects them):
+    theta [F,4] | cost [F] | status [F], nfev [F] as int32."""
+    res = torch.empty(6 * F, dtype=torch.float64, device=dev)
+    ints = res[5 * F:].view(torch.int32)
+    return res, res[:4 * F].view(F, 4), res[4 * F:5 * F], ints[:F], ints[F:2 * F]
+
+
 def fit_hyperbolic_launch(xs, ys, ws, ubs):
     """Upload F ragged fit problems and launch K4 on the current stream WITHOUT waiting for it; the returned
     handle goes to `fit_hyperbolic_collect`. Host work that does not need the fits can run in between."""
@@ -231,13 +239,66 @@ def fit_hyperbolic_launch(xs, ys, ws, ubs):
     d = torch.from_numpy(pack).to(dev)
     kl = torch.from_numpy(klen).to(dev)
     ub = _dev_f64(np.asarray(ubs, dtype=np.float64).reshape(F, 4))
-    theta = torch.empty(F, 4, dtype=torch.float64, device=dev)
-    status = torch.empty(F, dtype=torch.int32, device=dev)
-    nfev = torch.empty(F, dtype=torch.int32, device=dev)
-    cost = torch.empty(F, dtype=torch.float64, device=dev)
+    res, theta, cost, status, nfev = _fit_result_buffers(F, dev)
     check(lib().pgm_fit_hyperbolic_f64(ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(kl), ptr(ub), ptr(theta), ptr(status),
                                        ptr(nfev), ptr(cost), F, Kmax, _stream()))
-    return dict(inputs=(d, kl, ub), theta=theta, status=status, nfev=nfev, cost=cost)     # inputs kept alive until collect
+    return dict(inputs=(d, kl, ub), res=res, F=F)     # inputs kept alive until collect
+
+
+def fit_inputs_launch(objs, parent, edge_w, edge_dy, node_ids, cap_threshold):
+    """K4 front-end (csrc/k4_inputs.cu): neighbourhood search + widening for every member, then the gather of the
+    K4 inputs. objs [n_nodes,M], edges ordered by source node then successor: parent [E], edge_w / edge_dy [E,M];
+    node_ids [n]. Returns a dict: device `pack` [3,F,Kmax] (x, y filled; w left for the caller), `ub` [F,4], `klen_f` [F];
+    host `klen`, `steps` [n] and `source` [n,Kmax] (source node of every listed edge, zero padded)."""
+    import numpy as np
+    objs = np.ascontiguousarray(objs, dtype=np.float64)
+    n_nodes, M = objs.shape
+    E, n = len(parent), len(node_ids)
+    dev = torch.device("cuda")
+    if n == 0:
+        return dict(n=0, M=M, Kmax=1, klen=np.zeros(0, dtype=np.int32), steps=np.zeros(0, dtype=np.int32),
+                    source=np.zeros((0, 1), dtype=np.int32))
+    # two uploads: the float64 tables and the int32 tables
+    fbuf = np.concatenate([objs.reshape(-1), np.asarray(edge_w, dtype=np.float64).reshape(-1),
+                           np.asarray(edge_dy, dtype=np.float64).reshape(-1)])
+    ibuf = np.concatenate([np.asarray(parent, dtype=np.int32), np.asarray(node_ids, dtype=np.int32)])
+    d_f, d_i = torch.from_numpy(fbuf).to(dev), torch.from_numpy(ibuf).to(dev)
+    d_objs, d_ew, d_dy = d_f[:n_nodes * M], d_f[n_nodes * M:n_nodes * M + E * M], d_f[n_nodes * M + E * M:]
+    d_parent, d_nodes = d_i[:E], d_i[E:]
+    ks = torch.empty(2, n, dtype=torch.int32, device=dev)
+    edge_idx = torch.empty(n * max(E, 1), dtype=torch.int32, device=dev)
+    check(lib().pgm_fit_neighbours_f64(ptr(d_objs), n_nodes, M, ptr(d_parent) if E else None, E, ptr(d_ew) if E else None,
+                                       ptr(d_nodes), n, int(bool(cap_threshold)), ptr(ks[0]), ptr(ks[1]), ptr(edge_idx),
+                                       _stream()))
+    ks_h = ks.cpu().numpy()
+    Kmax = max(int(ks_h[0].max()), 1)
+    F = n * M
+    pack = torch.empty(3, F, Kmax, dtype=torch.float64, device=dev)
+    ub = torch.empty(F, 4, dtype=torch.float64, device=dev)
+    klen_f = torch.empty(F, dtype=torch.int32, device=dev)
+    source = torch.zeros(n, Kmax, dtype=torch.int32, device=dev)
+    check(lib().pgm_fit_gather_f64(ptr(edge_idx), ptr(ks[0]), n, E, M, ptr(d_parent) if E else None,
+                                   ptr(d_ew) if E else None, ptr(d_dy) if E else None, Kmax, ptr(pack[0]), ptr(pack[1]),
+                                   ptr(ub), ptr(klen_f), ptr(source), _stream()))
+    return dict(n=n, M=M, Kmax=Kmax, pack=pack, ub=ub, klen_f=klen_f, klen=ks_h[0], steps=ks_h[1],
+                source=source.cpu().numpy(), keep=(d_f, d_i, edge_idx, ks))
+
+
+def fit_hyperbolic_launch_packed(front, coef):
+    """Launch K4 on the inputs `fit_inputs_launch` left on the device; coef [n,Kmax] (host, float64) = the Gaussian
+    point weights of every member, shared by its M fits. Returns the handle `fit_hyperbolic_collect` takes."""
+    n, M, Kmax = front["n"], front["M"], front["Kmax"]
+    if n == 0:
+        return None
+    pack, dev = front["pack"], front["pack"].device
+    import numpy as np
+    c = torch.from_numpy(np.ascontiguousarray(coef, dtype=np.float64)).to(dev)
+    pack[2].view(n, M, Kmax).copy_(c.view(n, 1, Kmax).expand(n, M, Kmax))
+    F = n * M
+    res, theta, cost, status, nfev = _fit_result_buffers(F, dev)
+    check(lib().pgm_fit_hyperbolic_f64(ptr(pack[0]), ptr(pack[1]), ptr(pack[2]), ptr(front["klen_f"]), ptr(front["ub"]),
+                                       ptr(theta), ptr(status), ptr(nfev), ptr(cost), F, Kmax, _stream()))
+    return dict(inputs=front, res=res, F=F)
 
 
 def fit_hyperbolic_collect(handle):
@@ -245,8 +306,11 @@ def fit_hyperbolic_collect(handle):
     import numpy as np
     if handle is None:
         return np.zeros((0, 4)), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
-    return (handle["theta"].cpu().numpy(), handle["status"].cpu().numpy().astype(np.int64),
-            handle["nfev"].cpu().numpy().astype(np.int64), handle["cost"].cpu().numpy())
+    F = handle["F"]
+    res = handle["res"].cpu().numpy()                                  # one copy: theta | cost | status, nfev
+    ints = res[5 * F:].view(np.int32)
+    return (res[:4 * F].reshape(F, 4).copy(), ints[:F].astype(np.int64), ints[F:2 * F].astype(np.int64),
+            res[4 * F:5 * F].copy())
 
 
 def fit_hyperbolic(xs, ys, ws, ubs):

@@ -14,6 +14,8 @@ class OptGraph:
         self.delta_objs = []   # objs - objs[prev]; zeros for roots
         self.prev = []
         self.succ = []
+        self._flat_n = 0       # nodes already mirrored in the dense arrays of `flat()`
+        self._flat = None
 
     def insert(self, weights, objs, prev):
         """Append a node and return its id (opt_graph.py:16-27). `weights` may be a torch tensor
@@ -34,6 +36,32 @@ class OptGraph:
         return node
 
     # ---- dense views used by the device path (float64) ----
+    def flat(self):
+        """Dense float64 mirror of the node lists, extended incrementally (nodes are only ever appended):
+        -> (weights [n,M], objs [n,M], delta_objs [n,M], prev [n] int64). The arrays are over-allocated and sliced;
+        callers must not write into them."""
+        n = len(self.objs)
+        if n == 0:
+            return np.zeros((0, 0)), np.zeros((0, 0)), np.zeros((0, 0)), np.zeros(0, dtype=np.int64)
+        if self._flat is None or self._flat_n > n:
+            self._flat, self._flat_n = None, 0
+        M = len(np.asarray(self.objs[0]).reshape(-1))
+        if self._flat is None or self._flat[0].shape[0] < n:
+            cap = max(64, 2 * n)
+            new = [np.zeros((cap, M)), np.zeros((cap, M)), np.zeros((cap, M)), np.zeros(cap, dtype=np.int64)]
+            if self._flat is not None:
+                for a, b in zip(new, self._flat):
+                    a[:self._flat_n] = b[:self._flat_n]
+            self._flat = new
+        W, O, D, P = self._flat
+        for i in range(self._flat_n, n):
+            W[i] = np.asarray(self.weights[i], dtype=np.float64)
+            O[i] = np.asarray(self.objs[i], dtype=np.float64)
+            D[i] = np.asarray(self.delta_objs[i], dtype=np.float64)
+            P[i] = self.prev[i]
+        self._flat_n = n
+        return W[:n], O[:n], D[:n], P[:n]
+
     def arrays(self):
         """-> (weights [n,M], objs [n,M], delta_objs [n,M]) as float64 numpy arrays."""
         f = lambda seq: np.array([np.asarray(v, dtype=np.float64) for v in seq], dtype=np.float64)

@@ -9,8 +9,8 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import predict_candidates
-from .utils import get_ep_indices, norm2
+from .prediction import Candidates, predict_candidates
+from .utils import get_ep_indices, norm2, rownorm
 
 
 class Population:
@@ -110,28 +110,48 @@ class Population:
                     out.append(weight)
         return out
 
+    def _test_weights_batch(self, view, node_ids, num_weights):
+        """`_test_weights` for many members at once, same arithmetic element by element (the row-wise helpers of
+        utils.py give the bits of the scalar calls): -> (tests [n, num_weights, 2] with the kept weights first, in arc
+        order, padding = 1; counts [n])."""
+        n = len(node_ids)
+        center = view.weights[node_ids]
+        angle_center = np.arctan2(center[:, 1], center[:, 0])
+        lo, hi = angle_center - np.pi / 4., angle_center + np.pi / 4.
+        angle = lo[:, None] + ((hi - lo) / (num_weights - 1))[:, None] * np.arange(num_weights)[None, :]
+        weight = np.stack([np.cos(angle), np.sin(angle)], axis=2)
+        keep = (weight[:, :, 0] >= -1e-7) & (weight[:, :, 1] >= -1e-7)
+        member, succ = view.successors_of(node_ids)
+        if len(member):
+            w = view.weights[succ]
+            succ_w = w / rownorm(w)[:, None]
+            used = rownorm(succ_w[:, None, :] - weight[member]) < 1e-3            # [pairs, num_weights]
+            hit = np.zeros((n, num_weights), dtype=np.int64)
+            np.add.at(hit, member, used)
+            keep &= hit == 0
+        counts = keep.sum(axis=1)
+        order = np.argsort(~keep, axis=1, kind="stable")                          # kept weights first, arc order preserved
+        tests = np.take_along_axis(weight, order[:, :, None], axis=1)
+        tests[np.arange(num_weights)[None, :] >= counts[:, None]] = 1.0
+        return tests, counts
+
     def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
         """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_2d.py:229-304)."""
         N = args.num_tasks
         # ---- prediction: candidates = (sample, weight) pairs with their predicted objectives
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
         fork = bool(getattr(args, 'fork_scoring', False))     # the WorkingMorl/ copy's variant of this routine
-        all_tests, preds, self.last_fits = predict_candidates(
-            opt_graph, self.sample_batch, lambda sample: self._test_weights(opt_graph, sample, args.num_weight_candidates),
+        tests, counts, pred, self.last_fits = predict_candidates(
+            opt_graph, self.sample_batch, lambda view, ids: self._test_weights_batch(view, ids, args.num_weight_candidates),
             args.obj_num, cap_threshold=fork, max_tests=args.num_weight_candidates, zero_if_degenerate=fork)
-        samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
-        tests = [tw for tw in all_tests if len(tw) > 0]
-        candidates = []
-        for sample, tw, pr in zip(samples, tests, preds):
-            for w, p in zip(tw, pr):
-                candidates.append({'sample': sample, 'weight': w, 'prediction': p})
+        candidates = Candidates(self.sample_batch, tests, counts, pred)
         # ---- optimisation: greedy knapsack on the device
         virtual_ep = np.array([np.asarray(s.objs, dtype=np.float64) for s in ep.sample_batch]).reshape(-1, args.obj_num)
         elite_batch, scalarization_batch, predicted_offspring_objs = [], [], []
         if len(candidates) == 0:
             print('Too few candidates')
             return elite_batch, scalarization_batch, predicted_offspring_objs
-        cand_pred = np.array([c['prediction'] for c in candidates], dtype=np.float64)
+        cand_pred = np.ascontiguousarray(candidates.prediction, dtype=np.float64)
         if fork:
             best_ids, self.last_hv, self.last_sparsity = self._greedy_fork(virtual_ep, cand_pred, args.sparsity, N)
         else:

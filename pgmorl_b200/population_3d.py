@@ -9,8 +9,8 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import predict_candidates
-from .utils import generate_weights_batch_dfs, norm2
+from .prediction import Candidates, predict_candidates
+from .utils import generate_weights_batch_dfs, norm2, rowdot, rownorm
 
 
 class Population:
@@ -133,6 +133,60 @@ class Population:
                 out.append(weight)
         return out
 
+    def _test_weights_batch(self, args, view, node_ids, grid_arr, grid_norm):
+        """`_test_weights` for many members: the geometry (angle to the centre weight, weights already used by a
+        successor, the grid point that coincides with the centre) as whole-population array expressions with the bits
+        of the scalar calls (utils.rowdot / rownorm), then per member only the reference's np.random.shuffle -- it
+        consumes the global RNG, so it is called once per member in order -- and the pick of the first eligible grid
+        weights in shuffled order. -> (tests [n, num_weight_candidates + 1, M], counts [n]); padding = 1."""
+        num_weights = args.num_weight_candidates
+        n, G, M = len(node_ids), len(grid_arr), grid_arr.shape[1]
+        c = view.weights[node_ids]
+        center = c / c.sum(axis=1, keepdims=True)
+        step = args.delta_weight / 2.0
+        # a grid point within 1e-3 (L2) of a vector is the lattice point nearest to it (spacing >> 2e-3): look that one up
+        # and run the reference's exact test on it alone
+        lattice = {tuple(key): i for i, key in enumerate(np.rint(grid_arr / step).astype(np.int64).tolist())}
+        assert step > 4e-3 and len(lattice) == G
+
+        def coincident(vectors):
+            """index of the grid point with norm2(grid - vector) < 1e-3, or -1"""
+            keys = np.rint(vectors / step).astype(np.int64).tolist()
+            idx = np.array([lattice.get(tuple(k), -1) for k in keys], dtype=np.int64)
+            near = idx >= 0
+            if near.any():
+                exact = rownorm(grid_arr[idx[near]] - vectors[near]) < 1e-3
+                idx[np.nonzero(near)[0][~exact]] = -1
+            return idx
+
+        excluded = np.zeros((n, G), dtype=bool)
+        at_center = coincident(center)
+        excluded[np.nonzero(at_center >= 0)[0], at_center[at_center >= 0]] = True
+        has_center = np.ones(n, dtype=bool)
+        member, succ = view.successors_of(node_ids)
+        if len(member):
+            w = view.weights[succ]
+            succ_w = w / w.sum(axis=1, keepdims=True)
+            used_center = rownorm(succ_w - center[member]) < 1e-3
+            has_center[member[used_center]] = False
+            at_succ = coincident(succ_w)
+            excluded[member[at_succ >= 0], at_succ[at_succ >= 0]] = True
+        cosine = rowdot(center[:, None, :], grid_arr[None, :, :]) / rownorm(center)[:, None] / grid_norm[None, :]
+        angle = np.arccos(np.minimum(np.maximum(cosine, -1.0), 1.0))
+        eligible = (angle < np.pi / 4.0) & ~excluded
+        tests = np.ones((n, num_weights + 1, M))
+        counts = np.zeros(n, dtype=np.int64)
+        for b in range(n):
+            k = 0
+            if has_center[b]:
+                tests[b, 0] = center[b]; k = 1
+            order = np.arange(G)                       # same dtype and length as the reference's list-built array
+            np.random.shuffle(order)
+            picks = order[eligible[b][order]][:max(num_weights - k, 0)]
+            tests[b, k:k + len(picks)] = grid_arr[picks]
+            counts[b] = k + len(picks)
+        return tests, counts
+
     def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
         """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_3d.py:239-333)."""
         N = args.num_tasks
@@ -142,22 +196,17 @@ class Population:
         generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
         grid_arr = np.array(grid, dtype=np.float64)
-        grid_norm = [norm2(w) for w in grid]
-        all_tests, preds, self.last_fits = predict_candidates(
-            opt_graph, self.sample_batch, lambda sample: self._test_weights(args, opt_graph, sample, grid, grid_arr, grid_norm),
+        grid_norm = rownorm(grid_arr)
+        tests, counts, pred, self.last_fits = predict_candidates(
+            opt_graph, self.sample_batch, lambda view, ids: self._test_weights_batch(args, view, ids, grid_arr, grid_norm),
             args.obj_num, cap_threshold=True, max_tests=args.num_weight_candidates + 1, tests_in_lockstep=True)
-        samples = [s for s, tw in zip(self.sample_batch, all_tests) if len(tw) > 0]
-        tests = [tw for tw in all_tests if len(tw) > 0]
-        candidates = []
-        for sample, tw, pr in zip(samples, tests, preds):
-            for w, p in zip(tw, pr):
-                candidates.append({'sample': sample, 'weight': w, 'prediction': p})
+        candidates = Candidates(self.sample_batch, tests, counts, pred)
         virtual_ep = np.array([np.asarray(s.objs, dtype=np.float64) for s in ep.sample_batch]).reshape(-1, args.obj_num)
         elite_batch, scalarization_batch, predicted_offspring_objs = [], [], []
         if len(candidates) == 0:
             print('Too few candidates')
             return elite_batch, scalarization_batch, predicted_offspring_objs
-        cand_pred = np.array([c['prediction'] for c in candidates], dtype=np.float64)
+        cand_pred = np.ascontiguousarray(candidates.prediction, dtype=np.float64)
         best_ids, self.last_hv, self.last_sparsity, _ = K.select_greedy(virtual_ep, cand_pred, args.sparsity, N)
         for best_id in best_ids:
             if best_id == -1:

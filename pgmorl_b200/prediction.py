@@ -1,113 +1,75 @@
 """Hyperbolic prediction model of PG-MORL (mirror of predict_hyperbolic / collect_nearest_data,
 morl/population_2d.py:12-118 and morl/population_3d.py:13-113), batched over the whole population.
 
-Host side (numpy, same expressions as the reference so the fit inputs are bit-identical): neighbourhood
-search in the opt-graph with the widening (threshold, sigma) schedule and the Gaussian point weights.
-Device side: ALL fits of a selection call (n_pop x M bounded robust least-squares problems) in one
-launch of K4 (csrc/k4_fit.cu). Predictions are then objs + f(test weight)."""
+Device side: the neighbourhood search in the opt-graph with the widening (threshold, sigma) schedule and the
+gather of the training points of every model (csrc/k4_inputs.cu), then ALL fits of a selection call (n_pop x M
+bounded robust least-squares problems) in one launch of K4 (csrc/k4_fit.cu).
+Host side (numpy): the Gaussian point weights and the model evaluations -- the two places where the reference's
+numbers come out of numpy's exp, which no device routine reproduces bit for bit -- as whole-population array
+expressions built from the row-wise helpers of utils.py that give the bits of the scalar calls they replace.
+Predictions are then objs + f(test weight)."""
 import numpy as np
 
 from . import kernels as K
 from ._nvtx import rng as _nvtx
-from .utils import norm2
+from .utils import pow2, rowdot
 
 
 class GraphView:
-    """Flat arrays over an OptGraph for repeated neighbourhood queries."""
+    """Flat float64 arrays over an OptGraph. Edges (source node -> successor) in the data order of
+    collect_nearest_data: by source node, then by successor (successors are appended in node order)."""
 
     def __init__(self, opt_graph):
-        self.objs = np.array([np.asarray(o, dtype=np.float64) for o in opt_graph.objs])
-        parents, children = [], []
-        for i, succ in enumerate(opt_graph.succ):           # data order of collect_nearest_data: by node, then by successor
-            for s in succ:
-                parents.append(i); children.append(s)
-        self.parent = np.array(parents, dtype=np.int64)
-        self.child = np.array(children, dtype=np.int64)
-        # successor weights normalised to sum 1 (population_2d.py:19) and their objective gains
-        self.edge_w = np.array([np.asarray(opt_graph.weights[s], dtype=np.float64) / np.sum(np.asarray(opt_graph.weights[s], dtype=np.float64))
-                                for s in children]).reshape(len(children), -1)
-        self.edge_dy = np.array([np.asarray(opt_graph.delta_objs[s], dtype=np.float64) for s in children]).reshape(len(children), -1)
+        W, O, D, prev = opt_graph.flat()
+        self.weights, self.objs = W, O
+        child = np.nonzero(prev >= 0)[0]
+        child = child[np.argsort(prev[child], kind="stable")]
+        self.child, self.parent = child, prev[child]
+        wc = W[child]
+        self.edge_w = wc / wc.sum(axis=1, keepdims=True)        # successor weights normalised to sum 1 (population_2d.py:19)
+        self.edge_dy = D[child]                                  # ... and their objective gains
+        # successors of node i: child[estart[i]:estart[i + 1]]
+        self.estart = np.searchsorted(self.parent, np.arange(len(O) + 1))
 
-    def nearest_edges(self, k, threshold):
-        """Edges (i -> s) whose source node i lies within `threshold` (relative, per objective) of node k."""
-        ok = self.objs[k]
-        near = np.all(np.abs(ok - self.objs) < np.abs(ok) * threshold, axis=1)
-        return np.nonzero(near[self.parent])[0] if len(self.parent) else np.zeros(0, dtype=np.int64)
-
-
-def _enough_distinct(weights):
-    """More than 3 pairwise-distinct weights (L2 distance >= 1e-5), first-occurrence scan (population_2d.py:39-49)."""
-    cnt = 0
-    for i in range(len(weights)):
-        distinct = True
-        for j in range(i):
-            if norm2(weights[i] - weights[j]) < 1e-5:
-                distinct = False
-                break
-        if distinct:
-            cnt += 1
-            if cnt > 3:
-                return True
-    return False
+    def successors_of(self, nodes):
+        """-> (member index [P], successor node [P]) for the successor lists of `nodes`, members in order."""
+        nodes = np.asarray(nodes, dtype=np.int64)
+        start, cnt = self.estart[nodes], self.estart[nodes + 1] - self.estart[nodes]
+        member = np.repeat(np.arange(len(nodes)), cnt)
+        offs = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        return member, self.child[np.repeat(start, cnt) + offs]
 
 
-def fit_inputs(view, k, obj_num, cap_threshold):
-    """Training data of the model of node k: per objective (x, y, w, ub). `cap_threshold` reproduces the
-    3-objective variant's stop at threshold >= 1 (population_3d.py:46); the 2-objective one widens until
-    more than 3 distinct weights are found (population_2d.py:50)."""
-    threshold, sigma = 0.1, 0.03
-    ok = view.objs[k]
-    aok = np.abs(ok)
-    rel = np.abs(ok - view.objs)                              # |objs_k - objs_i| for every node i, reused by each widening
-    has_edges = len(view.parent) > 0
-    near_block = None
-    step = 0
-    while True:
-        if step == 0:
-            lt = rel < aok * threshold
-            near = lt[:, 0]
-            for m in range(1, lt.shape[1]):
-                near = near & lt[:, m]
-        else:
-            if (step - 1) % 4 == 0:                           # neighbourhoods of the next four thresholds in one comparison
-                thr = threshold * np.array([1.0, 2.0, 4.0, 8.0])     # exact doublings: the values `threshold *= 2` goes through
-                lt = rel[None, :, :] < aok[None, None, :] * thr[:, None, None]
-                near_block = lt[:, :, 0]
-                for m in range(1, lt.shape[2]):
-                    near_block = near_block & lt[:, :, m]
-            near = near_block[(step - 1) % 4]
-        e = np.nonzero(near[view.parent])[0] if has_edges else np.zeros(0, dtype=np.int64)
-        wd = view.edge_w[e]
-        if _enough_distinct(wd) or (cap_threshold and threshold >= 1.0):
-            break
-        if not np.isfinite(threshold):          # the reference would widen forever here (fewer than 4 distinct weights
-            break                               # in the whole graph); fits are launched for every sample, so stop instead
-        threshold *= 2.0
-        sigma *= 2.0
-        step += 1
-    q = rel / aok                                             # same element-wise operations as population_2d.py:92-93
-    coef = np.empty(len(e))
-    node_coef = {}
-    parents = view.parent[e].tolist()
-    for r, i in enumerate(parents):                           # one Gaussian weight per source node, shared by its edges
-        c = node_coef.get(i)
-        if c is None:
-            dist = norm2(q[i])
-            c = node_coef[i] = np.exp(-((dist / sigma) ** 2) / 2.0)
-        coef[r] = c
-    out = []
-    dy = view.edge_dy[e]
-    for dim in range(obj_num):
-        x = wd[:, dim].copy()
-        y = dy[:, dim].copy()
-        span = y.max() - y.min()                              # np.clip(max - min, 1, 500) of population_2d.py:100
-        ub = np.array([min(max(span, 1.0), 500.0), 20.0, 5.0, 500.0])
-        out.append((x, y, coef.copy(), ub))
-    return out
+def gaussian_weights(view, node_ids, steps, source):
+    """Point weights exp(-(dist / sigma)^2 / 2) of every listed edge (population_2d.py:88-96): dist = L2 norm of the
+    source node's relative objective distance to the member's node, sigma = 0.03 doubled `steps` times.
+    source [n, Kmax] (padding entries give meaningless values that K4 never reads)."""
+    ok = view.objs[np.asarray(node_ids, dtype=np.int64)]
+    with np.errstate(all="ignore"):
+        q = np.abs(ok[:, None, :] - view.objs[source]) / np.abs(ok)[:, None, :]
+        dist = np.sqrt(rowdot(q, q))
+        sigma = np.ldexp(0.03, np.asarray(steps, dtype=np.int32))          # exact doublings
+        return np.exp(-pow2(dist / sigma[:, None]) / 2.0)
 
 
 def model(x, A, a, b, c):
     return A * (np.exp(a * (x - b)) - 1) / (np.exp(a * (x - b)) + 1) + c
+
+
+class FitRecord(dict):
+    """Record of the most recent K4 launch (diagnostics / tests): theta, status, nfev, cost [F] as numpy arrays;
+    the ragged inputs x, y, w (lists of 1-D arrays) and ub are copied back from the device on first access."""
+
+    def __init__(self, lazy, **kw):
+        super().__init__(**kw)
+        self._lazy = lazy
+
+    def __missing__(self, key):
+        if key in ("x", "y", "w", "ub") and self._lazy is not None:
+            lazy, self._lazy = self._lazy, None
+            self.update(lazy())
+            return self[key]
+        raise KeyError(key)
 
 
 def launch_fits(opt_graph, node_ids, obj_num, cap_threshold):
@@ -115,47 +77,63 @@ def launch_fits(opt_graph, node_ids, obj_num, cap_threshold):
     Returns a handle for `finish_predictions`; the caller may do host work that does not need the fits meanwhile."""
     with _nvtx("selection.fit_inputs"):
         view = GraphView(opt_graph)
-        xs, ys, ws, ubs = [], [], [], []
-        for k in node_ids:
-            for x, y, w, ub in fit_inputs(view, k, obj_num, cap_threshold):
-                xs.append(x); ys.append(y); ws.append(w); ubs.append(ub)
+        node_ids = np.asarray(list(node_ids), dtype=np.int64)
+        front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, node_ids, cap_threshold)
+        coef = gaussian_weights(view, node_ids, front["steps"], front["source"]) if len(node_ids) else np.zeros((0, 1))
     with _nvtx("selection.k4_fits"):
-        fits = K.fit_hyperbolic_launch(xs, ys, ws, ubs)                    # all fits in one launch
-    return dict(view=view, node_ids=list(node_ids), obj_num=obj_num, x=xs, y=ys, w=ws, ub=ubs, fits=fits)
+        fits = K.fit_hyperbolic_launch_packed(front, coef)                  # all fits in one launch
+    return dict(view=view, node_ids=node_ids, obj_num=obj_num, front=front, fits=fits)
 
 
-def finish_predictions(handle, test_weights_per_node, zero_if_degenerate=False):
-    """Second half of `predict_population`. test_weights_per_node[i] is an array [n_i, M] for node_ids[i] (any
-    positive scaling; normalised to sum 1 here, as population_2d.py:28-32) or None / empty: that node then
+def _ragged_inputs(handle, keep):
+    """x, y, w, ub of the kept fits as the lists the scalar code used to hold (device -> host copy of the pack)."""
+    front = handle["front"]
+    pack, ub, klen = front["pack"].cpu().numpy(), front["ub"].cpu().numpy(), front["klen"]
+    M = handle["obj_num"]
+    out = dict(x=[], y=[], w=[], ub=[])
+    for f in keep:
+        k = int(klen[f // M])
+        out["x"].append(pack[0, f, :k].copy()); out["y"].append(pack[1, f, :k].copy())
+        out["w"].append(pack[2, f, :k].copy()); out["ub"].append(ub[f].copy())
+    return out
+
+
+def finish_predictions(handle, tests, counts, zero_if_degenerate=False):
+    """Second half of `predict_population`. tests [n, T, M] holds counts[i] test weights for node_ids[i] in its first
+    rows (any positive scaling; normalised to sum 1 here, as population_2d.py:28-32); a member without test weights
     contributes neither predictions nor fit records (the reference never fits a sample without test weights).
-    `zero_if_degenerate`: the fork copy's fallback (WorkingMorl/morl/population_2d.py:112-117)."""
+    Returns (pred [n, T, M], fit record). `zero_if_degenerate`: the fork copy's fallback
+    (WorkingMorl/morl/population_2d.py:112-117)."""
     theta, status, nfev, cost = K.fit_hyperbolic_collect(handle["fits"])
     view, M = handle["view"], handle["obj_num"]
-    preds, keep = [], []
-    for i, k in enumerate(handle["node_ids"]):
-        if test_weights_per_node[i] is None or len(test_weights_per_node[i]) == 0:
-            continue
-        keep.extend(range(i * M, (i + 1) * M))
-        tw = np.array(test_weights_per_node[i], dtype=np.float64)
-        tw = tw / tw.sum(axis=1, keepdims=True)                   # row /= np.sum(row), population_2d.py:28-32 (same bits)
-        cols = []
-        for dim in range(M):
-            x = handle["x"][i * M + dim]
-            if zero_if_degenerate and (len(x) == 0 or len(np.unique(x)) < 2):
-                cols.append(np.zeros(len(tw)))       # the fork copy predicts no change without usable data (:112-117)
-            else:
-                cols.append(model(tw.T[dim], *theta[i * M + dim]))
-        delta = np.transpose(np.array(cols))
-        preds.append(view.objs[k][None, :] + delta)
-    pick = lambda seq: [seq[j] for j in keep]
-    return preds, dict(x=pick(handle["x"]), y=pick(handle["y"]), w=pick(handle["w"]), ub=pick(handle["ub"]),
-                       theta=theta[keep], status=status[keep], nfev=nfev[keep], cost=cost[keep])
+    n = len(handle["node_ids"])
+    counts = np.asarray(counts, dtype=np.int64)
+    tests = np.asarray(tests, dtype=np.float64).reshape(n, -1, M)
+    with np.errstate(all="ignore"):
+        tw = tests / tests.sum(axis=2, keepdims=True)              # row /= np.sum(row), population_2d.py:28-32 (same bits)
+        th = theta.reshape(n, 1, M, 4)
+        delta = model(tw, th[..., 0], th[..., 1], th[..., 2], th[..., 3])
+    if zero_if_degenerate:
+        # the fork copy predicts no change without usable data (:112-117): fewer than two distinct training weights
+        front = handle["front"]
+        x = front["pack"][0].cpu().numpy()
+        for f in range(n * M):
+            k = int(front["klen"][f // M])
+            if k == 0 or len(np.unique(x[f, :k])) < 2:
+                delta[f // M, :, f % M] = 0.0
+    pred = view.objs[handle["node_ids"]][:, None, :] + delta
+    keep = np.nonzero(np.repeat(counts > 0, M))[0]
+    record = FitRecord(lambda: _ragged_inputs(handle, keep.tolist()), theta=theta[keep], status=status[keep],
+                       nfev=nfev[keep], cost=cost[keep])
+    return pred, record
 
 
 def predict_candidates(opt_graph, samples, make_tests, obj_num, cap_threshold, max_tests, zero_if_degenerate=False,
                        tests_in_lockstep=False):
-    """Test weights and predicted objectives of every population member: -> (all_tests: one [n_i, M] list per member,
-    preds: one [n_i, M] array per member WITH test weights, fit record).
+    """Test weights and predicted objectives of every population member.
+    `make_tests(view, node_ids) -> (tests [n, max_tests, M], counts [n])` enumerates the test weights of the given
+    members (rows past counts[i] are padding, any finite positive numbers).
+    -> (tests [n_pop, max_tests, M], counts [n_pop], pred [n_pop, max_tests, M], fit record).
 
     Single process: all fits in one K4 launch, issued before the host enumerates the test weights so that it runs under
     that work. Under torch.distributed (sharded runs) the members are split over the ranks
@@ -167,41 +145,53 @@ def predict_candidates(opt_graph, samples, make_tests, obj_num, cap_threshold, m
     from . import dist as pdist
     rank, W = pdist.world()
     n = len(samples)
-    if W == 1 or n < W:
-        pending = launch_fits(opt_graph, [s.optgraph_id for s in samples], obj_num, cap_threshold)
-        all_tests = [make_tests(s) for s in samples]
-        preds, fits = finish_predictions(pending, all_tests, zero_if_degenerate=zero_if_degenerate)
-        return all_tests, preds, fits
-    mine = list(range(rank, n, W))
-    pending = launch_fits(opt_graph, [samples[i].optgraph_id for i in mine], obj_num, cap_threshold)
-    if tests_in_lockstep:
-        everyone = [make_tests(s) for s in samples]
-        my_tests = [everyone[i] for i in mine]
-    else:
-        my_tests = [make_tests(samples[i]) for i in mine]
-    my_preds, fits = finish_predictions(pending, my_tests, zero_if_degenerate=zero_if_degenerate)
+    ids = np.array([s.optgraph_id for s in samples], dtype=np.int64)
     M = obj_num
-    rows = np.zeros((len(mine), 1 + 2 * max_tests * M))
-    it = iter(my_preds)
-    for j, tw in enumerate(my_tests):
-        k = len(tw)
-        assert k <= max_tests
-        rows[j, 0] = k
-        if k:
-            rows[j, 1:1 + k * M] = np.asarray(tw, dtype=np.float64).reshape(-1)
-            rows[j, 1 + max_tests * M:1 + max_tests * M + k * M] = np.asarray(next(it), dtype=np.float64).reshape(-1)
+    if W == 1 or n < W:
+        pending = launch_fits(opt_graph, ids, obj_num, cap_threshold)
+        with _nvtx("selection.test_weights"):
+            tests, counts = make_tests(pending["view"], ids)
+        pred, fits = finish_predictions(pending, tests, counts, zero_if_degenerate=zero_if_degenerate)
+        return tests, counts, pred, fits
+    mine = np.arange(rank, n, W)
+    pending = launch_fits(opt_graph, ids[mine], obj_num, cap_threshold)
+    with _nvtx("selection.test_weights"):
+        if tests_in_lockstep:
+            tests, counts = make_tests(pending["view"], ids)
+            my_tests, my_counts = tests[mine], counts[mine]
+        else:
+            my_tests, my_counts = make_tests(pending["view"], ids[mine])
+    my_pred, fits = finish_predictions(pending, my_tests, my_counts, zero_if_degenerate=zero_if_degenerate)
+    T = max_tests
+    rows = np.zeros((len(mine), 1 + 2 * T * M))
+    rows[:, 0] = my_counts
+    valid = (np.arange(T)[None, :] < np.asarray(my_counts)[:, None])[:, :, None]
+    rows[:, 1:1 + T * M] = np.where(valid, my_tests, 0.0).reshape(len(mine), -1)
+    rows[:, 1 + T * M:] = np.where(valid, my_pred, 0.0).reshape(len(mine), -1)
     table = pdist.all_gather_rows(rows, n)
-    all_tests, preds = [], []
-    for i in range(n):
-        k = int(table[i, 0])
-        tw = table[i, 1:1 + k * M].reshape(k, M)
-        all_tests.append([tw[j].copy() for j in range(k)])
-        if k:
-            preds.append(table[i, 1 + max_tests * M:1 + max_tests * M + k * M].reshape(k, M).copy())
-    return all_tests, preds, fits
+    counts = table[:, 0].astype(np.int64)
+    tests = table[:, 1:1 + T * M].reshape(n, T, M).copy()
+    pred = table[:, 1 + T * M:].reshape(n, T, M).copy()
+    tests[~(np.arange(T)[None, :] < counts[:, None])] = 1.0          # padding stays finite and positive
+    return tests, counts, pred, fits
 
 
-def predict_population(opt_graph, node_ids, test_weights_per_node, obj_num, cap_threshold):
-    """For every node: predicted objectives objs + delta(test weight) for each of its test weights.
-    Returns (list of [n_i, M] prediction arrays, fit record dict)."""
-    return finish_predictions(launch_fits(opt_graph, node_ids, obj_num, cap_threshold), test_weights_per_node)
+class Candidates:
+    """The (sample, weight, prediction) triples of a selection call, kept as arrays; indexable like the reference's
+    list of dicts (`candidates[i]['prediction']`)."""
+
+    def __init__(self, samples, tests, counts, pred):
+        valid = np.arange(tests.shape[1])[None, :] < np.asarray(counts)[:, None]
+        self.member, slot = np.nonzero(valid)                       # member order, then test order: the reference's order
+        self.weight = tests[self.member, slot]
+        self.prediction = pred[self.member, slot]
+        self._samples = samples
+
+    def __len__(self):
+        return len(self.member)
+
+    def __getitem__(self, i):
+        return {'sample': self._samples[int(self.member[i])], 'weight': self.weight[i], 'prediction': self.prediction[i]}
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))

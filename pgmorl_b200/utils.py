@@ -88,3 +88,62 @@ def norm2(v):
     (sqnorm = v.dot(v); sqrt(sqnorm)), hence the same bits -- the selection compares these against thresholds."""
     v = np.asarray(v)
     return math.sqrt(v.dot(v))
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-wise versions of the scalar numpy expressions the reference evaluates per point. The selection
+# front-end batches them over the whole population, and the batched form has to give the SAME BITS as
+# the scalar calls it replaces: BLAS ddot (np.dot / np.linalg.norm of a short vector) accumulates with
+# fused multiply-adds, C pow (`float ** 2`) is not always the correctly rounded square. np.vecdot and
+# np.float_power go through the same code as the scalar calls; that is checked once on this machine's
+# numpy / BLAS build, and the scalar loop is used instead should it ever not hold.
+# ---------------------------------------------------------------------------------------------
+def _rowdot_loop(a, b):
+    out = np.empty(a.shape[:-1])
+    flat_a, flat_b, flat_o = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1]), out.reshape(-1)
+    for i in range(len(flat_o)):
+        flat_o[i] = flat_a[i].dot(flat_b[i])
+    return out
+
+
+def _pow2_loop(x):
+    out = np.empty(x.shape)
+    flat_x, flat_o = x.reshape(-1), out.reshape(-1)
+    for i in range(len(flat_o)):
+        flat_o[i] = math.pow(flat_x[i], 2.0)
+    return out
+
+
+def _batched_forms_match():
+    rng = np.random.RandomState(12345)
+    if not hasattr(np, "vecdot"):
+        return False, False
+    dot_ok = True
+    for m in (2, 3, 4):
+        a = rng.rand(512, m) * rng.choice([1e-3, 1.0, 50.0], size=(512, 1))
+        b = rng.rand(512, m) - 0.5
+        dot_ok = dot_ok and np.array_equal(np.vecdot(a, b), _rowdot_loop(a, b))
+    x = np.abs(rng.randn(4096)) * 3.0
+    pow_ok = np.array_equal(np.float_power(x, 2.0), _pow2_loop(x))
+    return dot_ok, pow_ok
+
+
+_ROWDOT_FAST, _POW2_FAST = _batched_forms_match()
+
+
+def rowdot(a, b):
+    """dot product of corresponding rows (last axis), bit-identical to `a[i].dot(b[i])`."""
+    a, b = np.broadcast_arrays(a, b)
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    return np.vecdot(a, b) if _ROWDOT_FAST else _rowdot_loop(a, b)
+
+
+def rownorm(a):
+    """np.linalg.norm of every row (last axis), bit-identical to the per-row call (sqrt of the BLAS dot)."""
+    return np.sqrt(rowdot(a, a))
+
+
+def pow2(x):
+    """x ** 2 as Python floats / numpy scalars compute it (C pow), element-wise."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.float_power(x, 2.0) if _POW2_FAST else _pow2_loop(x)

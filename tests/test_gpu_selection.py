@@ -298,3 +298,98 @@ def test_fork_scoring_variant_matches_the_fork_reference():
     finally:
         torch.set_default_dtype(torch.float32)
     assert exact == gens            # measured on a B200: 5/5 generations identical
+
+
+def _front_end_vs_oracle(graph, ids, M, cap):
+    """csrc/k4_inputs.cu (through kernels.fit_inputs_launch) + prediction.gaussian_weights against the scalar oracle
+    scan of every member: same edge lists, widening steps, x / y / w / ub, bit for bit."""
+    from pgmorl_b200 import kernels as K
+    from pgmorl_b200.prediction import GraphView, gaussian_weights
+    view, ref = GraphView(graph), so.GraphArrays(graph)
+    ids = np.asarray(ids, dtype=np.int64)
+    front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, ids, cap)
+    coef = gaussian_weights(view, ids, front["steps"], front["source"])
+    pack, ub = front["pack"].cpu().numpy(), front["ub"].cpu().numpy()
+    klen_f = front["klen_f"].cpu().numpy()
+    for b, k in enumerate(ids):
+        out, steps, e = so.fit_inputs(ref, int(k), M, cap, with_steps=True)
+        assert front["klen"][b] == len(e) and front["steps"][b] == steps, (b, k, front["klen"][b], len(e), front["steps"][b], steps)
+        assert np.array_equal(front["source"][b, :len(e)], ref.parent[e])
+        for dim, (x, y, w, u) in enumerate(out):
+            f = b * M + dim
+            assert klen_f[f] == len(e)
+            assert np.array_equal(pack[0, f, :len(e)], x) and np.array_equal(pack[1, f, :len(e)], y)
+            assert np.array_equal(coef[b, :len(e)], w, equal_nan=True) and np.array_equal(ub[f], u)
+    return front
+
+
+@pytest.mark.parametrize("name,M", [("selection_2d.npz", 2), ("selection_3d.npz", 3)])
+def test_fit_input_kernels_match_reference_goldens(name, M):
+    """The device front-end on the recorded histories: every generation's fit inputs equal the oracle's (which
+    tests/test_host_selection.py pins to the reference's recorded x / y / w / ub)."""
+    from tests.helpers import rebuild_selection_state
+    z = np.load(os.path.join(GOLDEN, name))
+    gens = int(z["meta"][1])
+    for g in range(gens):
+        args, graph, pop, ep = rebuild_selection_state(z, g, M)
+        ids = [s.optgraph_id for s in pop.sample_batch]
+        front = _front_end_vs_oracle(graph, ids, M, cap=(M != 2))
+        if g == gens - 1:          # and directly against the recorded arrays, where every member has test weights
+            n_fits = int(z[f"g{g}_n_fits"])
+            if n_fits == len(ids) * M:
+                pack = front["pack"].cpu().numpy()
+                for f in range(n_fits):
+                    k = int(front["klen"][f // M])
+                    assert np.array_equal(pack[0, f, :k], z[f"g{g}_fit{f}_x"]) and np.array_equal(pack[1, f, :k], z[f"g{g}_fit{f}_y"])
+
+
+def test_fit_input_kernels_edge_cases():
+    """Synthetic opt-graphs that drive every exit of the widening loop: plenty of distinct weights at the first
+    threshold; several doublings; fewer than four distinct weights in the whole graph (threshold runs to +inf, every
+    edge listed); a member with a zero objective (its neighbourhood stays empty until the product |objs| * inf is
+    formed, NaN for the zero component: empty edge list); a graph without edges; duplicated weights that only differ
+    below the 1e-5 tolerance; the 3-objective stop at threshold >= 1; more edges than one scan pass (256) handles."""
+    from pgmorl_b200.opt_graph import OptGraph
+    rng = np.random.RandomState(11)
+
+    def family_graph(M, roots, kids, spread, weights=None, zero_root=False):
+        g = OptGraph()
+        members = []
+        for r in range(roots):
+            base = rng.uniform(40.0, 60.0, M) * (1.0 + spread * r)
+            if zero_root and r == 0:
+                base[0] = 0.0
+            root = g.insert(np.ones(M) / M, base.copy(), -1)
+            for j in range(kids):
+                w = rng.dirichlet(np.ones(M)) if weights is None else np.asarray(weights[j % len(weights)], dtype=np.float64)
+                members.append(g.insert(w.copy(), base + rng.normal(0, 2.0, M), root))
+        return g, members
+
+    for M in (2, 3):
+        for cap in (False, True):
+            g, members = family_graph(M, 6, 5, 0.02)                       # dense: done at the first threshold(s)
+            _front_end_vs_oracle(g, members + [0], M, cap)
+            g, members = family_graph(M, 8, 2, 0.9)                        # sparse: several doublings
+            _front_end_vs_oracle(g, members, M, cap)
+            two = [np.eye(M)[0] * 0.7 + 0.3 / M, np.eye(M)[1] * 0.7 + 0.3 / M]
+            g, members = family_graph(M, 4, 3, 0.5, weights=two)           # 2 distinct weights: runs to +inf unless capped
+            front = _front_end_vs_oracle(g, members[:5], M, cap)
+            if not cap:
+                assert (front["steps"] > 1000).all() and (front["klen"] == 12).all()
+            near_dup = [np.full(M, 1.0 / M), np.full(M, 1.0 / M) + 1e-7 * np.arange(M), np.eye(M)[0] * 0.5 + 0.5 / M,
+                        np.eye(M)[1] * 0.5 + 0.5 / M, np.eye(M)[1] * 0.2 + 0.8 / M]
+            g, members = family_graph(M, 5, 5, 0.05, weights=near_dup)
+            _front_end_vs_oracle(g, members, M, cap)
+            g, members = family_graph(M, 3, 4, 0.3, zero_root=True)        # member 0 = the root with a zero objective
+            _front_end_vs_oracle(g, [0] + members, M, cap)
+            g, members = family_graph(M, 2, 400, 0.01)                     # 800 edges: several scan passes per step
+            _front_end_vs_oracle(g, members[::37], M, cap)
+    g = OptGraph()                                                         # roots only: no edge at all
+    for r in range(3):
+        g.insert(np.ones(2) / 2, rng.uniform(10, 20, 2), -1)
+    from pgmorl_b200 import kernels as K
+    from pgmorl_b200.prediction import GraphView
+    view = GraphView(g)
+    front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, np.arange(3), False)
+    assert (front["klen"] == 0).all() and (front["steps"] > 1000).all()
+    assert np.array_equal(front["ub"].cpu().numpy(), np.tile([1.0, 20.0, 5.0, 500.0], (6, 1)))

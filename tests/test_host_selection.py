@@ -8,7 +8,8 @@ import pytest
 
 import synth_envs
 from pgmorl_b200 import synthetic
-from pgmorl_b200.prediction import GraphView, fit_inputs
+from oracle import selection_oracle as so
+from pgmorl_b200.prediction import GraphView, gaussian_weights
 from tests.helpers import rebuild_selection_state
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -72,12 +73,73 @@ def test_candidate_weights_and_fit_inputs_bit_exact(name, M):
                 weights.append(np.asarray(w, dtype=np.float64)); nodes.append(s.optgraph_id)
         assert nodes == z[f"g{g}_cand_node"].tolist()
         assert np.array_equal(np.array(weights), z[f"g{g}_cand_weight"])
-        view = GraphView(graph)
+        view = so.GraphArrays(graph)
         i = 0
         for k in fit_nodes:
-            for x, y, w, ub in fit_inputs(view, k, M, cap_threshold=(M != 2)):
+            for x, y, w, ub in so.fit_inputs(view, k, M, cap_threshold=(M != 2)):
                 pre = f"g{g}_fit{i}_"
                 assert np.array_equal(x, z[pre + "x"]) and np.array_equal(y, z[pre + "y"])
                 assert np.array_equal(w, z[pre + "w"]) and np.array_equal(ub, z[pre + "ub"])
                 i += 1
         assert i == int(z[f"g{g}_n_fits"])
+
+
+@pytest.mark.parametrize("name,M", [("selection_2d.npz", 2), ("selection_3d.npz", 3)])
+def test_batched_front_end_matches_reference_bits(name, M):
+    """The whole-population array forms the product uses (flat opt-graph view, batched test weights, Gaussian point
+    weights from the listed edges) against the reference's recorded candidates and fit inputs, bit for bit."""
+    from pgmorl_b200.utils import generate_weights_batch_dfs, rownorm
+    z = np.load(os.path.join(GOLDEN, name))
+    gens = int(z["meta"][1])
+    for g in (0, gens // 2, gens - 1):
+        args, graph, pop, ep = rebuild_selection_state(z, g, M)
+        np.random.seed(1000 + g)
+        view, ref = GraphView(graph), so.GraphArrays(graph)
+        for a in ("objs", "parent", "child", "edge_w", "edge_dy"):
+            assert np.array_equal(getattr(view, a), getattr(ref, a)), a
+        ids = np.array([s.optgraph_id for s in pop.sample_batch], dtype=np.int64)
+        if M == 2:
+            tests, counts = pop._test_weights_batch(view, ids, args.num_weight_candidates)
+        else:
+            grid = []
+            generate_weights_batch_dfs(0, M, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
+            grid_arr = np.array(grid, dtype=np.float64)
+            tests, counts = pop._test_weights_batch(args, view, ids, grid_arr, rownorm(grid_arr))
+        nodes = np.repeat(ids, counts)
+        weights = np.concatenate([tests[b, :counts[b]] for b in range(len(ids))])
+        assert nodes.tolist() == z[f"g{g}_cand_node"].tolist()
+        assert np.array_equal(weights, z[f"g{g}_cand_weight"])
+        # Gaussian point weights from (steps, source nodes of the listed edges) -- here taken from the oracle's scan,
+        # on the device they come from csrc/k4_inputs.cu (tests/test_gpu_selection.py)
+        fit_ids = ids[counts > 0]
+        scans = [so.fit_inputs(ref, int(k), M, cap_threshold=(M != 2), with_steps=True) for k in fit_ids]
+        kmax = max(len(e) for _, _, e in scans)
+        source = np.zeros((len(fit_ids), kmax), dtype=np.int64)
+        for b, (_, _, e) in enumerate(scans):
+            source[b, :len(e)] = ref.parent[e]
+        coef = gaussian_weights(view, fit_ids, [st for _, st, _ in scans], source)
+        i = 0
+        for b, (out, _, e) in enumerate(scans):
+            for dim in range(M):
+                assert np.array_equal(coef[b, :len(e)], z[f"g{g}_fit{i}_w"])
+                assert np.array_equal(view.edge_w[e, dim], z[f"g{g}_fit{i}_x"])
+                i += 1
+        assert i == int(z[f"g{g}_n_fits"])
+
+
+def test_rowwise_helpers_give_the_scalar_bits():
+    """utils.rowdot / rownorm / pow2 against the scalar numpy / Python expressions of the reference."""
+    from pgmorl_b200 import utils
+    rng = np.random.RandomState(3)
+    for m in (2, 3):
+        a = rng.rand(2000, m) * rng.choice([1e-4, 1.0, 80.0], size=(2000, 1))
+        b = rng.rand(2000, m) - 0.3
+        assert np.array_equal(utils.rowdot(a, b), np.array([np.dot(p, q) for p, q in zip(a, b)]))
+        assert np.array_equal(utils.rownorm(a), np.array([np.linalg.norm(p) for p in a]))
+        assert np.array_equal(utils.rowdot(a[:7, None, :], b[None, :5, :]),
+                              np.array([[np.dot(p, q) for q in b[:5]] for p in a[:7]]))
+    x = np.abs(rng.randn(5000)) * 4.0
+    assert np.array_equal(utils.pow2(x), np.array([float(v) ** 2 for v in x]))
+    assert np.array_equal(np.exp(-utils.pow2(x) / 2.0), np.array([np.exp(-(float(v) ** 2) / 2.0) for v in x]))
+    # both implementations behind the switch agree with each other
+    assert np.array_equal(utils._rowdot_loop(a, b), utils.rowdot(a, b)) and np.array_equal(utils._pow2_loop(x), utils.pow2(x))
