@@ -15,6 +15,8 @@
 // with the CPU reference to the last bit. Parallelism comes from the candidates (one thread per
 // candidate in 2-D, one CTA per candidate in 3-D with one thread per z-slice), never from
 // re-associating a sum.
+#include <climits>
+
 #include "common.cuh"
 
 namespace pgm {
@@ -87,11 +89,22 @@ __global__ void k5_rank_kernel(const double *__restrict__ objs, int n, const int
 // ------------------------------------------------------------------------------------------------
 // selection state in the workspace
 // ------------------------------------------------------------------------------------------------
+// What the 3-objective scorer needs of the round's base front and every candidate shares (built once per round by
+// base3d_build): negated coordinates in front order, the three sorted lists of preProcess and the z ranks, the slice
+// areas, and the hypervolume chain after every term.
+struct Base3d {
+    double *nx, *ny, *nz;     // [nmax]
+    double *area;             // [nmax] 2-D area of the first k+1 points of the z list
+    double *vpre;             // [nmax] vpre[k] = sum of the terms 1..k of the hypervolume chain (vpre[0] = 0)
+    int *xl, *yl, *zl, *zr;   // [nmax] sorted lists (positions in the front) and z rank of every point
+};
+
 struct SelState {
     double *front[2];   // virtual EP, double buffered [Emax][M]
     int *count;         // [2] sizes of front[0] / front[1]
     int *mask;          // [C] 1 = candidate still available
     int *done;          // [1] set when a round found no candidate
+    Base3d b3;          // 3 objectives only
 };
 
 // ---- 2 objectives: one thread per candidate -------------------------------------------------------
@@ -302,16 +315,268 @@ __global__ void __launch_bounds__(256) k5_score3d_kernel(SelState st, int buf, c
     }
 }
 
+// ---- 3 objectives, incremental: every candidate of a round extends the SAME base front ---------------------------
+// In-place exclusive prefix sum of a[0..n) in shared memory; returns the total. Every thread of the CTA calls it.
+__device__ __forceinline__ int block_excl_scan(int *a, int n, int *wtot) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int per = (n + nt - 1) / nt, lo = min(n, tid * per), hi = min(n, lo + per);
+    int local = 0;
+    for (int i = lo; i < hi; ++i) local += a[i];
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < nw; ++w) { const int v = wtot[w]; if (w < warp) off += v; total += v; }
+    int run = off + inc - local;
+    for (int i = lo; i < hi; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+    return total;
+}
+
+// 2-D area of the points with z rank <= k, walked in y-list order (hypervolume.py:92-105)
+__device__ __forceinline__ double slice_area(const double *nx, const double *ny, const int *yl, const int *zr, int n, int k) {
+    double h = 0.0, acc = 0.0, prevy = 0.0;
+    bool first = true;
+    for (int t = 0; t < n; ++t) {
+        const int j = yl[t];
+        if (zr[j] > k) continue;
+        if (first) { h = nx[j]; prevy = ny[j]; first = false; }
+        else {
+            acc = dadd(acc, dmul(h, dsub(prevy, ny[j])));
+            if (nx[j] < h) h = nx[j];
+            prevy = ny[j];
+        }
+    }
+    return dadd(acc, dmul(h, prevy));
+}
+
+// Base data of front f (n0 points) for the incremental scorer; all threads of ONE CTA. Global memory only (written and
+// read back by the same CTA across __syncthreads).
+__device__ inline void base3d_build(const double *f, int n0, Base3d b) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < n0; i += nt) { b.nx[i] = -f[3 * i]; b.ny[i] = -f[3 * i + 1]; b.nz[i] = -f[3 * i + 2]; }
+    if (tid == 0) b.vpre[0] = 0.0;
+    __syncthreads();
+    // the three sorted lists of preProcess (hypervolume.py:156-164): successive stable sorts by x, y, z
+    for (int i = tid; i < n0; i += nt) {
+        const double xi = b.nx[i], yi = b.ny[i], zi = b.nz[i];
+        int rx = 0, ry = 0, rz = 0;
+        for (int j = 0; j < n0; ++j) {
+            const double xj = b.nx[j], yj = b.ny[j], zj = b.nz[j];
+            const bool xlt = xj < xi || (xj == xi && j < i);
+            const bool ylt = yj < yi || (yj == yi && xlt);
+            const bool zlt = zj < zi || (zj == zi && ylt);
+            rx += xlt; ry += ylt; rz += zlt;
+        }
+        b.xl[rx] = i; b.yl[ry] = i; b.zl[rz] = i; b.zr[i] = rz;
+    }
+    __syncthreads();
+    for (int k = tid; k < n0; k += nt) b.area[k] = slice_area(b.nx, b.ny, b.yl, b.zr, n0, k);
+    __syncthreads();
+    for (int k = 1 + tid; k < n0; k += nt) b.vpre[k] = dmul(b.area[k - 1], dsub(b.nz[b.zl[k]], b.nz[b.zl[k - 1]]));
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+#pragma unroll 8
+        for (int k = 1; k < n0; ++k) { v = dadd(v, b.vpre[k]); b.vpre[k] = v; }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k5_base3d_kernel(SelState st, int buf) { base3d_build(st.front[buf], st.count[buf], st.b3); }
+
+// One CTA per candidate p: L = update_ep(front, p); hv = round4(InnerHyperVolume(L)); sp = compute_sparsity(L) -- the same
+// numbers as k5_score3d_kernel, bit for bit, without redoing what L shares with the base front:
+//  * the sorted lists of L are the base lists with the points p dominates filtered out (prefix sums of the keep flags
+//    along each list) and p slotted in at its rank (one comparison per point; ties broken by the position update_ep gives p);
+//  * the slices below n_same = min(z rank of p, lowest z rank of a removed point) contain exactly the base points in the base
+//    order, so their areas and the head of the hypervolume chain are the base's; only the slices from n_same on are walked;
+//  * warps 0-7 walk slices while warp 8 forms the sparsity terms and runs that serial sum.
+// Points are named by id: position in the base front, or n0 for p.
+constexpr int S3_WORKERS = 256, S3_THREADS = 288;
+__global__ void __launch_bounds__(S3_THREADS) k5_score3d_inc_kernel(SelState st, int buf, const double *__restrict__ cand, int C,
+                                                                    double *__restrict__ hv, double *__restrict__ sp, int nmax) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    if (*st.done || !st.mask[c]) {
+        if (tid == 0) { hv[c] = 0.0; sp[c] = 0.0; }
+        return;
+    }
+    double *cx = reinterpret_cast<double *>(smraw), *cy = cx + nmax, *cz = cy + nmax, *area = cz + nmax, *term = area + nmax;
+    double *gsq = term + nmax;                                             // [3 * nmax]
+    int *km = reinterpret_cast<int *>(gsq + 3 * nmax), *tmp = km + nmax, *xl = tmp + nmax, *yl = xl + nmax, *zl = yl + nmax,
+        *zr = zl + nmax;
+    unsigned char *rel = reinterpret_cast<unsigned char *>(zr + nmax);      // bit 0/1/2: point precedes p in the x/y/z list; bit 3: kept
+    __shared__ int s_on_ep, s_ip, s_rp[3], s_zmin, wtot[S3_THREADS / 32];
+
+    const Base3d b = st.b3;
+    const int n0 = st.count[buf];
+    const double p0 = cand[3 * c], p1 = cand[3 * c + 1], p2 = cand[3 * c + 2];
+    const bool p_valid = p0 >= 0.0 && p1 >= 0.0 && p2 >= 0.0;
+    for (int i = tid; i < n0; i += nt) { cx[i] = b.nx[i]; cy[i] = b.ny[i]; cz[i] = b.nz[i]; }
+    if (tid == 0) {
+        cx[n0] = -p0; cy[n0] = -p1; cz[n0] = -p2;
+        s_on_ep = 1; s_ip = INT_MAX; s_rp[0] = s_rp[1] = s_rp[2] = 0; s_zmin = INT_MAX;
+    }
+    __syncthreads();
+    // ---- update_ep (utils.py:42-65): keep flags, on_ep ----
+    for (int i = tid; i < n0; i += nt) {
+        const double q0 = -cx[i], q1 = -cy[i], q2 = -cz[i];
+        bool keep = true;
+        if (p_valid) {
+            keep = !(p0 >= q0 && p1 >= q1 && p2 >= q2);
+            if (q0 >= p0 - 1e-5 && q1 >= p1 - 1e-5 && q2 >= p2 - 1e-5 && (q0 > p0 + 1e-5 || q1 > p1 + 1e-5 || q2 > p2 + 1e-5))
+                s_on_ep = 0;                                     // benign race: every writer stores 0
+        }
+        km[i] = keep ? 1 : 0;
+        rel[i] = keep ? 8 : 0;
+    }
+    __syncthreads();
+    const int kept = block_excl_scan(km, n0, wtot);              // km[i] = position of base point i among the kept ones
+    const bool ins = p_valid && s_on_ep;
+    if (ins)
+        for (int i = tid; i < n0; i += nt)
+            if ((rel[i] & 8) && p0 < -cx[i]) atomicMin(&s_ip, km[i]);      // p goes before the first kept q with p0 < q0
+    __syncthreads();
+    const int ip = min(s_ip, kept), n = kept + (ins ? 1 : 0);
+    if (n == 0) {
+        if (tid == 0) { hv[c] = 0.0; sp[c] = 0.0; }
+        return;
+    }
+    // ---- where p ranks in the three lists; lowest base z rank among the removed points ----
+    {
+        const double px = cx[n0], py = cy[n0], pz = cz[n0];
+        int r0 = 0, r1 = 0, r2 = 0, zmin = INT_MAX;
+        for (int j = tid; j < n0; j += nt) {
+            if (!(rel[j] & 8)) { zmin = min(zmin, b.zr[j]); continue; }
+            if (!ins) continue;
+            const bool xlt = cx[j] < px || (cx[j] == px && km[j] < ip);       // key (x, position in L)
+            const bool ylt = cy[j] < py || (cy[j] == py && xlt);              // key (y, x, position)
+            const bool zlt = cz[j] < pz || (cz[j] == pz && ylt);              // key (z, y, x, position)
+            rel[j] |= (xlt ? 1 : 0) | (ylt ? 2 : 0) | (zlt ? 4 : 0);
+            r0 += xlt; r1 += ylt; r2 += zlt;
+        }
+        if (r0) atomicAdd(&s_rp[0], r0);
+        if (r1) atomicAdd(&s_rp[1], r1);
+        if (r2) atomicAdd(&s_rp[2], r2);
+        if (zmin != INT_MAX) atomicMin(&s_zmin, zmin);
+    }
+    __syncthreads();
+    // ---- the sorted lists of L ----
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int *bl = d == 0 ? b.xl : (d == 1 ? b.yl : b.zl);
+        int *lst = d == 0 ? xl : (d == 1 ? yl : zl);
+        for (int t = tid; t < n0; t += nt) tmp[t] = (rel[bl[t]] >> 3) & 1;
+        __syncthreads();
+        block_excl_scan(tmp, n0, wtot);
+        for (int t = tid; t < n0; t += nt) {
+            const int j = bl[t];
+            if (!(rel[j] & 8)) continue;
+            const int r = tmp[t] + ((ins && !((rel[j] >> d) & 1)) ? 1 : 0);
+            lst[r] = j;
+            if (d == 2) zr[j] = r;
+        }
+        if (tid == 0 && ins) { lst[s_rp[d]] = n0; if (d == 2) zr[n0] = s_rp[2]; }
+        __syncthreads();
+    }
+    const int n_same = min(ins ? s_rp[2] : n, s_zmin == INT_MAX ? n : s_zmin);
+    // ---- slices (warps 0-7) | sparsity (warp 8) ----
+    if (warp < S3_WORKERS / 32) {
+        for (int k = tid; k < n_same; k += S3_WORKERS) area[k] = b.area[k];
+        for (int k = n_same + tid; k < n; k += S3_WORKERS) area[k] = slice_area(cx, cy, yl, zr, n, k);
+    } else {
+        // utils.compute_sparsity: per dimension the ascending values (= the negated lists read backwards), one running sum
+        const int m1 = n - 1;
+        for (int idx = lane; idx < 3 * m1; idx += 32) {
+            const int d = idx / m1, i = idx - d * m1 + 1;
+            const int *lst = d == 0 ? xl : (d == 1 ? yl : zl);
+            const double *v = d == 0 ? cx : (d == 1 ? cy : cz);
+            const double g = dsub(-v[lst[n - 1 - i]], -v[lst[n - i]]);
+            gsq[idx] = dmul(g, g);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double sacc = 0.0;
+#pragma unroll 8
+            for (int idx = 0; idx < 3 * m1; ++idx) sacc = dadd(sacc, gsq[idx]);
+            sp[c] = n >= 2 ? sacc / (double)m1 : 0.0;
+        }
+    }
+    __syncthreads();
+    // ---- hypervolume: sum over the slices in order; the head of the sum is the base front's ----
+    const int k0 = max(n_same, 1);
+    for (int k = k0 + tid; k < n; k += nt) term[k] = dmul(area[k - 1], dsub(cz[zl[k]], cz[zl[k - 1]]));
+    __syncthreads();
+    if (tid == 0) {
+        double v = b.vpre[k0 - 1];
+#pragma unroll 8
+        for (int k = k0; k < n; ++k) v = dadd(v, term[k]);
+        v = dsub(v, dmul(area[n - 1], cz[zl[n - 1]]));
+        hv[c] = round4(v);
+    }
+}
+
+// update_ep (utils.py:42-65) by all threads of one CTA: same result as update_front_3d. flags: [n] ints of shared memory.
+__device__ inline void update_front_3d_block(const double *f, int n, const double *p, double *out, int *count_out, int *flags,
+                                             int *wtot) {
+    __shared__ int s_on, s_pos;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double p0 = p[0], p1 = p[1], p2 = p[2];
+    if (p0 < 0.0 || p1 < 0.0 || p2 < 0.0) {
+        for (int i = tid; i < 3 * n; i += nt) out[i] = f[i];
+        if (tid == 0) *count_out = n;
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) { s_on = 1; s_pos = INT_MAX; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const double q0 = f[3 * i], q1 = f[3 * i + 1], q2 = f[3 * i + 2];
+        if (q0 >= p0 - 1e-5 && q1 >= p1 - 1e-5 && q2 >= p2 - 1e-5 && (q0 > p0 + 1e-5 || q1 > p1 + 1e-5 || q2 > p2 + 1e-5)) s_on = 0;
+        flags[i] = (p0 >= q0 && p1 >= q1 && p2 >= q2) ? 0 : 1;
+    }
+    __syncthreads();
+    const int m = block_excl_scan(flags, n, wtot);
+    const bool on = s_on != 0;
+    if (on)
+        for (int i = tid; i < n; i += nt) {
+            const double q0 = f[3 * i], q1 = f[3 * i + 1], q2 = f[3 * i + 2];
+            if (!(p0 >= q0 && p1 >= q1 && p2 >= q2) && p0 < q0) atomicMin(&s_pos, flags[i]);
+        }
+    __syncthreads();
+    const int pos = min(s_pos, m);
+    for (int i = tid; i < n; i += nt) {
+        const double q0 = f[3 * i], q1 = f[3 * i + 1], q2 = f[3 * i + 2];
+        if (p0 >= q0 && p1 >= q1 && p2 >= q2) continue;
+        const int dst = flags[i] + ((on && flags[i] >= pos) ? 1 : 0);
+        out[3 * dst] = q0; out[3 * dst + 1] = q1; out[3 * dst + 2] = q2;
+    }
+    if (tid == 0) {
+        if (on) { out[3 * pos] = p0; out[3 * pos + 1] = p1; out[3 * pos + 2] = p2; }
+        *count_out = m + (on ? 1 : 0);
+    }
+    __syncthreads();
+}
+
 // ---- arg-max + virtual EP update: single CTA ---------------------------------------------------------
+// 3 objectives: dynamic shared memory of nmax ints; the new front's base data for the next round's scorer is built here.
 template <int M>
 __global__ void __launch_bounds__(1024) k5_pick_kernel(SelState st, int buf, const double *__restrict__ cand, int C,
                                                        const double *__restrict__ hv, const double *__restrict__ sp,
                                                        double alpha, int32_t *__restrict__ best_out) {
+    extern __shared__ __align__(16) unsigned char pick_smem[];
     __shared__ double sv[32];
     __shared__ int si[32];
+    __shared__ int wtot[32];
     const int tid = threadIdx.x;
-    __shared__ int s_copy;
-    if (tid == 0) s_copy = *st.done;
+    __shared__ int s_copy, s_bi;
+    if (tid == 0) { s_copy = *st.done; s_bi = -1; }
     __syncthreads();
     if (!s_copy) {
         double bv = -INFINITY;
@@ -335,16 +600,19 @@ __global__ void __launch_bounds__(1024) k5_pick_kernel(SelState st, int buf, con
                 if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
             }
             *best_out = bi;
+            s_bi = bi;
             if (bi < 0) { *st.done = 1; s_copy = 1; }      // "Too few candidates": stop, keep the front
             else {
                 st.mask[bi] = 0;
-                const double *f = st.front[buf];
-                double *out = st.front[buf ^ 1];
-                if (M == 2) st.count[buf ^ 1] = update_front_2d(f, st.count[buf], cand[2 * bi], cand[2 * bi + 1], out);
-                else st.count[buf ^ 1] = update_front_3d(f, st.count[buf], cand + 3 * bi, out);
+                if (M == 2) st.count[buf ^ 1] = update_front_2d(st.front[buf], st.count[buf], cand[2 * bi], cand[2 * bi + 1], st.front[buf ^ 1]);
             }
         }
         __syncthreads();
+        if (M == 3 && s_bi >= 0) {
+            update_front_3d_block(st.front[buf], st.count[buf], cand + 3 * s_bi, st.front[buf ^ 1], &st.count[buf ^ 1],
+                                  reinterpret_cast<int *>(pick_smem), wtot);
+            base3d_build(st.front[buf ^ 1], st.count[buf ^ 1], st.b3);
+        }
     } else if (tid == 0) *best_out = -1;
     if (s_copy) {      // no pick this round: carry the front over so the buffers keep alternating
         const int n = st.count[buf];
@@ -395,10 +663,21 @@ static size_t sel_carve(SelState &st, char *ws, int E, int C, int M, int num_tas
         st.front[0] = (double *)(ws + o0); st.front[1] = (double *)(ws + o1);
         st.count = (int *)(ws + oc); st.mask = (int *)(ws + om); st.done = (int *)(ws + od);
     }
+    if (M == 3) {
+        const size_t nmax = (size_t)(E + num_tasks + 1);
+        const size_t od5 = seg(5 * nmax * sizeof(double)), oi4 = seg(4 * nmax * sizeof(int));
+        if (ws) {
+            double *d = (double *)(ws + od5);
+            int *i = (int *)(ws + oi4);
+            st.b3.nx = d; st.b3.ny = d + nmax; st.b3.nz = d + 2 * nmax; st.b3.area = d + 3 * nmax; st.b3.vpre = d + 4 * nmax;
+            st.b3.xl = i; st.b3.yl = i + nmax; st.b3.zl = i + 2 * nmax; st.b3.zr = i + 3 * nmax;
+        }
+    }
     return off;
 }
 
 static size_t score3d_smem(int nmax) { return (size_t)nmax * (4 * sizeof(double) + 5 * sizeof(int)); }
+static size_t score3d_inc_smem(int nmax) { return (size_t)nmax * (8 * sizeof(double) + 6 * sizeof(int) + 1) + 16; }
 
 }  // namespace pgm
 
@@ -440,24 +719,25 @@ extern "C" int pgm_select_greedy_f64(const double *ep, int E, const double *cand
     if (need > workspace_bytes) { set_error("pgm_select_greedy_f64: workspace too small: need %zu, got %zu", need, workspace_bytes); return PGM_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     const int nmax = E + num_tasks + 1;
-    const size_t smem3 = score3d_smem(nmax);
+    const size_t smem3 = score3d_inc_smem(nmax);
     if (M == 3) {
         PGM_REQUIRE(smem3 <= 200 * 1024, "pgm_select_greedy_f64: front of %d points exceeds the 3-D scorer's shared memory", nmax);
-        PGM_CUDA(cudaFuncSetAttribute(k5_score3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        PGM_CUDA(cudaFuncSetAttribute(k5_score3d_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     }
     {
         const int nthr = (E * M > C ? E * M : C) + 1;
         k5_init_kernel<<<(nthr + 255) / 256, 256, 0, s>>>(st, ep, E, M, C);
+        if (M == 3 && C > 0) k5_base3d_kernel<<<1, 1024, 0, s>>>(st, 0);
     }
     for (int r = 0; r < num_tasks; ++r) {
         const int buf = r & 1;
         double *hv_r = hv + (size_t)r * C, *sp_r = sparsity + (size_t)r * C;
         if (C > 0) {
             if (M == 2) k5_score2d_kernel<<<(C + 127) / 128, 128, 0, s>>>(st, buf, cand, C, hv_r, sp_r);
-            else k5_score3d_kernel<<<C, 256, smem3, s>>>(st, buf, cand, C, hv_r, sp_r, nmax, 1);
+            else k5_score3d_inc_kernel<<<C, S3_THREADS, smem3, s>>>(st, buf, cand, C, hv_r, sp_r, nmax);
         }
         if (M == 2) k5_pick_kernel<2><<<1, 1024, 0, s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r);
-        else k5_pick_kernel<3><<<1, 1024, 0, s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r);
+        else k5_pick_kernel<3><<<1, 1024, (size_t)nmax * sizeof(int), s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r);
     }
     k5_finish_kernel<<<8, 256, 0, s>>>(st, num_tasks & 1, M, front_out, n_front);
     PGM_CUDA(cudaGetLastError());

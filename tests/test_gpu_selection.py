@@ -393,3 +393,41 @@ def test_fit_input_kernels_edge_cases():
     front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, np.arange(3), False)
     assert (front["klen"] == 0).all() and (front["steps"] > 1000).all()
     assert np.array_equal(front["ub"].cpu().numpy(), np.tile([1.0, 20.0, 5.0, 500.0], (6, 1)))
+
+
+def test_incremental_3d_scorer_matches_oracle_on_adversarial_fronts():
+    """K5's 3-objective scorer reuses the round's base front (sorted lists, slice areas, head of the hypervolume sum)
+    for every candidate. Fronts and candidates built to hit its special cases -- ties in every coordinate, candidates
+    equal to a front point, candidates that dominate many points (removals below and above their own z rank), dominated
+    and negative candidates, an empty archive -- scored over several greedy rounds: every round's hv / sparsity array and
+    every pick must equal the python restatement of the reference (update_ep + InnerHyperVolume + compute_sparsity)."""
+    from pgmorl_b200 import kernels as K
+    rng = np.random.RandomState(5)
+
+    def shell(n, r, quant=None):
+        v = np.abs(rng.normal(size=(n, 3))) + 0.05
+        v = v / np.linalg.norm(v, axis=1, keepdims=True) * r
+        if quant:
+            v = np.round(v / quant) * quant              # coordinates on a coarse grid: many exact ties
+        return v
+
+    cases = []
+    ep = shell(40, 50.0)
+    cand = np.concatenate([shell(30, 50.0), shell(20, 56.0), shell(10, 44.0), ep[:5].copy(), ep[5:8] + [0.0, 1e-6, 0.0],
+                           np.array([[60.0, 60.0, 60.0], [-1.0, 70.0, 70.0], [0.0, 0.0, 0.0], [49.0, 49.0, 0.5]])])
+    cases.append((ep, cand, 4))
+    ep = shell(60, 30.0, quant=2.0)
+    ep = ep[so.get_ep_indices(ep)]
+    cand = np.concatenate([shell(40, 31.0, quant=2.0), shell(20, 34.0, quant=1.0), ep[:6].copy()])
+    cases.append((ep, cand, 5))
+    cases.append((np.zeros((0, 3)), shell(12, 10.0), 3))                                  # empty archive
+    cases.append((shell(1, 20.0), np.concatenate([shell(8, 20.0), shell(4, 25.0)]), 3))
+    for ep, cand, rounds in cases:
+        ep = ep[np.argsort(ep[:, 0], kind="stable")] if len(ep) else ep
+        for alpha in (0.0, 1.0):
+            best, hv, sp, front = K.select_greedy(ep, cand, alpha, rounds)
+            obest, ohv, osp = so.greedy_select_3d(ep, cand, alpha, rounds)
+            assert best.tolist() == list(obest), (best, obest)
+            for r in range(rounds):
+                assert np.array_equal(hv[r], ohv[r]), (r, np.nonzero(hv[r] != ohv[r])[0][:5])
+                assert np.array_equal(sp[r], osp[r]), (r, np.nonzero(sp[r] != osp[r])[0][:5])
