@@ -338,47 +338,59 @@ __device__ __forceinline__ int block_excl_scan(int *a, int n, int *wtot) {
     return total;
 }
 
-// 2-D area of the points with z rank <= k, walked in y-list order (hypervolume.py:92-105)
-__device__ __forceinline__ double slice_area(const double *nx, const double *ny, const int *yl, const int *zr, int n, int k) {
+// 2-D area of the points with z rank <= k, walked in y-list order (hypervolume.py:92-105). The points come in y-list
+// order already (hx[t], hy[t] = x, y of the t-th point of the y list, hz[t] = its z rank): every load is independent of
+// the running sums, and all threads of a warp (one slice each) read the same t -- shared-memory broadcasts.
+__device__ __forceinline__ double slice_area(const double *hx, const double *hy, const int *hz, int n, int k) {
     double h = 0.0, acc = 0.0, prevy = 0.0;
     bool first = true;
+#pragma unroll 4
     for (int t = 0; t < n; ++t) {
-        const int j = yl[t];
-        if (zr[j] > k) continue;
-        if (first) { h = nx[j]; prevy = ny[j]; first = false; }
+        const double x = hx[t], y = hy[t];
+        if (hz[t] > k) continue;
+        if (first) { h = x; prevy = y; first = false; }
         else {
-            acc = dadd(acc, dmul(h, dsub(prevy, ny[j])));
-            if (nx[j] < h) h = nx[j];
-            prevy = ny[j];
+            acc = dadd(acc, dmul(h, dsub(prevy, y)));
+            if (x < h) h = x;
+            prevy = y;
         }
     }
     return dadd(acc, dmul(h, prevy));
 }
 
-// Base data of front f (n0 points) for the incremental scorer; all threads of ONE CTA. Global memory only (written and
-// read back by the same CTA across __syncthreads).
-__device__ inline void base3d_build(const double *f, int n0, Base3d b) {
+// Base data of front f (n0 points) for the incremental scorer; all threads of ONE CTA.
+// Dynamic shared memory: 5 * nmax doubles + nmax ints (coordinates; the points in y-list order).
+static size_t base3d_smem(int nmax) { return (size_t)nmax * (5 * sizeof(double) + sizeof(int)); }
+__device__ inline void base3d_build(const double *f, int n0, int nmax, Base3d b, unsigned char *smem) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < n0; i += nt) { b.nx[i] = -f[3 * i]; b.ny[i] = -f[3 * i + 1]; b.nz[i] = -f[3 * i + 2]; }
+    double *sx = reinterpret_cast<double *>(smem), *sy = sx + nmax, *sz = sy + nmax, *hx = sz + nmax, *hy = hx + nmax;
+    int *hz = reinterpret_cast<int *>(hy + nmax);
+    for (int i = tid; i < n0; i += nt) {
+        const double x = -f[3 * i], y = -f[3 * i + 1], z = -f[3 * i + 2];
+        sx[i] = x; sy[i] = y; sz[i] = z;
+        b.nx[i] = x; b.ny[i] = y; b.nz[i] = z;
+    }
     if (tid == 0) b.vpre[0] = 0.0;
     __syncthreads();
     // the three sorted lists of preProcess (hypervolume.py:156-164): successive stable sorts by x, y, z
     for (int i = tid; i < n0; i += nt) {
-        const double xi = b.nx[i], yi = b.ny[i], zi = b.nz[i];
+        const double xi = sx[i], yi = sy[i], zi = sz[i];
         int rx = 0, ry = 0, rz = 0;
+#pragma unroll 4
         for (int j = 0; j < n0; ++j) {
-            const double xj = b.nx[j], yj = b.ny[j], zj = b.nz[j];
+            const double xj = sx[j], yj = sy[j], zj = sz[j];
             const bool xlt = xj < xi || (xj == xi && j < i);
             const bool ylt = yj < yi || (yj == yi && xlt);
             const bool zlt = zj < zi || (zj == zi && ylt);
             rx += xlt; ry += ylt; rz += zlt;
         }
         b.xl[rx] = i; b.yl[ry] = i; b.zl[rz] = i; b.zr[i] = rz;
+        hx[ry] = xi; hy[ry] = yi; hz[ry] = rz;
     }
     __syncthreads();
-    for (int k = tid; k < n0; k += nt) b.area[k] = slice_area(b.nx, b.ny, b.yl, b.zr, n0, k);
+    for (int k = tid; k < n0; k += nt) b.area[k] = slice_area(hx, hy, hz, n0, k);
     __syncthreads();
-    for (int k = 1 + tid; k < n0; k += nt) b.vpre[k] = dmul(b.area[k - 1], dsub(b.nz[b.zl[k]], b.nz[b.zl[k - 1]]));
+    for (int k = 1 + tid; k < n0; k += nt) b.vpre[k] = dmul(b.area[k - 1], dsub(sz[b.zl[k]], sz[b.zl[k - 1]]));
     __syncthreads();
     if (tid == 0) {
         double v = 0.0;
@@ -388,7 +400,10 @@ __device__ inline void base3d_build(const double *f, int n0, Base3d b) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) k5_base3d_kernel(SelState st, int buf) { base3d_build(st.front[buf], st.count[buf], st.b3); }
+__global__ void __launch_bounds__(1024) k5_base3d_kernel(SelState st, int buf, int nmax) {
+    extern __shared__ __align__(16) unsigned char base_smem[];
+    base3d_build(st.front[buf], st.count[buf], nmax, st.b3, base_smem);
+}
 
 // One CTA per candidate p: L = update_ep(front, p); hv = round4(InnerHyperVolume(L)); sp = compute_sparsity(L) -- the same
 // numbers as k5_score3d_kernel, bit for bit, without redoing what L shares with the base front:
@@ -408,9 +423,11 @@ __global__ void __launch_bounds__(S3_THREADS) k5_score3d_inc_kernel(SelState st,
         return;
     }
     double *cx = reinterpret_cast<double *>(smraw), *cy = cx + nmax, *cz = cy + nmax, *area = cz + nmax, *term = area + nmax;
-    double *gsq = term + nmax;                                             // [3 * nmax]
-    int *km = reinterpret_cast<int *>(gsq + 3 * nmax), *tmp = km + nmax, *xl = tmp + nmax, *yl = xl + nmax, *zl = yl + nmax,
+    double *gsq = term + nmax, *hy = gsq + 3 * nmax;                       // gsq [3 * nmax]
+    double *hx = term;                                                     // the slice walk is over before `term` is formed
+    int *km = reinterpret_cast<int *>(hy + nmax), *tmp = km + nmax, *xl = tmp + nmax, *yl = xl + nmax, *zl = yl + nmax,
         *zr = zl + nmax;
+    int *hz = tmp;                                                         // the scans are over before the slice walk
     unsigned char *rel = reinterpret_cast<unsigned char *>(zr + nmax);      // bit 0/1/2: point precedes p in the x/y/z list; bit 3: kept
     __shared__ int s_on_ep, s_ip, s_rp[3], s_zmin, wtot[S3_THREADS / 32];
 
@@ -486,10 +503,12 @@ __global__ void __launch_bounds__(S3_THREADS) k5_score3d_inc_kernel(SelState st,
         __syncthreads();
     }
     const int n_same = min(ins ? s_rp[2] : n, s_zmin == INT_MAX ? n : s_zmin);
+    for (int t = tid; t < n; t += nt) { const int j = yl[t]; hx[t] = cx[j]; hy[t] = cy[j]; hz[t] = zr[j]; }
+    __syncthreads();
     // ---- slices (warps 0-7) | sparsity (warp 8) ----
     if (warp < S3_WORKERS / 32) {
         for (int k = tid; k < n_same; k += S3_WORKERS) area[k] = b.area[k];
-        for (int k = n_same + tid; k < n; k += S3_WORKERS) area[k] = slice_area(cx, cy, yl, zr, n, k);
+        for (int k = n_same + tid; k < n; k += S3_WORKERS) area[k] = slice_area(hx, hy, hz, n, k);
     } else {
         // utils.compute_sparsity: per dimension the ascending values (= the negated lists read backwards), one running sum
         const int m1 = n - 1;
@@ -565,11 +584,12 @@ __device__ inline void update_front_3d_block(const double *f, int n, const doubl
 }
 
 // ---- arg-max + virtual EP update: single CTA ---------------------------------------------------------
-// 3 objectives: dynamic shared memory of nmax ints; the new front's base data for the next round's scorer is built here.
+// 3 objectives: dynamic shared memory of base3d_smem(nmax) bytes (first used as nmax ints by the front update); the new
+// front's base data for the next round's scorer is built here.
 template <int M>
 __global__ void __launch_bounds__(1024) k5_pick_kernel(SelState st, int buf, const double *__restrict__ cand, int C,
                                                        const double *__restrict__ hv, const double *__restrict__ sp,
-                                                       double alpha, int32_t *__restrict__ best_out) {
+                                                       double alpha, int32_t *__restrict__ best_out, int nmax) {
     extern __shared__ __align__(16) unsigned char pick_smem[];
     __shared__ double sv[32];
     __shared__ int si[32];
@@ -611,7 +631,7 @@ __global__ void __launch_bounds__(1024) k5_pick_kernel(SelState st, int buf, con
         if (M == 3 && s_bi >= 0) {
             update_front_3d_block(st.front[buf], st.count[buf], cand + 3 * s_bi, st.front[buf ^ 1], &st.count[buf ^ 1],
                                   reinterpret_cast<int *>(pick_smem), wtot);
-            base3d_build(st.front[buf ^ 1], st.count[buf ^ 1], st.b3);
+            base3d_build(st.front[buf ^ 1], st.count[buf ^ 1], nmax, st.b3, pick_smem);
         }
     } else if (tid == 0) *best_out = -1;
     if (s_copy) {      // no pick this round: carry the front over so the buffers keep alternating
@@ -677,7 +697,7 @@ static size_t sel_carve(SelState &st, char *ws, int E, int C, int M, int num_tas
 }
 
 static size_t score3d_smem(int nmax) { return (size_t)nmax * (4 * sizeof(double) + 5 * sizeof(int)); }
-static size_t score3d_inc_smem(int nmax) { return (size_t)nmax * (8 * sizeof(double) + 6 * sizeof(int) + 1) + 16; }
+static size_t score3d_inc_smem(int nmax) { return (size_t)nmax * (9 * sizeof(double) + 6 * sizeof(int) + 1) + 16; }
 
 }  // namespace pgm
 
@@ -719,15 +739,17 @@ extern "C" int pgm_select_greedy_f64(const double *ep, int E, const double *cand
     if (need > workspace_bytes) { set_error("pgm_select_greedy_f64: workspace too small: need %zu, got %zu", need, workspace_bytes); return PGM_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     const int nmax = E + num_tasks + 1;
-    const size_t smem3 = score3d_inc_smem(nmax);
+    const size_t smem3 = score3d_inc_smem(nmax), smemb = base3d_smem(nmax);
     if (M == 3) {
         PGM_REQUIRE(smem3 <= 200 * 1024, "pgm_select_greedy_f64: front of %d points exceeds the 3-D scorer's shared memory", nmax);
         PGM_CUDA(cudaFuncSetAttribute(k5_score3d_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        PGM_CUDA(cudaFuncSetAttribute(k5_base3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb));
+        PGM_CUDA(cudaFuncSetAttribute(k5_pick_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb));
     }
     {
         const int nthr = (E * M > C ? E * M : C) + 1;
         k5_init_kernel<<<(nthr + 255) / 256, 256, 0, s>>>(st, ep, E, M, C);
-        if (M == 3 && C > 0) k5_base3d_kernel<<<1, 1024, 0, s>>>(st, 0);
+        if (M == 3 && C > 0) k5_base3d_kernel<<<1, 1024, smemb, s>>>(st, 0, nmax);
     }
     for (int r = 0; r < num_tasks; ++r) {
         const int buf = r & 1;
@@ -736,8 +758,8 @@ extern "C" int pgm_select_greedy_f64(const double *ep, int E, const double *cand
             if (M == 2) k5_score2d_kernel<<<(C + 127) / 128, 128, 0, s>>>(st, buf, cand, C, hv_r, sp_r);
             else k5_score3d_inc_kernel<<<C, S3_THREADS, smem3, s>>>(st, buf, cand, C, hv_r, sp_r, nmax);
         }
-        if (M == 2) k5_pick_kernel<2><<<1, 1024, 0, s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r);
-        else k5_pick_kernel<3><<<1, 1024, (size_t)nmax * sizeof(int), s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r);
+        if (M == 2) k5_pick_kernel<2><<<1, 1024, 0, s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r, nmax);
+        else k5_pick_kernel<3><<<1, 1024, smemb, s>>>(st, buf, cand, C, hv_r, sp_r, alpha, best_ids + r, nmax);
     }
     k5_finish_kernel<<<8, 256, 0, s>>>(st, num_tasks & 1, M, front_out, n_front);
     PGM_CUDA(cudaGetLastError());

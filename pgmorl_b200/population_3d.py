@@ -192,11 +192,15 @@ class Population:
         N = args.num_tasks
         # the reference rebuilds this simplex grid for every sample (population_3d.py:262-263); it is a pure function of the
         # arguments (no RNG), so it is enumerated once
-        grid = []
-        generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
+        key = (args.obj_num, args.delta_weight)
+        if getattr(self, '_grid_key', None) != key:
+            grid = []
+            generate_weights_batch_dfs(0, args.obj_num, 0.0, 1.0, args.delta_weight / 2.0, [], grid)
+            self._grid_arr = np.array(grid, dtype=np.float64)
+            self._grid_norm = rownorm(self._grid_arr)
+            self._grid_key = key
+        grid_arr, grid_norm = self._grid_arr, self._grid_norm
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
-        grid_arr = np.array(grid, dtype=np.float64)
-        grid_norm = rownorm(grid_arr)
         tests, counts, pred, self.last_fits = predict_candidates(
             opt_graph, self.sample_batch, lambda view, ids: self._test_weights_batch(args, view, ids, grid_arr, grid_norm),
             args.obj_num, cap_threshold=True, max_tests=args.num_weight_candidates + 1, tests_in_lockstep=True)
