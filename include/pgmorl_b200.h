@@ -193,11 +193,14 @@ int pgm_fit_hyperbolic_f64(const double *x, const double *y, const double *w, co
  *   source [n,Kmax] = source node of every listed edge. Kmax >= max(klen). The Gaussian point weights
  *   exp(-(dist / sigma)^2 / 2) (population_2d.py:90-96) need numpy's exp bit for bit and are formed by the host from
  *   `source`.
- * M in 2..4; the opt-graph must fit one CTA's shared memory (E*(8M+4) + 2*n_nodes <= 200 KB).
+ * M in 2..4. Per-member scratch of E*(8M+4) + 2*n_nodes bytes lives in shared memory up to 200 KB; larger opt-graphs need
+ * a device workspace of pgm_fit_neighbours_workspace_bytes(...) bytes, 16-byte aligned (0 when shared memory suffices:
+ * pass NULL then; a non-NULL workspace of n * scratch bytes is always used, which is how the tests reach that variant).
  */
+size_t pgm_fit_neighbours_workspace_bytes(int n_nodes, int M, int E, int n);
 int pgm_fit_neighbours_f64(const double *objs, int n_nodes, int M, const int32_t *parent, int E, const double *edge_w,
                            const int32_t *node_ids, int n, int cap_threshold, int32_t *klen, int32_t *steps,
-                           int32_t *edge_idx, void *stream);
+                           int32_t *edge_idx, void *workspace, size_t workspace_bytes, void *stream);
 int pgm_fit_gather_f64(const int32_t *edge_idx, const int32_t *klen, int n, int E, int M, const int32_t *parent,
                        const double *edge_w, const double *edge_dy, int Kmax, double *x, double *y, double *ub,
                        int32_t *klen_f, int32_t *source, void *stream);

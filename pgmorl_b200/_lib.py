@@ -44,7 +44,8 @@ SIGNATURES = {
     "pgm_ppo_update_f32": (_I, [_P, _P, _P, _P, _P, _P, _Z, _P, _P, _P, _Z, _P, _P, _P, _I, _I, _I,
                                 C.POINTER(PpoHyper), _P, _P, _Z, _I, _I, _I, _I, _I, _I, _P]),
     "pgm_fit_hyperbolic_f64": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "pgm_fit_neighbours_f64": (_I, [_P, _I, _I, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "pgm_fit_neighbours_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "pgm_fit_neighbours_f64": (_I, [_P, _I, _I, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "pgm_fit_gather_f64": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "pgm_ep_filter_f64": (_I, [_P, _I, _I, _P, _P, _P]),
     "pgm_front_metrics_f64": (_I, [_P, _I, _I, _P, _P, _Z, _P]),

@@ -49,16 +49,20 @@ __device__ __forceinline__ int block_min(int v, int *scratch) {
     return t;
 }
 
-template <int M>
+// GS = false: the per-member scratch (successor weights and ids of the listed edges, first-near step of every node) lives
+// in dynamic shared memory; GS = true (opt-graphs beyond ~200 KB of scratch): in a global workspace slice per CTA.
+template <int M, bool GS>
 __global__ void __launch_bounds__(K4I_THREADS) k4_neighbours_kernel(const double *__restrict__ objs, int n_nodes,
                                                                     const int32_t *__restrict__ parent, int E,
                                                                     const double *__restrict__ edge_w,
                                                                     const int32_t *__restrict__ node_ids, int cap_threshold,
                                                                     int s_inf, int s_cap,
                                                                     int32_t *__restrict__ klen, int32_t *__restrict__ steps,
-                                                                    int32_t *__restrict__ edge_idx) {
+                                                                    int32_t *__restrict__ edge_idx, unsigned char *gscratch,
+                                                                    size_t scratch_per_cta) {
     extern __shared__ __align__(16) unsigned char k4i_smem[];
-    double *wl = reinterpret_cast<double *>(k4i_smem);                       // [E][M] successor weights of the listed edges
+    unsigned char *member_scratch = GS ? gscratch + (size_t)blockIdx.x * scratch_per_cta : k4i_smem;
+    double *wl = reinterpret_cast<double *>(member_scratch);                        // [E][M] successor weights of the listed edges
     int *e_list = reinterpret_cast<int *>(wl + (size_t)E * M);               // [E]
     unsigned short *s_node = reinterpret_cast<unsigned short *>(e_list + E); // [n_nodes]
     __shared__ int scratch[K4I_THREADS / 32 + 1];
@@ -183,33 +187,57 @@ __global__ void k4_gather_kernel(const int32_t *__restrict__ edge_idx, const int
     }
 }
 
+constexpr size_t K4I_SMEM_LIMIT = 200 * 1024;
+static size_t k4i_scratch_bytes(int n_nodes, int M, int E) {
+    const size_t b = (size_t)E * M * sizeof(double) + (size_t)E * sizeof(int) + (size_t)n_nodes * sizeof(unsigned short);
+    return (b + 15) & ~(size_t)15;
+}
+
 }  // namespace pgm
 
 using namespace pgm;
 
+extern "C" size_t pgm_fit_neighbours_workspace_bytes(int n_nodes, int M, int E, int n) {
+    const size_t per = k4i_scratch_bytes(n_nodes, M, E);
+    return per <= K4I_SMEM_LIMIT ? 0 : per * (size_t)(n > 0 ? n : 0);
+}
+
 extern "C" int pgm_fit_neighbours_f64(const double *objs, int n_nodes, int M, const int32_t *parent, int E,
                                       const double *edge_w, const int32_t *node_ids, int n, int cap_threshold,
-                                      int32_t *klen, int32_t *steps, int32_t *edge_idx, void *stream) {
+                                      int32_t *klen, int32_t *steps, int32_t *edge_idx, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
     PGM_REQUIRE(objs && node_ids && klen && steps, "pgm_fit_neighbours_f64: null pointer");
     PGM_REQUIRE(E == 0 || (parent && edge_w && edge_idx), "pgm_fit_neighbours_f64: null edge arrays with E=%d", E);
     PGM_REQUIRE(M >= 2 && M <= 4, "pgm_fit_neighbours_f64: M=%d objectives not in 2..4", M);
     PGM_REQUIRE(n >= 0 && n_nodes >= 1 && E >= 0, "pgm_fit_neighbours_f64: bad sizes n=%d nodes=%d E=%d", n, n_nodes, E);
     if (n == 0) return PGM_OK;
-    const size_t smem = (size_t)E * M * sizeof(double) + (size_t)E * sizeof(int) + (((size_t)n_nodes * sizeof(unsigned short) + 15) & ~(size_t)15);
+    const size_t per = k4i_scratch_bytes(n_nodes, M, E);
+    const bool gs = per > K4I_SMEM_LIMIT || workspace != nullptr;      // a workspace, when given, is used
+    if (gs) {
+        PGM_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "pgm_fit_neighbours_f64: this opt-graph (%d nodes, %d edges) needs a 16-byte aligned workspace", n_nodes, E);
+        if (workspace_bytes < per * (size_t)n) {
+            set_error("pgm_fit_neighbours_f64: workspace too small: need %zu, got %zu", per * (size_t)n, workspace_bytes);
+            return PGM_ERR_WORKSPACE;
+        }
+    }
     int s_inf = 0, s_cap = 0;
     for (double thr = 0.1; !std::isinf(thr); thr *= 2.0) ++s_inf;
     for (double thr = 0.1; !(thr >= 1.0); thr *= 2.0) ++s_cap;
-    PGM_REQUIRE(smem <= 200 * 1024, "pgm_fit_neighbours_f64: opt-graph too large for shared memory (%d nodes, %d edges)", n_nodes, E);
-    auto launch = [&](auto kern) -> int {
-        PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto launch = [&](auto kern, size_t smem) -> int {
+        if (smem) PGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n, K4I_THREADS, smem, (cudaStream_t)stream>>>(objs, n_nodes, parent, E, edge_w, node_ids, cap_threshold, s_inf, s_cap,
-                                                              klen, steps, edge_idx);
+                                                              klen, steps, edge_idx, (unsigned char *)workspace, per);
         PGM_CUDA(cudaGetLastError());
         return PGM_OK;
     };
-    if (M == 2) return launch(k4_neighbours_kernel<2>);
-    if (M == 3) return launch(k4_neighbours_kernel<3>);
-    return launch(k4_neighbours_kernel<4>);
+    if (gs) {
+        if (M == 2) return launch(k4_neighbours_kernel<2, true>, 0);
+        if (M == 3) return launch(k4_neighbours_kernel<3, true>, 0);
+        return launch(k4_neighbours_kernel<4, true>, 0);
+    }
+    if (M == 2) return launch(k4_neighbours_kernel<2, false>, per);
+    if (M == 3) return launch(k4_neighbours_kernel<3, false>, per);
+    return launch(k4_neighbours_kernel<4, false>, per);
 }
 
 extern "C" int pgm_fit_gather_f64(const int32_t *edge_idx, const int32_t *klen, int n, int E, int M, const int32_t *parent,

@@ -245,7 +245,7 @@ def fit_hyperbolic_launch(xs, ys, ws, ubs):
     return dict(inputs=(d, kl, ub), res=res, F=F)     # inputs kept alive until collect
 
 
-def fit_inputs_launch(objs, parent, edge_w, edge_dy, node_ids, cap_threshold):
+def fit_inputs_launch(objs, parent, edge_w, edge_dy, node_ids, cap_threshold, force_global_scratch=False):
     """K4 front-end (csrc/k4_inputs.cu): neighbourhood search + widening for every member, then the gather of the
     K4 inputs. objs [n_nodes,M], edges ordered by source node then successor: parent [E], edge_w / edge_dy [E,M];
     node_ids [n]. Returns a dict: device `pack` [3,F,Kmax] (x, y filled; w left for the caller), `ub` [F,4], `klen_f` [F];
@@ -267,9 +267,13 @@ def fit_inputs_launch(objs, parent, edge_w, edge_dy, node_ids, cap_threshold):
     d_parent, d_nodes = d_i[:E], d_i[E:]
     ks = torch.empty(2, n, dtype=torch.int32, device=dev)
     edge_idx = torch.empty(n * max(E, 1), dtype=torch.int32, device=dev)
+    nb = lib().pgm_fit_neighbours_workspace_bytes(n_nodes, M, E, n)       # 0 unless the graph outgrows shared memory
+    if force_global_scratch:
+        nb = max(nb, n * ((E * (8 * M + 4) + 2 * n_nodes + 15) // 16 * 16))
+    ws, (wp, wn) = _ws(nb, dev) if nb else (None, (None, 0))
     check(lib().pgm_fit_neighbours_f64(ptr(d_objs), n_nodes, M, ptr(d_parent) if E else None, E, ptr(d_ew) if E else None,
                                        ptr(d_nodes), n, int(bool(cap_threshold)), ptr(ks[0]), ptr(ks[1]), ptr(edge_idx),
-                                       _stream()))
+                                       wp, wn, _stream()))
     ks_h = ks.cpu().numpy()
     Kmax = max(int(ks_h[0].max()), 1)
     F = n * M
@@ -281,7 +285,7 @@ def fit_inputs_launch(objs, parent, edge_w, edge_dy, node_ids, cap_threshold):
                                    ptr(d_ew) if E else None, ptr(d_dy) if E else None, Kmax, ptr(pack[0]), ptr(pack[1]),
                                    ptr(ub), ptr(klen_f), ptr(source), _stream()))
     return dict(n=n, M=M, Kmax=Kmax, pack=pack, ub=ub, klen_f=klen_f, klen=ks_h[0], steps=ks_h[1],
-                source=source.cpu().numpy(), keep=(d_f, d_i, edge_idx, ks))
+                source=source.cpu().numpy(), keep=(d_f, d_i, edge_idx, ks, ws))
 
 
 def fit_hyperbolic_launch_packed(front, coef):

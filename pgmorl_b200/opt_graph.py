@@ -43,7 +43,7 @@ class OptGraph:
         n = len(self.objs)
         if n == 0:
             return np.zeros((0, 0)), np.zeros((0, 0)), np.zeros((0, 0)), np.zeros(0, dtype=np.int64)
-        if self._flat is None or self._flat_n > n:
+        if getattr(self, '_flat', None) is None or self._flat_n > n:      # (graphs unpickled from before the cache existed)
             self._flat, self._flat_n = None, 0
         M = len(np.asarray(self.objs[0]).reshape(-1))
         if self._flat is None or self._flat[0].shape[0] < n:

@@ -300,14 +300,15 @@ def test_fork_scoring_variant_matches_the_fork_reference():
     assert exact == gens            # measured on a B200: 5/5 generations identical
 
 
-def _front_end_vs_oracle(graph, ids, M, cap):
+def _front_end_vs_oracle(graph, ids, M, cap, force_global_scratch=False):
     """csrc/k4_inputs.cu (through kernels.fit_inputs_launch) + prediction.gaussian_weights against the scalar oracle
     scan of every member: same edge lists, widening steps, x / y / w / ub, bit for bit."""
     from pgmorl_b200 import kernels as K
     from pgmorl_b200.prediction import GraphView, gaussian_weights
     view, ref = GraphView(graph), so.GraphArrays(graph)
     ids = np.asarray(ids, dtype=np.int64)
-    front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, ids, cap)
+    front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, ids, cap,
+                                force_global_scratch=force_global_scratch)
     coef = gaussian_weights(view, ids, front["steps"], front["source"])
     pack, ub = front["pack"].cpu().numpy(), front["ub"].cpu().numpy()
     klen_f = front["klen_f"].cpu().numpy()
@@ -384,6 +385,12 @@ def test_fit_input_kernels_edge_cases():
             _front_end_vs_oracle(g, [0] + members, M, cap)
             g, members = family_graph(M, 2, 400, 0.01)                     # 800 edges: several scan passes per step
             _front_end_vs_oracle(g, members[::37], M, cap)
+            _front_end_vs_oracle(g, members[::53], M, cap, force_global_scratch=True)     # per-member scratch in global memory
+    # an opt-graph beyond the shared-memory scratch (13 000 nodes): the library switches to the global workspace by itself
+    from pgmorl_b200._lib import lib
+    g, members = family_graph(2, 1000, 12, 0.002)
+    assert lib().pgm_fit_neighbours_workspace_bytes(len(g.objs), 2, 12000, 7) > 0
+    _front_end_vs_oracle(g, members[::1801], 2, False)
     g = OptGraph()                                                         # roots only: no edge at all
     for r in range(3):
         g.insert(np.ones(2) / 2, rng.uniform(10, 20, 2), -1)
