@@ -5,6 +5,7 @@ import ctypes as C
 import torch
 
 from ._lib import PpoHyper, check, lib, ptr
+from ._nvtx import rng as _nvtx
 from .layout import NetDims
 
 ACT_SAMPLE, ACT_DETERMINISTIC, ACT_EVALUATE = 0, 1, 2
@@ -204,9 +205,10 @@ def select_greedy(ep, cand, alpha, num_tasks):
     nfront = torch.zeros(1, dtype=torch.int32, device=dev)
     nb = lib().pgm_select_workspace_bytes(E, C, M, num_tasks)
     ws, (wp, wn) = _ws(nb, dev)
-    check(lib().pgm_select_greedy_f64(ptr(ep_d), E, ptr(cand_d), C, M, float(alpha), num_tasks, ptr(best), ptr(hv),
-                                      ptr(sp), ptr(front), ptr(nfront), wp, wn, _stream()))
-    nf = int(nfront.item())
+    with _nvtx("selection.k5_greedy"):
+        check(lib().pgm_select_greedy_f64(ptr(ep_d), E, ptr(cand_d), C, M, float(alpha), num_tasks, ptr(best), ptr(hv),
+                                          ptr(sp), ptr(front), ptr(nfront), wp, wn, _stream()))
+        nf = int(nfront.item())
     return (best.cpu().numpy().astype(np.int64), hv[:, :C].cpu().numpy(), sp[:, :C].cpu().numpy(),
             front[:nf].cpu().numpy())
 
