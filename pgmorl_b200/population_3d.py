@@ -146,7 +146,10 @@ class Population:
         step = args.delta_weight / 2.0
         # a grid point within 1e-3 (L2) of a vector is the lattice point nearest to it (spacing >> 2e-3): look that one up
         # and run the reference's exact test on it alone
-        lattice = {tuple(key): i for i, key in enumerate(np.rint(grid_arr / step).astype(np.int64).tolist())}
+        if getattr(self, '_lattice_of', None) is not grid_arr:
+            self._lattice = {tuple(key): i for i, key in enumerate(np.rint(grid_arr / step).astype(np.int64).tolist())}
+            self._lattice_of = grid_arr
+        lattice = self._lattice
         assert step > 4e-3 and len(lattice) == G
 
         def coincident(vectors):
@@ -174,17 +177,21 @@ class Population:
         cosine = rowdot(center[:, None, :], grid_arr[None, :, :]) / rownorm(center)[:, None] / grid_norm[None, :]
         angle = np.arccos(np.minimum(np.maximum(cosine, -1.0), 1.0))
         eligible = (angle < np.pi / 4.0) & ~excluded
-        tests = np.ones((n, num_weights + 1, M))
-        counts = np.zeros(n, dtype=np.int64)
+        # one np.random.shuffle per member, in member order: the reference's RNG stream (np.random.permutation(G) is
+        # shuffle(arange(G)): same dtype and length as the reference's list-built array)
+        orders = np.empty((n, G), dtype=np.int64)
         for b in range(n):
-            k = 0
-            if has_center[b]:
-                tests[b, 0] = center[b]; k = 1
-            order = np.arange(G)                       # same dtype and length as the reference's list-built array
-            np.random.shuffle(order)
-            picks = order[eligible[b][order]][:max(num_weights - k, 0)]
-            tests[b, k:k + len(picks)] = grid_arr[picks]
-            counts[b] = k + len(picks)
+            orders[b] = np.random.permutation(G)
+        # ... then, for all members at once, the first eligible grid weights in shuffled order up to the cap
+        elig = np.take_along_axis(eligible, orders, axis=1)
+        nth = np.cumsum(elig, axis=1)                                # 1-based rank among the eligible ones
+        k0 = has_center.astype(np.int64)
+        take = elig & (nth <= (num_weights - k0)[:, None])
+        tests = np.ones((n, num_weights + 1, M))
+        tests[has_center, 0] = center[has_center]
+        rows, cols = np.nonzero(take)                                # row-major: shuffled order within each member
+        tests[rows, k0[rows] + nth[rows, cols] - 1] = grid_arr[orders[rows, cols]]
+        counts = k0 + take.sum(axis=1)
         return tests, counts
 
     def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
