@@ -236,8 +236,10 @@ class GenerationBoundary:
                     prev = self.graph.insert(w.copy(), o.copy(), prev)
                     s.optgraph_id = prev
                     offspring.append(s)
-        self.ep.update(all_samples)
         self.population.update(offspring)
+        if not self.cpu:
+            self.population.prefetch_fits(self.args, self.graph)      # the K4 chain runs under the archive update
+        self.ep.update(all_samples)
         t2 = time.perf_counter()
         np.random.seed(1000 + self.gen)
         if self.cpu:

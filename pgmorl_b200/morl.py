@@ -231,8 +231,12 @@ def run(args, device="cuda", cluster=0, save=True):
                     offspring_batch.append(sample)
             last_offspring_batch[task_id] = offsprings[-1]
 
-        ep.update(all_sample_batch)
+        # (the reference updates the archive first; the two updates are independent, and with the population done first
+        # the model fits of the selection can already run on the device while the archive is filtered)
         population.update(offspring_batch)
+        if args.selection_method == 'prediction-guided':
+            population.prefetch_fits(args, opt_graph)
+        ep.update(all_sample_batch)
 
         t0 = time.time()
         elite_batch, scalarization_batch, predicted = select_tasks(args, population, ep, opt_graph, template, iteration,

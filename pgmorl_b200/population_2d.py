@@ -9,7 +9,7 @@ from copy import deepcopy
 import numpy as np
 
 from . import kernels as K
-from .prediction import Candidates, predict_candidates
+from .prediction import Candidates, predict_candidates, prefetch
 from .utils import get_ep_indices, norm2, rownorm
 
 
@@ -135,18 +135,30 @@ class Population:
         tests[np.arange(num_weights)[None, :] >= counts[:, None]] = 1.0
         return tests, counts
 
+    def prefetch_fits(self, args, opt_graph):
+        """Optional: launch the model fits of the current population now (after `update`), so that they run under whatever
+        the caller does before `prediction_guided_selection` (archive update, logging); results are identical."""
+        self._pending = prefetch(opt_graph, self.sample_batch, args.obj_num, bool(getattr(args, 'fork_scoring', False)))
+
     def prediction_guided_selection(self, args, iteration, ep, opt_graph, scalarization_template):
         """Returns (elite_batch, scalarization_batch, predicted_offspring_objs) (population_2d.py:229-304)."""
         N = args.num_tasks
         # ---- prediction: candidates = (sample, weight) pairs with their predicted objectives
         # the fits need only the opt-graph: launch all of them (K4) first and enumerate the test weights while they run
         fork = bool(getattr(args, 'fork_scoring', False))     # the WorkingMorl/ copy's variant of this routine
+        prep = {}
+
+        def while_fitting():            # host work that does not need the fits, done while they run
+            prep['virtual_ep'] = np.array([np.asarray(s.objs, dtype=np.float64) for s in ep.sample_batch]).reshape(-1, args.obj_num)
+            prep['scalarizations'] = [deepcopy(scalarization_template) for _ in range(N)]
+        pending, self._pending = getattr(self, '_pending', None), None
         tests, counts, pred, self.last_fits = predict_candidates(
             opt_graph, self.sample_batch, lambda view, ids: self._test_weights_batch(view, ids, args.num_weight_candidates),
-            args.obj_num, cap_threshold=fork, max_tests=args.num_weight_candidates, zero_if_degenerate=fork)
+            args.obj_num, cap_threshold=fork, max_tests=args.num_weight_candidates, zero_if_degenerate=fork,
+            pending=pending, while_fitting=while_fitting)
         candidates = Candidates(self.sample_batch, tests, counts, pred)
         # ---- optimisation: greedy knapsack on the device
-        virtual_ep = np.array([np.asarray(s.objs, dtype=np.float64) for s in ep.sample_batch]).reshape(-1, args.obj_num)
+        virtual_ep = prep['virtual_ep']
         elite_batch, scalarization_batch, predicted_offspring_objs = [], [], []
         if len(candidates) == 0:
             print('Too few candidates')
@@ -162,7 +174,7 @@ class Population:
                 break
             c = candidates[int(best_id)]
             elite_batch.append(c['sample'])
-            scalarization = deepcopy(scalarization_template)
+            scalarization = prep['scalarizations'][len(scalarization_batch)]
             scalarization.update_weights(c['weight'] / np.sum(c['weight']))
             scalarization_batch.append(scalarization)
             predicted_offspring_objs.append(deepcopy(c['prediction']))

@@ -56,6 +56,21 @@ def model(x, A, a, b, c):
     return A * (np.exp(a * (x - b)) - 1) / (np.exp(a * (x - b)) + 1) + c
 
 
+_FIT_STREAMS = {}
+
+
+def fit_stream():
+    """The fit chain (front-end kernels, K4 and the copies around them) runs on its own CUDA stream: a launch issued early
+    (`prefetch`) is then not held up by -- and does not hold up -- the small kernels and synchronising copies the caller
+    issues on the current stream meanwhile (the archive's dominance filter). Inputs come from and results go to the host
+    inside this stream, so there is no device-side dependency on any other stream."""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _FIT_STREAMS:
+        _FIT_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _FIT_STREAMS[dev]
+
+
 class FitRecord(dict):
     """Record of the most recent K4 launch (diagnostics / tests): theta, status, nfev, cost [F] as numpy arrays;
     the ragged inputs x, y, w (lists of 1-D arrays) and ub are copied back from the device on first access."""
@@ -75,20 +90,25 @@ class FitRecord(dict):
 def launch_fits(opt_graph, node_ids, obj_num, cap_threshold):
     """Build the training data of every node's model and launch all n x M fits (K4) without waiting for them.
     Returns a handle for `finish_predictions`; the caller may do host work that does not need the fits meanwhile."""
-    with _nvtx("selection.fit_inputs"):
-        view = GraphView(opt_graph)
-        node_ids = np.asarray(list(node_ids), dtype=np.int64)
-        front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, node_ids, cap_threshold)
-        coef = gaussian_weights(view, node_ids, front["steps"], front["source"]) if len(node_ids) else np.zeros((0, 1))
-    with _nvtx("selection.k4_fits"):
-        fits = K.fit_hyperbolic_launch_packed(front, coef)                  # all fits in one launch
-    return dict(view=view, node_ids=node_ids, obj_num=obj_num, front=front, fits=fits)
+    import torch
+    with torch.cuda.stream(fit_stream()):
+        with _nvtx("selection.fit_inputs"):
+            view = GraphView(opt_graph)
+            node_ids = np.asarray(list(node_ids), dtype=np.int64)
+            front = K.fit_inputs_launch(view.objs, view.parent, view.edge_w, view.edge_dy, node_ids, cap_threshold)
+            coef = gaussian_weights(view, node_ids, front["steps"], front["source"]) if len(node_ids) else np.zeros((0, 1))
+        with _nvtx("selection.k4_fits"):
+            fits = K.fit_hyperbolic_launch_packed(front, coef)                  # all fits in one launch
+    return dict(view=view, node_ids=node_ids, obj_num=obj_num, front=front, fits=fits, n_nodes=len(view.objs),
+                cap_threshold=bool(cap_threshold))
 
 
 def _ragged_inputs(handle, keep):
     """x, y, w, ub of the kept fits as the lists the scalar code used to hold (device -> host copy of the pack)."""
+    import torch
     front = handle["front"]
-    pack, ub, klen = front["pack"].cpu().numpy(), front["ub"].cpu().numpy(), front["klen"]
+    with torch.cuda.stream(fit_stream()):
+        pack, ub, klen = front["pack"].cpu().numpy(), front["ub"].cpu().numpy(), front["klen"]
     M = handle["obj_num"]
     out = dict(x=[], y=[], w=[], ub=[])
     for f in keep:
@@ -104,7 +124,9 @@ def finish_predictions(handle, tests, counts, zero_if_degenerate=False):
     contributes neither predictions nor fit records (the reference never fits a sample without test weights).
     Returns (pred [n, T, M], fit record). `zero_if_degenerate`: the fork copy's fallback
     (WorkingMorl/morl/population_2d.py:112-117)."""
-    theta, status, nfev, cost = K.fit_hyperbolic_collect(handle["fits"])
+    import torch
+    with torch.cuda.stream(fit_stream()):
+        theta, status, nfev, cost = K.fit_hyperbolic_collect(handle["fits"])
     view, M = handle["view"], handle["obj_num"]
     n = len(handle["node_ids"])
     counts = np.asarray(counts, dtype=np.int64)
@@ -116,7 +138,8 @@ def finish_predictions(handle, tests, counts, zero_if_degenerate=False):
     if zero_if_degenerate:
         # the fork copy predicts no change without usable data (:112-117): fewer than two distinct training weights
         front = handle["front"]
-        x = front["pack"][0].cpu().numpy()
+        with torch.cuda.stream(fit_stream()):
+            x = front["pack"][0].cpu().numpy()
         for f in range(n * M):
             k = int(front["klen"][f // M])
             if k == 0 or len(np.unique(x[f, :k])) < 2:
@@ -128,8 +151,30 @@ def finish_predictions(handle, tests, counts, zero_if_degenerate=False):
     return pred, record
 
 
+def _my_members(n):
+    """Indices of the population members whose fits this rank computes (all of them in a single process)."""
+    from . import dist as pdist
+    rank, W = pdist.world()
+    return np.arange(n) if (W == 1 or n < W) else np.arange(rank, n, W)
+
+
+def prefetch(opt_graph, samples, obj_num, cap_threshold):
+    """Launch this rank's share of the fits of `samples` NOW and return the handle; `predict_candidates(..., pending=...)`
+    picks it up if population and opt-graph are still the ones it was launched for. Lets the caller put the fit chain
+    (milliseconds of dependent FP64 latency) under host work that does not need it, e.g. the archive update."""
+    ids = np.array([s.optgraph_id for s in samples], dtype=np.int64)
+    pending = launch_fits(opt_graph, ids[_my_members(len(ids))], obj_num, cap_threshold)
+    pending["all_ids"] = ids
+    return pending
+
+
+def _usable(pending, opt_graph, ids, cap_threshold):
+    return (pending is not None and pending["n_nodes"] == len(opt_graph.objs) and pending["cap_threshold"] == bool(cap_threshold)
+            and np.array_equal(pending["all_ids"], ids))
+
+
 def predict_candidates(opt_graph, samples, make_tests, obj_num, cap_threshold, max_tests, zero_if_degenerate=False,
-                       tests_in_lockstep=False):
+                       tests_in_lockstep=False, pending=None, while_fitting=None):
     """Test weights and predicted objectives of every population member.
     `make_tests(view, node_ids) -> (tests [n, max_tests, M], counts [n])` enumerates the test weights of the given
     members (rows past counts[i] are padding, any finite positive numbers).
@@ -141,26 +186,32 @@ def predict_candidates(opt_graph, samples, make_tests, obj_num, cap_threshold, m
     one all-gather of a padded float64 table (count, test weights, predictions per member) gives every rank the identical
     candidate set -- the per-rank cost of the selection front-end stays flat as tasks and GPUs grow together.
     `tests_in_lockstep`: the test weights consume numpy's global RNG (3 objectives), so every rank enumerates them for
-    every member to keep the streams identical; only fits and predictions are split."""
+    every member to keep the streams identical; only fits and predictions are split.
+    `pending`: a handle from `prefetch` (used if it was launched for this population and opt-graph);
+    `while_fitting`: host work of the caller to run once the test weights are enumerated and before the fits are awaited."""
     from . import dist as pdist
     rank, W = pdist.world()
     n = len(samples)
     ids = np.array([s.optgraph_id for s in samples], dtype=np.int64)
     M = obj_num
+    mine = _my_members(n)
+    if not _usable(pending, opt_graph, ids, cap_threshold):
+        pending = launch_fits(opt_graph, ids[mine], obj_num, cap_threshold)
     if W == 1 or n < W:
-        pending = launch_fits(opt_graph, ids, obj_num, cap_threshold)
         with _nvtx("selection.test_weights"):
             tests, counts = make_tests(pending["view"], ids)
+        if while_fitting is not None:
+            while_fitting()
         pred, fits = finish_predictions(pending, tests, counts, zero_if_degenerate=zero_if_degenerate)
         return tests, counts, pred, fits
-    mine = np.arange(rank, n, W)
-    pending = launch_fits(opt_graph, ids[mine], obj_num, cap_threshold)
     with _nvtx("selection.test_weights"):
         if tests_in_lockstep:
             tests, counts = make_tests(pending["view"], ids)
             my_tests, my_counts = tests[mine], counts[mine]
         else:
             my_tests, my_counts = make_tests(pending["view"], ids[mine])
+    if while_fitting is not None:
+        while_fitting()
     my_pred, fits = finish_predictions(pending, my_tests, my_counts, zero_if_degenerate=zero_if_degenerate)
     T = max_tests
     rows = np.zeros((len(mine), 1 + 2 * T * M))
