@@ -322,8 +322,8 @@ def cpu_reference_leg(d, P_total, T, N, E, B, gamma, steps, warmup, boundary=Tru
 
 def selection_leg(cpu=True):
     """Secondary BASELINE metric: prediction-guided selection ms/generation on the recorded synthetic histories
-    (tests/golden/selection_{2d,3d}.npz, last generation): product path = host candidate generation + K4 fits + K5
-    greedy loop; CPU = oracle port (scipy least_squares + python scoring; 3-D scoring timed on ONE of the 15 rounds
+    (tests/golden/selection_{2d,3d}.npz, last generation): product path = K4 front-end kernels + K4 fits (+ the host's
+    test-weight enumeration under them) + K5 greedy loop; CPU = oracle port (scipy least_squares + python scoring; 3-D scoring timed on ONE of the 15 rounds
     and scaled, stated in `cpu_sample`)."""
     import torch
     from helpers import rebuild_selection_state
