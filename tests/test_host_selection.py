@@ -143,3 +143,41 @@ def test_rowwise_helpers_give_the_scalar_bits():
     assert np.array_equal(np.exp(-utils.pow2(x) / 2.0), np.array([np.exp(-(float(v) ** 2) / 2.0) for v in x]))
     # both implementations behind the switch agree with each other
     assert np.array_equal(utils._rowdot_loop(a, b), utils.rowdot(a, b)) and np.array_equal(utils._pow2_loop(x), utils.pow2(x))
+
+
+def test_opt_graph_flat_cache_and_graph_view_stay_in_step_with_the_lists():
+    """OptGraph.flat() mirrors the node lists incrementally (the selection front-end reads it every generation);
+    GraphView's edge order is the reference's walk over opt_graph.succ."""
+    from pgmorl_b200.opt_graph import OptGraph
+    rng = np.random.RandomState(0)
+    g = OptGraph()
+    for step in range(5):
+        for _ in range(40):                                  # grows past the initial capacity: the arrays are re-allocated
+            n = len(g.objs)
+            prev = -1 if n == 0 or rng.rand() < 0.2 else int(rng.randint(n))
+            g.insert(rng.dirichlet(np.ones(3)), rng.uniform(1, 9, 3), prev)
+        W, O, D, P = g.flat()
+        assert np.array_equal(O, np.array(g.objs)) and np.array_equal(D, np.array(g.delta_objs))
+        assert np.array_equal(W, np.array(g.weights)) and P.tolist() == g.prev
+        view, ref = GraphView(g), so.GraphArrays(g)
+        for a in ("objs", "parent", "child", "edge_w", "edge_dy"):
+            assert np.array_equal(getattr(view, a), getattr(ref, a)), a
+        nodes = rng.randint(len(g.objs), size=7)
+        member, succ = view.successors_of(nodes)
+        assert succ.tolist() == [s for k in nodes for s in g.succ[k]]
+        assert member.tolist() == [i for i, k in enumerate(nodes) for _ in g.succ[k]]
+
+
+def test_candidates_container_and_lazy_fit_record():
+    from pgmorl_b200.prediction import Candidates, FitRecord
+    tests = np.arange(2 * 3 * 2, dtype=np.float64).reshape(2, 3, 2)
+    pred = tests + 100.0
+    c = Candidates(["a", "b"], tests, [2, 0], pred)
+    assert len(c) == 2 and c[1]["sample"] == "a" and np.array_equal(c[1]["weight"], tests[0, 1])
+    assert np.array_equal(c.prediction, pred[0, :2]) and [x["sample"] for x in c] == ["a", "a"]
+    calls = []
+    rec = FitRecord(lambda: calls.append(1) or dict(x=[1], y=[2], w=[3], ub=[4]), theta=np.zeros((1, 4)))
+    assert "x" not in rec and rec["theta"].shape == (1, 4) and not calls
+    assert rec["x"] == [1] and rec["ub"] == [4] and calls == [1]          # one device -> host copy, on first access
+    with pytest.raises(KeyError):
+        rec["nope"]
