@@ -96,7 +96,9 @@ def _worker(rank, world, port, out_dir):
 
 def test_sharded_candidates_equal_single_process(tmp_path, monkeypatch):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    import torch
     _install_oracle_stubs(monkeypatch.setattr)
+    monkeypatch.setattr(torch, "set_default_dtype", lambda d: None)   # (the workers switch to float64 like the reference; not needed here)
     for name, M in (("selection_2d.npz", 2), ("selection_3d.npz", 3)):
         tests, counts, pred = _candidates(name, M)                    # single process (no process group)
         valid = np.arange(tests.shape[1])[None, :] < counts[:, None]
