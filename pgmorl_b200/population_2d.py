@@ -35,6 +35,9 @@ class Population:
         buffer_id = int(np.arccos(np.clip(f[1] / dist, -1.0, 1.0)) // self.dtheta)
         if buffer_id < 0 or buffer_id >= self.pbuffer_num:
             return False
+        return self._insert_sorted(index, dist, buffer_id)
+
+    def _insert_sorted(self, index, dist, buffer_id):
         ids, dists = self.pbuffers[buffer_id], self.pbuffer_dist[buffer_id]
         pos = next((i for i, dcur in enumerate(dists) if dcur < dist), None)
         if pos is not None:
@@ -51,8 +54,16 @@ class Population:
         everyone = self.sample_batch + sample_batch
         self.pbuffers = [[] for _ in range(self.pbuffer_num)]
         self.pbuffer_dist = [[] for _ in range(self.pbuffer_num)]
-        for i, sample in enumerate(everyone):
-            self.insert_pbuffer(i, sample.objs)
+        if everyone:
+            # distance and angular buffer of every sample at once (the expressions of insert_pbuffer, element by element,
+            # with the bits of the scalar calls: utils.rownorm); the insertions themselves stay sequential, in order
+            F = np.array([np.asarray(s.objs, dtype=np.float64) for s in everyone]).reshape(len(everyone), -1) - self.z_min
+            with np.errstate(all="ignore"):
+                dist = rownorm(F)
+                bid = np.arccos(np.clip(F[:, 1] / dist, -1.0, 1.0)) // self.dtheta
+            ok = (F.min(axis=1) >= 1e-7) & (bid >= 0) & (bid < self.pbuffer_num)
+            for i in np.nonzero(ok)[0].tolist():
+                self._insert_sorted(i, float(dist[i]), int(bid[i]))
         self.sample_batch = [everyone[i] for buf in self.pbuffers for i in buf]
 
     # ------------------------------------------------------------------ metrics (device)
