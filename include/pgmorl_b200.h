@@ -232,7 +232,10 @@ int pgm_front_metrics_f64(const double *pts, int n, int M, double *out, void *wo
  * Per round r < num_tasks: hv[r,c], sparsity[r,c] of EP_r + {cand c} for unmasked c (0 for masked),
  * best_ids[r] = first argmax of hv - alpha*sparsity (or -1 when no candidate is left, then stops);
  * EP_{r+1} = EP_r with the winner's prediction folded in. n_front [1] out: size of the final
- * virtual front, written to front_out [E+num_tasks, M] (both optional / may be NULL). */
+ * virtual front, written to front_out [E+num_tasks, M] (both optional / may be NULL).
+ * 3 objectives: every candidate of a round is scored on top of the round's shared base front (sorted lists, slice areas
+ * and the head of the hypervolume sum are built once per round in the workspace); the per-candidate scratch of
+ * 97 * (E + num_tasks + 1) bytes must fit 200 KB of shared memory (archive fronts up to ~2 100 points), else an error. */
 size_t pgm_select_workspace_bytes(int E, int C, int M, int num_tasks);
 int pgm_select_greedy_f64(const double *ep, int E, const double *cand, int C, int M, double alpha,
                           int num_tasks, int32_t *best_ids, double *hv, double *sparsity,
